@@ -1,0 +1,193 @@
+"""ctypes binding of the C ABI (include/lexicmap_gpu.h) + the host-side mirror of the reference's search interface."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblexicmap_gpu.so")
+TSV_HEADER = "query\tqlen\thits\tsgenome\tsseqid\tqcovGnm\tcls\thsp\tqcovHSP\talenHSP\tpident\tgaps\tqstart\tqend\tsstart\tsend\tsstr\tslen\tevalue\tbitscore"  # search.go:426
+
+
+class Params(C.Structure):  # lmg_params
+    _fields_ = [("min_prefix", C.c_int32), ("min_single_prefix", C.c_int32), ("top_n_genomes", C.c_int32), ("top_n_chains", C.c_int32),
+                ("max_gap", C.c_float), ("max_distance", C.c_float), ("ext_len", C.c_int32), ("ext_len2", C.c_int32),
+                ("min_qcov_genome", C.c_double), ("max_evalue", C.c_double),
+                ("align_max_gap", C.c_int32), ("align_min_len", C.c_int32), ("align_band", C.c_int32), ("output_seq", C.c_int32),
+                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double)]
+
+
+class Info(C.Structure):  # lmg_info
+    _fields_ = [("k", C.c_int32), ("masks", C.c_int32), ("chunks", C.c_int32), ("partitions", C.c_int32), ("genomes", C.c_int32), ("genome_batches", C.c_int32),
+                ("contig_interval", C.c_int32), ("mask_prefix", C.c_int32), ("anchor_prefix", C.c_int32), ("input_bases", C.c_int64),
+                ("seed_keys", C.c_uint64), ("seed_values", C.c_uint64), ("image_bytes", C.c_uint64)]
+
+
+HSP_DTYPE = np.dtype([("query", "<u4"), ("hits", "<u4"), ("genome", "<u8"), ("seq_idx", "<u4"), ("n_seqs", "<u4"), ("chunk_idx", "<u4"), ("n_chunks", "<u4"),
+                      ("seq_len", "<i4"), ("cls", "<i4"), ("hsp", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("tb", "<i4"), ("te", "<i4"), ("rc", "<i4"),
+                      ("alen", "<i4"), ("matches", "<i4"), ("gaps", "<i4"), ("score", "<i4"), ("bitscore", "<i4"), ("pad0", "<i4"),
+                      ("evalue", "<f8"), ("qcov_hsp", "<f8"), ("pident", "<f8"), ("qcov_gnm", "<f8"), ("cigar_off", "<u8"), ("cigar_len", "<u4"), ("pad", "<u4")])
+ANCHOR_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("qbegin", "<i4"), ("tbegin", "<i4"), ("len", "u1"), ("qrc", "u1"), ("trc", "u1"), ("pad", "u1")])
+CHAIN_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("score", "<f4"), ("n_seeds", "<i4"), ("q0", "<i4"), ("t0", "<i4"), ("len0", "<i4"),
+                        ("q1", "<i4"), ("t1", "<i4"), ("len1", "<i4"), ("rc", "<i4")])
+
+_lib = None
+
+
+def load_library():
+    """Load liblexicmap_gpu.so. Fails loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liblexicmap_gpu.so is missing: run `python -m lexicmap_b200.build` (needs nvcc); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.lmg_default_params.argtypes = [C.POINTER(Params)]
+    L.lmg_last_error.restype = C.c_char_p
+    L.lmg_index_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.lmg_index_info.argtypes = [vp, C.POINTER(Info)]
+    L.lmg_genome_name.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.lmg_index_close.argtypes = [vp]
+    L.lmg_search_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp)]
+    L.lmg_results_rows.argtypes = [vp, C.POINTER(vp), u64p, C.POINTER(vp), u64p]
+    L.lmg_results_seq_id.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p)]
+    L.lmg_results_free.argtypes = [vp]
+    L.lmg_last_timing.argtypes = [vp, vp, vp]
+    L.lmg_mask_batch.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, u64p]
+    L.lmg_anchor_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
+    L.lmg_chain_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
+    L.lmg_wfa_batch.argtypes = [C.c_int, vp, vp, C.c_int32, C.POINTER(vp), u64p]
+    L.lmg_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def pack_queries(seqs):
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    buf = np.frombuffer(b"".join(bs) + b"\0" * 16, dtype=np.uint8).copy()
+    return buf, off
+
+
+class Index:
+    """GPU-resident LexicMap index (NewIndexSearcher, lib-index-search.go:237)."""
+
+    def __init__(self, lmi_dir, device=0, shard=0, n_shards=1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if self.lib.lmg_index_open(os.fsencode(lmi_dir), device, shard, n_shards, C.byref(h)) != 0:
+            raise RuntimeError(self.lib.lmg_last_error().decode())
+        self.h = h
+        self.info = Info()
+        self.lib.lmg_index_info(self.h, C.byref(self.info))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lmg_index_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def default_params(self, **kw):
+        p = Params()
+        self.lib.lmg_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def _err(self):
+        raise RuntimeError(self.lib.lmg_last_error().decode())
+
+    def genome_name(self, g):
+        s = C.c_char_p()
+        self.lib.lmg_genome_name(self.h, int(g), C.byref(s))
+        return (s.value or b"").decode()
+
+    # ---- Index.Search, batched (lib-index-search.go:1191)
+    def search(self, seqs, params=None, packed=None):
+        """returns (rows: HSP_DTYPE array, seqids, cigars). `packed` = (uint8 buf, uint64 off) to skip re-packing."""
+        p = params or self.default_params()
+        buf, off = packed if packed is not None else pack_queries(seqs)
+        n = len(off) - 1
+        r = C.c_void_p()
+        if self.lib.lmg_search_batch(self.h, C.byref(p), buf.ctypes.data, off.ctypes.data, n, C.byref(r)) != 0:
+            self._err()
+        rows_p, pool_p, nr, npool = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self.lib.lmg_results_rows(r, C.byref(rows_p), C.byref(nr), C.byref(pool_p), C.byref(npool))
+        rows = np.frombuffer(C.string_at(rows_p, nr.value * HSP_DTYPE.itemsize), dtype=HSP_DTYPE).copy() if nr.value else np.zeros(0, HSP_DTYPE)
+        pool = C.string_at(pool_p, npool.value) if npool.value else b""
+        seqids = []
+        s = C.c_char_p()
+        for i in range(nr.value):
+            self.lib.lmg_results_seq_id(r, i, C.byref(s))
+            seqids.append(s.value.decode())
+        cig = [pool[int(o):int(o) + int(l)].decode() for o, l in zip(rows["cigar_off"], rows["cigar_len"])]
+        self.lib.lmg_results_free(r)
+        return rows, seqids, cig
+
+    def timing(self):
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.uint64)
+        self.lib.lmg_last_timing(self.h, ms.ctypes.data, cnt.ctypes.data)
+        return ms, cnt
+
+    def format_tsv(self, rows, seqids, qids, qlens, cigars=None):
+        """printResult (search.go:437-533): 20 columns (+cigar with -a)."""
+        out = []
+        for i, r in enumerate(rows):
+            q = int(r["query"])
+            line = "%s\t%d\t%d\t%s\t%s\t%.3f\t%d\t%d\t%.3f\t%d\t%.3f\t%d\t%d\t%d\t%d\t%d\t%s\t%d\t%.2e\t%d" % (
+                qids[q], qlens[q], r["hits"], self.genome_name(r["genome"]), seqids[i], r["qcov_gnm"], r["cls"], r["hsp"], r["qcov_hsp"], r["alen"], r["pident"], r["gaps"],
+                r["qb"] + 1, r["qe"] + 1, r["tb"] + 1, r["te"] + 1, "-" if r["rc"] else "+", r["seq_len"], r["evalue"], r["bitscore"])
+            if cigars is not None:
+                line += "\t" + cigars[i]
+            out.append(line)
+        return out
+
+    # ---- stage-wise entry points (parity tests)
+    def mask(self, seqs):
+        buf, off = pack_queries(seqs)
+        n, m = len(seqs), self.info.masks
+        kmers, nlocs, minloc = np.zeros(n * m, np.uint64), np.zeros(n * m, np.uint32), np.zeros(n * m, np.uint32)
+        suf = np.zeros(4 * n * m, np.uint64)
+        ns = C.c_uint64()
+        if self.lib.lmg_mask_batch(self.h, buf.ctypes.data, off.ctypes.data, n, kmers.ctypes.data, nlocs.ctypes.data, minloc.ctypes.data, suf.ctypes.data, n * m, C.byref(ns)) != 0:
+            self._err()
+        return kmers, nlocs, minloc, suf[:4 * ns.value].reshape(-1, 4)
+
+    def _stage(self, fn, dtype, seqs, params):
+        p = params or self.default_params()
+        buf, off = pack_queries(seqs)
+        ptr, n = C.c_void_p(), C.c_uint64()
+        if fn(self.h, C.byref(p), buf.ctypes.data, off.ctypes.data, len(seqs), C.byref(ptr), C.byref(n)) != 0:
+            self._err()
+        a = np.frombuffer(C.string_at(ptr, n.value * dtype.itemsize), dtype=dtype).copy() if n.value else np.zeros(0, dtype)
+        self.lib.lmg_free(ptr)
+        return a
+
+    def anchors(self, seqs, params=None):
+        return self._stage(self.lib.lmg_anchor_batch, ANCHOR_DTYPE, seqs, params)
+
+    def chains(self, seqs, params=None):
+        return self._stage(self.lib.lmg_chain_batch, CHAIN_DTYPE, seqs, params)
+
+
+def wfa_batch(pairs, device=0):
+    L = load_library()
+    flat = []
+    for q, t in pairs:
+        flat += [q, t]
+    buf, off = pack_queries(flat)
+    ptr, n = C.c_void_p(), C.c_uint64()
+    if L.lmg_wfa_batch(device, buf.ctypes.data, off.ctypes.data, len(pairs), C.byref(ptr), C.byref(n)) != 0:
+        raise RuntimeError(L.lmg_last_error().decode())
+    s = C.string_at(ptr, n.value).decode()
+    L.lmg_free(ptr)
+    return s.split("\n")[:-1]
