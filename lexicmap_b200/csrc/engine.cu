@@ -240,6 +240,128 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, DBuf<Cap
 }
 
 // =====================================================================================================
+// K3: ClearSubstrPairs (lib-index-search.go:864-990) + Chainer.Chain (lib-chaining.go:122-633)
+// =====================================================================================================
+__device__ __forceinline__ i32 a_q(u64 lo) { return (i32)(lo >> 36); }
+__device__ __forceinline__ i32 a_len(u64 lo) { return 63 - (i32)((lo >> 30) & 63); }
+__device__ __forceinline__ i32 a_t(u64 lo) { return (i32)((lo >> 2) & 0x0FFFFFFF); }
+__device__ __forceinline__ float seedw(float l) { return __fmul_rn(__fmul_rn(0.1f, l), l); }   // seedWeight lib-chaining.go:635 (no FMA contraction, as Go/amd64)
+
+struct ChainParams { float max_gap, min_score, max_distance; int top_chains, k; const float* gap_score; int gap_tab; };
+
+// one warp per (query, genome) segment. Anchors arrive sorted by (QBegin asc, QEnd desc, TBegin asc, qrc, trc).
+// Phase 1: mark anchors nested in an earlier anchor within the k-window, compact in place order into c_lo.
+// Phase 2: DP. For anchor i the predecessors are j < i with |TBegin diff| <= max_distance (RangeIndex query, :380-385),
+//          QBegin/TBegin different, QBegin diff <= max_distance (break, :416), gap <= max_gap; lanes evaluate 32 candidates at a
+//          time in descending j, the warp keeps the best score with ties to the larger j (= first strict improvement, :462).
+__global__ void __launch_bounds__(128) k_clear_chain(const u64* __restrict__ lo_in, const u64* __restrict__ seg_off, u32 nseg, ChainParams P,
+                                                     u64* __restrict__ c_lo, u32* __restrict__ c_n, float* __restrict__ score, u32* __restrict__ pred, signed char* __restrict__ dirs, u64* __restrict__ s2i) {
+  u32 seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31; if (seg >= nseg) return;
+  u64 b = seg_off[seg]; u32 n = (u32)(seg_off[seg + 1] - b); const u64* A = lo_in + b; u64* C = c_lo + b; const int k = P.k;
+  // ---- phase 1
+  u32 kept = 0;
+  for (u32 base = 0; base < n; base += 32) {
+    u32 i = base + lane; bool keep = false;
+    if (i < n) { keep = true; if (i > 0) { u64 v = A[i]; i32 vq = a_q(v), vl = a_len(v), vt = a_t(v); i32 vQEnd = vq + vl, up = max(vQEnd - k, 0), vTEnd = vt + vl;
+        for (i32 j = (i32)i - 1; j >= 0; j--) { u64 p = A[j]; i32 pq = a_q(p); if (pq < up) break; i32 pl = a_len(p), pt = a_t(p); if (vQEnd <= pq + pl && vt >= pt && vTEnd <= pt + pl) { keep = false; break; } } } }
+    u32 bal = __ballot_sync(FULLMASK, keep); if (keep) C[kept + __popc(bal & ((1u << lane) - 1))] = A[i]; kept += __popc(bal);
+  }
+  __syncwarp(); n = kept; if (lane == 0) c_n[seg] = n;
+  float* S = score + b; u32* Pd = pred + b; signed char* D = dirs + b; u64* K2 = s2i + b;
+  if (n == 1) { if (lane == 0) { float w = seedw((float)a_len(C[0])); S[0] = w; Pd[0] = 0; D[0] = 0; K2[0] = ((u64)__float_as_uint(w) << 32); } return; }
+  if (lane == 0) { float w = seedw((float)a_len(C[0])); S[0] = w; Pd[0] = 0; D[0] = 0; K2[0] = ((u64)__float_as_uint(w) << 32); }
+  __syncwarp();
+  const i32 maxDist = (i32)P.max_distance;
+  for (u32 i = 1; i < n; i++) {
+    u64 av = C[i]; i32 aq = a_q(av), al = a_len(av), at = a_t(av); float m0 = seedw((float)al);
+    float bs = -1.0f; i32 bj = -1; int bdir = 0; bool stop = false;
+    for (i32 top = (i32)i - 1; top >= 0 && !stop; top -= 32) {
+      i32 j = top - lane; float s = -1.0f; int dir = 0; bool valid = false;
+      if (j >= 0) { u64 bv = C[j]; i32 bq = a_q(bv), bl = a_len(bv), bt = a_t(bv);
+        if (aq - bq > maxDist) stop = true;   // all smaller j are at least as far
+        else if (aq != bq && at != bt && bt >= (at < maxDist ? 0 : at - maxDist) && bt <= at + maxDist) {
+          i32 dq = abs(aq - bq), dt; if (at >= bt) dt = abs(at - bt); else dt = abs(at + al - bt - bl);
+          i32 g = abs(dq - dt);
+          if ((float)g <= P.max_gap) {
+            float w; if (aq > bq + bl) w = seedw((float)al); else if (g == 0) w = __fadd_rn(-seedw((float)bl), seedw((float)(aq + al - bq))); else w = seedw((float)(aq + al - (bq + bl)));
+            dir = (at >= bt) ? 1 : -1; int dj = D[j]; float prev = (dj == 0 || dj == dir) ? S[j] : seedw((float)bl);
+            float gs = (g == 0) ? 0.0f : P.gap_score[min(g, P.gap_tab - 1)];
+            s = __fsub_rn(__fadd_rn(prev, w), gs); valid = (s >= P.min_score);
+          } } }
+      if (!valid) s = -1.0f;
+      // warp arg-max, ties -> larger j (smaller lane)
+      float rs = s; i32 rj = valid ? j : -1; int rd = dir;
+      for (int o = 16; o; o >>= 1) { float os = __shfl_xor_sync(FULLMASK, rs, o); i32 oj = __shfl_xor_sync(FULLMASK, rj, o); int od = __shfl_xor_sync(FULLMASK, rd, o); if (os > rs || (os == rs && oj > rj)) { rs = os; rj = oj; rd = od; } }
+      if (rj >= 0 && rs > bs) { bs = rs; bj = rj; bdir = rd; }
+      stop = __any_sync(FULLMASK, stop);
+    }
+    if (lane == 0) { float m = m0; u32 mj = i; int md = 0; if (bj >= 0 && bs > m0) { m = bs; mj = (u32)bj; md = bdir; } S[i] = m; Pd[i] = mj; D[i] = (signed char)md; K2[i] = ((u64)__float_as_uint(m) << 32) | i; }
+    __syncwarp();
+  }
+}
+
+struct ChainRec { u32 seg, ord; i32 q0, t0, len0, q1, t1, len1; u32 flags1; i32 nseeds; float score; u32 pad; };  // flags1: bit1 qrc, bit0 trc of the LAST anchor
+
+// one thread per segment: backtrack (lib-chaining.go:490-629). s2i_sorted ascending within the segment.
+__global__ void k_backtrack(const u64* __restrict__ seg_off, const u32* __restrict__ c_n, u32 nseg, const u64* __restrict__ c_lo, const u32* __restrict__ pred, const signed char* __restrict__ dirs,
+                            const u64* __restrict__ s2i_sorted, u8* __restrict__ visited, ChainParams P, ChainRec* __restrict__ out, u32* __restrict__ nout, u32 cap, float* __restrict__ seg_score) {
+  u32 seg = blockIdx.x * blockDim.x + threadIdx.x; if (seg >= nseg) return; u64 b = seg_off[seg]; i32 n = (i32)c_n[seg]; const u64* C = c_lo + b; const u32* Pd = pred + b; const signed char* D = dirs + b; const u64* K2 = s2i_sorted + b; u8* V = visited + b;
+  u32 ord = 0;
+  auto emit = [&](i32 first, i32 last, i32 cnt, float sc) { u32 w = atomicAdd(nout, 1u); if (w < cap) { ChainRec r; r.seg = seg; r.ord = ord; u64 f = C[first], l = C[last]; r.q0 = a_q(f); r.t0 = a_t(f); r.len0 = a_len(f); r.q1 = a_q(l); r.t1 = a_t(l); r.len1 = a_len(l); r.flags1 = (u32)(l & 3); r.nseeds = cnt; r.score = sc; r.pad = 0; out[w] = r; } ord++; };
+  if (n == 1) { float w = __uint_as_float((u32)(K2[0] >> 32)); seg_score[seg] = w; if (w >= P.min_score) emit(0, 0, 1, w); return; }
+  i32 iMax = n - 1; float maxScore = 0; bool first = true; int nChecked = 0;
+  for (;;) {
+    nChecked++; if (P.top_chains > 0 && nChecked > P.top_chains) break;
+    float M = 0; u32 Mi = 0;
+    while (iMax >= 0) { u64 e = K2[iMax]; M = __uint_as_float((u32)(e >> 32)); Mi = (u32)e; if (!V[Mi]) { iMax--; break; } iMax--; }
+    if (M < P.min_score) break;
+    i32 i = (i32)Mi; if (first) { maxScore = M; first = false; }
+    i32 cnt = 0, lastA = -1, firstA = -1;
+    for (;;) { i32 j = (i32)Pd[i]; bool change = (i != j && D[j] != 0 && D[i] != D[j]);
+      if (V[j] && !change) { cnt = 0; V[i] = 1; break; }
+      if (cnt == 0) lastA = i; firstA = i; cnt++; V[i] = 1;
+      if (i == j || change) { if (change) { firstA = j; cnt++; } emit(firstA, lastA, cnt, 0.0f); cnt = -1; break; } else i = j; }
+  }
+  seg_score[seg] = maxScore;
+}
+
+struct Segments { u32 nseg = 0; DBuf<u64> key, off; DBuf<u32> cn; DBuf<u64> c_lo; DBuf<float> score; std::vector<u64> h_key, h_off; };
+struct Chains { u32 n = 0; DBuf<ChainRec> rec; std::vector<ChainRec> h; std::vector<float> seg_score; };
+
+static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segments& S, Chains& Cn) {
+  cudaStream_t st = ix->st; u64 N = A.n; S.nseg = 0; Cn.n = 0; if (N == 0) return;
+  // segments = runs of equal (query, genome)
+  DBuf<u64> ukey(N, st); DBuf<u32> cnt(N + 1, st); DBuf<u32> nruns(1, st);
+  { size_t tb = 0; cub::DeviceRunLengthEncode::Encode(nullptr, tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); cub::DeviceRunLengthEncode::Encode(ix->tmp.get(tb), tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); KERNEL_CHECK(); }
+  u32 nseg = nruns.to_host()[0]; S.nseg = nseg; S.off.alloc(nseg + 1, st);
+  { DBuf<u64> c64(nseg + 1, st); struct Dummy {}; // widen counts
+    std::vector<u32> hc = cnt.to_host(nseg); S.h_off.assign(nseg + 1, 0); for (u32 i = 0; i < nseg; i++) S.h_off[i + 1] = S.h_off[i] + hc[i]; S.off.from_host(S.h_off.data(), nseg + 1); }
+  S.h_key = ukey.to_host(nseg); S.key = std::move(ukey);
+  // gap-score table on the host (gapScore lib-chaining.go:662: 0.1*g + 0.5*float32(log2(float64(g))), g integer <= max_gap)
+  int gt = std::max(2, (int)std::floor(prm->max_gap) + 2); std::vector<float> gtab(gt, 0.0f);
+  for (int g = 1; g < gt; g++) { volatile float a = 0.1f * (float)g; volatile float bb = 0.5f * (float)std::log2((double)g); volatile float c = a + bb; gtab[g] = c; }
+  DBuf<float> dgt(gt, st); dgt.from_host(gtab.data(), gt);
+  ChainParams P; P.max_gap = prm->max_gap; { volatile float w = 0.1f * (float)prm->min_single_prefix; volatile float w2 = w * (float)prm->min_single_prefix; P.min_score = w2; } P.max_distance = prm->max_distance; P.top_chains = prm->top_n_chains; P.k = ix->img.k; P.gap_score = dgt.p; P.gap_tab = gt;
+  S.c_lo.alloc(N, st); S.cn.alloc(nseg, st); S.score.alloc(nseg, st); DBuf<float> sc(N, st); DBuf<u32> pred(N, st); DBuf<signed char> dirs(N, st); DBuf<u64> s2i(N, st), s2i_s(N, st); DBuf<u8> visited(N, st); visited.zero();
+  k_clear_chain<<<cdiv((i64)nseg * 32, 128), 128, 0, st>>>(A.lo.p, S.off.p, nseg, P, S.c_lo.p, S.cn.p, sc.p, pred.p, dirs.p, s2i.p); KERNEL_CHECK();
+  // per-segment ascending sort of (score bits << 32 | index) over the compacted prefix of each segment
+  DBuf<u64> seg_end(nseg, st);
+  { std::vector<u32> hcn = S.cn.to_host(nseg); std::vector<u64> he(nseg); for (u32 i = 0; i < nseg; i++) he[i] = S.h_off[i] + hcn[i]; seg_end.from_host(he.data(), nseg); CUDA_CHECK(cudaStreamSynchronize(st)); }
+  { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); KERNEL_CHECK(); }
+  u32 cap = (u32)std::min<u64>(N + nseg, 0x7fffffffu); Cn.rec.alloc(cap, st); DBuf<u32> nout(1, st); nout.zero();
+  k_backtrack<<<cdiv(nseg, 128), 128, 0, st>>>(S.off.p, S.cn.p, nseg, S.c_lo.p, pred.p, dirs.p, s2i_s.p, visited.p, P, Cn.rec.p, nout.p, cap, S.score.p); KERNEL_CHECK();
+  u32 nc = nout.to_host()[0]; if (nc > cap) throw std::runtime_error("chain list overflow"); Cn.n = nc; Cn.seg_score = S.score.to_host(nseg);
+  Cn.h = Cn.rec.to_host(nc);
+  // drop genomes below min score (:1724), optional top-N genomes per query (:1780-1805), order chains by (segment, first TBegin, emission order) (:1967-1974)
+  std::vector<char> keep(nseg, 1); for (u32 s = 0; s < nseg; s++) if (Cn.seg_score[s] < P.min_score) keep[s] = 0;
+  if (prm->top_n_genomes > 0) { u32 s0 = 0; while (s0 < nseg) { u32 q = (u32)(S.h_key[s0] >> 36), s1 = s0; std::vector<u32> v; while (s1 < nseg && (u32)(S.h_key[s1] >> 36) == q) { if (keep[s1]) v.push_back(s1); s1++; }
+      if ((int)v.size() > prm->top_n_genomes) { std::stable_sort(v.begin(), v.end(), [&](u32 a, u32 b) { return Cn.seg_score[a] > Cn.seg_score[b]; }); for (size_t t = prm->top_n_genomes; t < v.size(); t++) keep[v[t]] = 0; } s0 = s1; } }
+  std::vector<ChainRec> kept; kept.reserve(nc); for (auto& r : Cn.h) if (keep[r.seg]) { r.score = Cn.seg_score[r.seg]; kept.push_back(r); }
+  std::sort(kept.begin(), kept.end(), [](const ChainRec& a, const ChainRec& b) { if (a.seg != b.seg) return a.seg < b.seg; if (a.t0 != b.t0) return a.t0 < b.t0; return a.ord < b.ord; });
+  Cn.h.swap(kept); Cn.n = (u32)Cn.h.size();
+}
+
+// =====================================================================================================
 // C ABI (part 1)
 // =====================================================================================================
 extern "C" {
@@ -280,6 +402,16 @@ int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
     *out = o; *n_out = A.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
+
+#define LMG_HAVE_CHAIN 1
+int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_chain** out, uint64_t* n_out) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+    Anchors A; seed_probe(ix, B, p, cap, owner, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
+    lmg_chain* o = (lmg_chain*)malloc(sizeof(lmg_chain) * (C.n + 1));
+    for (u32 i = 0; i < C.n; i++) { const ChainRec& r = C.h[i]; lmg_chain& c = o[i]; u64 key = S.h_key[r.seg]; c.query = (u32)(key >> 36); c.genome = ix->img.genome_bgi[(u32)((key >> 2) & 0x3FFFFFFFFull)]; c.score = r.score; c.n_seeds = r.nseeds;
+      c.q0 = r.q0; c.t0 = r.t0; c.len0 = r.len0; c.q1 = r.q1; c.t1 = r.t1; c.len1 = r.len1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1; c.rc = (r.nseeds == 1) ? (qrc != trc) : (r.t0 > r.t1); }
+    *out = o; *n_out = C.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 }  // extern "C"
 
 // ---- not yet implemented entry points (fail loudly)

@@ -31,3 +31,20 @@ def test_anchors_match_oracle(gpu_small, oracle_small, small_queries):
     oa = oracle_small.anchors(seqs)
     assert len(ga) == len(oa) and len(ga) > 100
     assert ga.tobytes() == oa.tobytes(), "anchor multiset differs"
+
+
+def test_chains_match_oracle(gpu_small, oracle_small, small_queries):
+    ids, seqs = small_queries
+    gc = gpu_small.chains(seqs)
+    oc = oracle_small.chains(seqs)
+    assert len(gc) == len(oc) and len(gc) > 20
+    for f in gc.dtype.names:
+        assert np.array_equal(gc[f], oc[f]), "chain field %s differs" % f
+
+
+def test_chains_top_n(gpu_small, oracle_small, small_queries):
+    ids, seqs = small_queries
+    p = dict(top_n_genomes=2, top_n_chains=1)
+    gc = gpu_small.chains(seqs, gpu_small.default_params(**p))
+    oc = oracle_small.chains(seqs, oracle_small.default_params(**p))
+    assert gc.tobytes() == oc.tobytes()
