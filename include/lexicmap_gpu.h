@@ -89,13 +89,19 @@ void lmg_index_close(lmg_index* idx);
 /* Index.Search for a batch (lib-index-search.go:1191). seqs: concatenated query sequences (ASCII, any case);
  * seq_off[n+1]. Host buffers in, host rows out; blocking. */
 int  lmg_search_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, const uint64_t* seq_off, int32_t n_queries, lmg_results** out);
-/* same work, but inputs are staged to HBM by lmg_stage_queries beforehand (bench "value" leg) */
+/* same work with the query batch staged to HBM beforehand (bench "value" leg: inputs resident when the timed region starts) */
+typedef struct lmg_queries lmg_queries;
+int  lmg_queries_upload(lmg_index* idx, const uint8_t* seqs, const uint64_t* seq_off, int32_t n_queries, lmg_queries** out);
+int  lmg_search_staged(lmg_index* idx, const lmg_params* p, lmg_queries* q, lmg_results** out);
+void lmg_queries_free(lmg_index* idx, lmg_queries* q);
 int  lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** strpool, uint64_t* strpool_len);
 int  lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid);
 void lmg_results_free(lmg_results* r);
-/* per-stage device time of the last lmg_search_batch, ms: [0]=h2d [1]=sketch [2]=seed probe [3]=anchor sort/chain
- * [4]=pseudo-align [5]=extend+wfa [6]=d2h+finish [7]=total; plus algorithmic byte counters for the probe kernel */
-int  lmg_last_timing(const lmg_index* idx, double* ms8, uint64_t* counters8);
+/* CUDA-event times of the last search, ms[16]: [0]=h2d [1]=sketch [2]=seed probe [3]=anchor sort/chain [4]=pseudo-align
+ * [5]=extend+wfa [6]=host finish [7]=total [8]=k_probe_find kernel alone.  counters[16]: [0..5] probe statistics of the last
+ * lmg_anchor_batch (issued, with anchor, search steps, entries scanned, hit records, anchors) [6]=query bases [7]=queries
+ * [8]=probe slots [15]=kernels launched by this library so far */
+int  lmg_last_timing(const lmg_index* idx, double* ms16, uint64_t* counters16);
 
 /* ---- stage-wise entry points (parity tests; mirror a1-a7 of SURVEY.md §8a) ---- */
 /* lexichash mask + DUST filter + suffix re-masking (lib-index-search.go:1212-1350): kmers[n*m], nlocs[n*m], minloc[n*m];

@@ -54,6 +54,9 @@ def load_library():
     L.lmg_results_seq_id.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p)]
     L.lmg_results_free.argtypes = [vp]
     L.lmg_last_timing.argtypes = [vp, vp, vp]
+    L.lmg_queries_upload.argtypes = [vp, vp, vp, C.c_int32, C.POINTER(vp)]
+    L.lmg_search_staged.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(vp)]
+    L.lmg_queries_free.argtypes = [vp, vp]
     L.lmg_mask_batch.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, u64p]
     L.lmg_anchor_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_chain_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
@@ -119,6 +122,47 @@ class Index:
         r = C.c_void_p()
         if self.lib.lmg_search_batch(self.h, C.byref(p), buf.ctypes.data, off.ctypes.data, n, C.byref(r)) != 0:
             self._err()
+        return self._collect(r)
+
+    def stage(self, seqs=None, packed=None):
+        """copy a query batch to HBM ahead of time; returns an opaque handle for search_staged()"""
+        buf, off = packed if packed is not None else pack_queries(seqs)
+        q = C.c_void_p()
+        if self.lib.lmg_queries_upload(self.h, buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(q)) != 0:
+            self._err()
+        return q
+
+    def search_staged(self, q, params=None, collect=True):
+        p = params or self.default_params()
+        r = C.c_void_p()
+        if self.lib.lmg_search_staged(self.h, C.byref(p), q, C.byref(r)) != 0:
+            self._err()
+        if collect:
+            return self._collect(r)
+        nr = self._nrows(r)
+        self.lib.lmg_results_free(r)
+        return nr
+
+    def free_staged(self, q):
+        self.lib.lmg_queries_free(self.h, q)
+
+    def _nrows(self, r):
+        rows_p, pool_p, nr, npool = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self.lib.lmg_results_rows(r, C.byref(rows_p), C.byref(nr), C.byref(pool_p), C.byref(npool))
+        return nr.value
+
+    def search_count(self, packed, params=None):
+        """search from host buffers, return only the number of rows (bench e2e leg: no Python-side row copies)"""
+        p = params or self.default_params()
+        buf, off = packed
+        r = C.c_void_p()
+        if self.lib.lmg_search_batch(self.h, C.byref(p), buf.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(r)) != 0:
+            self._err()
+        nr = self._nrows(r)
+        self.lib.lmg_results_free(r)
+        return nr
+
+    def _collect(self, r):
         rows_p, pool_p, nr, npool = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
         self.lib.lmg_results_rows(r, C.byref(rows_p), C.byref(nr), C.byref(pool_p), C.byref(npool))
         rows = np.frombuffer(C.string_at(rows_p, nr.value * HSP_DTYPE.itemsize), dtype=HSP_DTYPE).copy() if nr.value else np.zeros(0, HSP_DTYPE)
@@ -133,8 +177,8 @@ class Index:
         return rows, seqids, cig
 
     def timing(self):
-        ms = np.zeros(8, np.float64)
-        cnt = np.zeros(8, np.uint64)
+        ms = np.zeros(16, np.float64)
+        cnt = np.zeros(16, np.uint64)
         self.lib.lmg_last_timing(self.h, ms.ctypes.data, cnt.ctypes.data)
         return ms, cnt
 

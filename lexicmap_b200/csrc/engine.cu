@@ -18,11 +18,17 @@
 #include <numeric>
 #include <chrono>
 #include <mutex>
+#include <set>
+#include <array>
 
 // =====================================================================================================
 // small device utilities
 // =====================================================================================================
 #define FULLMASK 0xffffffffu
+static unsigned long long g_launches = 0;   // kernels of THIS library launched (CUB's internal kernels are not counted)
+#undef KERNEL_CHECK
+#define KERNEL_CHECK() do { g_launches++; CUDA_CHECK(cudaGetLastError()); } while (0)
+#define CUB_CHECK() CUDA_CHECK(cudaGetLastError())
 static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 
 struct CubTemp {  // grow-only temp storage for CUB calls
@@ -35,8 +41,11 @@ struct CubTemp {  // grow-only temp storage for CUB calls
 // K1: sketch
 // =====================================================================================================
 // ASCII -> 2-bit packed (4 bases / byte, first base in bits 7-6). One thread per output byte.
-__global__ void k_pack_queries(const u8* __restrict__ ascii, const u64* __restrict__ off, const u64* __restrict__ boff, u8* __restrict__ packed, int nq) {
-  int q = blockIdx.y; if (q >= nq) return; u64 a0 = off[q], L = off[q + 1] - a0; u64 nb = (L + 3) >> 2; u8* out = packed + boff[q];
+__device__ __forceinline__ u32 is_acgt(u8 c) { c &= 0xDF; return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// amask: 1 bit per base (bit i&7 of byte i>>3) = base is not A/C/G/T; base-level alignment compares raw bytes in the reference, so such bases never match
+__global__ void k_pack_queries(const u8* __restrict__ ascii, const u64* __restrict__ off, const u64* __restrict__ boff, u8* __restrict__ packed, u8* __restrict__ amask, int nq) {
+  int q = blockIdx.y; if (q >= nq) return; u64 a0 = off[q], L = off[q + 1] - a0; u64 nb = (L + 3) >> 2; u8* out = packed + boff[q]; u8* am = amask + boff[q];
+  for (u64 b = blockIdx.x * (u64)blockDim.x + threadIdx.x; b < ((L + 7) >> 3); b += (u64)gridDim.x * blockDim.x) { u32 v = 0; for (int j = 0; j < 8; j++) { u64 i = b * 8 + j; if (i < L && !is_acgt(ascii[a0 + i])) v |= 1u << j; } am[b] = (u8)v; }
   for (u64 b = blockIdx.x * (u64)blockDim.x + threadIdx.x; b < nb; b += (u64)gridDim.x * blockDim.x) {
     u32 v = 0; for (int j = 0; j < 4; j++) { u64 i = b * 4 + j; u32 c = (i < L) ? base2bit(ascii[a0 + i]) : 0; v = (v << 2) | c; } out[b] = (u8)v; }
 }
@@ -155,13 +164,13 @@ __global__ void k_probe_emit(ProbeParams P, const ProbeHit* __restrict__ hits, c
 // =====================================================================================================
 struct QBatch {  // device-side query batch
   int nq = 0; u64 total_bases = 0, total_k = 0;
-  DBuf<u8> ascii, packed; DBuf<u64> off, boff, koff; std::vector<u64> h_off, h_boff, h_koff;
+  DBuf<u8> ascii, packed, amask; DBuf<u64> off, boff, koff; std::vector<u64> h_off, h_boff, h_koff;
   DBuf<u64> qkeys; DBuf<u32> qvals;    // per-query sorted (k-mer, loc) tables
 };
 
 struct lmg_index {
   Image img; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[8] = {0}; u64 counters[8] = {0}; std::mutex mu;
+  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[2] = {nullptr, nullptr};
 };
 
 static thread_local std::string g_err;
@@ -175,18 +184,18 @@ static void upload_queries(lmg_index* ix, const u8* seqs, const u64* off, int nq
   B.h_boff[nq] = b; B.h_koff[nq] = kk; B.total_k = kk;
   B.ascii.alloc(B.total_bases + 16, st); B.ascii.from_host(seqs + off[0], B.total_bases); B.off.alloc(nq + 1, st); B.off.from_host(B.h_off.data(), nq + 1);
   B.boff.alloc(nq + 1, st); B.boff.from_host(B.h_boff.data(), nq + 1); B.koff.alloc(nq + 1, st); B.koff.from_host(B.h_koff.data(), nq + 1);
-  B.packed.alloc(b + 64, st); B.packed.zero();
+  B.packed.alloc(b + 64, st); B.packed.zero(); B.amask.alloc(b + 64, st); B.amask.zero();
 }
 
 // K1a: pack + k-mers + per-query stable sort by k-mer
 static void sketch_tables(lmg_index* ix, QBatch& B) {
   cudaStream_t st = ix->st; const int k = ix->img.k; int nq = B.nq; u64 maxL = 0; for (int q = 0; q < nq; q++) maxL = std::max(maxL, B.h_off[q + 1] - B.h_off[q]);
-  dim3 g1((unsigned)std::max(1, std::min(64, cdiv((i64)(maxL + 3) / 4, 256))), nq); k_pack_queries<<<g1, 256, 0, st>>>(B.ascii.p, B.off.p, B.boff.p, B.packed.p, nq); KERNEL_CHECK();
+  dim3 g1((unsigned)std::max(1, std::min(64, cdiv((i64)(maxL + 3) / 4, 256))), nq); k_pack_queries<<<g1, 256, 0, st>>>(B.ascii.p, B.off.p, B.boff.p, B.packed.p, B.amask.p, nq); KERNEL_CHECK();
   DBuf<u64> keys_in(B.total_k + 2, st); DBuf<u32> vals_in(B.total_k + 2, st); B.qkeys.alloc(B.total_k + 2, st); B.qvals.alloc(B.total_k + 2, st);
   if (B.total_k == 0) return;
   dim3 g2((unsigned)std::max(1, std::min(64, cdiv((i64)maxL, 128))), nq); k_gen_kmers<<<g2, 128, 0, st>>>(B.packed.p, B.boff.p, B.off.p, B.koff.p, keys_in.p, vals_in.p, nq, k); KERNEL_CHECK();
   size_t tb = 0; cub::DeviceSegmentedSort::StableSortPairs(nullptr, tb, keys_in.p, B.qkeys.p, vals_in.p, B.qvals.p, (int)B.total_k, nq, B.koff.p, B.koff.p + 1, st);
-  cub::DeviceSegmentedSort::StableSortPairs(ix->tmp.get(tb), tb, keys_in.p, B.qkeys.p, vals_in.p, B.qvals.p, (int)B.total_k, nq, B.koff.p, B.koff.p + 1, st); KERNEL_CHECK();
+  cub::DeviceSegmentedSort::StableSortPairs(ix->tmp.get(tb), tb, keys_in.p, B.qkeys.p, vals_in.p, B.qvals.p, (int)B.total_k, nq, B.koff.p, B.koff.p + 1, st); CUB_CHECK();
 }
 
 // K1b: capture
@@ -207,7 +216,7 @@ static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
-  cub::DeviceRadixSort::SortPairs(ix->tmp.get(tb), tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st); KERNEL_CHECK();
+  cub::DeviceRadixSort::SortPairs(ix->tmp.get(tb), tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st); CUB_CHECK();
 }
 
 static int bits_for(u64 v) { int b = 1; while ((v >> b) && b < 64) b++; return b; }
@@ -222,13 +231,14 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, DBuf<Cap
   // first pass with a bounded list; typical hit rates are a few % of probes
   u64 tryCap = std::min<u64>(capHits, std::max<u64>(1u << 20, nprobe / 4));
   for (;;) { hits.alloc(tryCap, st); nh.zero(); if (stats) dstats.zero();
-    k_probe_find<<<cdiv((i64)nprobe, 256), 256, 0, st>>>(P, cap.p, owner.p, B.koff.p, nprobe, hits.p, nh.p, stats ? dstats.p : nullptr); KERNEL_CHECK();
-    u32 h = nh.to_host()[0]; if (h <= tryCap) { tryCap = h; break; } tryCap = capHits; }
+    if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); } cudaEventRecord(ix->kev[0], st);
+    k_probe_find<<<cdiv((i64)nprobe, 256), 256, 0, st>>>(P, cap.p, owner.p, B.koff.p, nprobe, hits.p, nh.p, stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
+    u32 h = nh.to_host()[0]; { float f = 0; cudaEventElapsedTime(&f, ix->kev[0], ix->kev[1]); ix->ms[8] = f; ix->counters[8] = nprobe; } if (h <= tryCap) { tryCap = h; break; } tryCap = capHits; }
   u32 nhit = (u32)tryCap; if (stats) { auto s = dstats.to_host(); for (int i = 0; i < 4; i++) ix->counters[i] = s[i]; ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
   DBuf<u64> hoff(nhit + 1, st);
   { DBuf<u64> cnt(nhit + 1, st); k_hit_counts<<<cdiv(nhit + 1, 256), 256, 0, st>>>(hits.p, nhit, cnt.p); KERNEL_CHECK();
-    size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, hoff.p, (int)(nhit + 1), st); cub::DeviceScan::ExclusiveSum(ix->tmp.get(tb), tb, cnt.p, hoff.p, (int)(nhit + 1), st); KERNEL_CHECK(); }
+    size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, hoff.p, (int)(nhit + 1), st); cub::DeviceScan::ExclusiveSum(ix->tmp.get(tb), tb, cnt.p, hoff.p, (int)(nhit + 1), st); CUB_CHECK(); }
   u64 total; CUDA_CHECK(cudaMemcpyAsync(&total, hoff.p + nhit, 8, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st));
   A.n = total; if (stats) ix->counters[5] = total; if (total == 0) return; if (total >= (1ull << 31)) throw std::runtime_error("more than 2^31 anchors in one batch; use smaller batches");
   DBuf<u64> hi0(total, st), lo0(total, st); A.hi.alloc(total, st); A.lo.alloc(total, st);
@@ -332,7 +342,7 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   cudaStream_t st = ix->st; u64 N = A.n; S.nseg = 0; Cn.n = 0; if (N == 0) return;
   // segments = runs of equal (query, genome)
   DBuf<u64> ukey(N, st); DBuf<u32> cnt(N + 1, st); DBuf<u32> nruns(1, st);
-  { size_t tb = 0; cub::DeviceRunLengthEncode::Encode(nullptr, tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); cub::DeviceRunLengthEncode::Encode(ix->tmp.get(tb), tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); KERNEL_CHECK(); }
+  { size_t tb = 0; cub::DeviceRunLengthEncode::Encode(nullptr, tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); cub::DeviceRunLengthEncode::Encode(ix->tmp.get(tb), tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); CUB_CHECK(); }
   u32 nseg = nruns.to_host()[0]; S.nseg = nseg; S.off.alloc(nseg + 1, st);
   { DBuf<u64> c64(nseg + 1, st); struct Dummy {}; // widen counts
     std::vector<u32> hc = cnt.to_host(nseg); S.h_off.assign(nseg + 1, 0); for (u32 i = 0; i < nseg; i++) S.h_off[i + 1] = S.h_off[i] + hc[i]; S.off.from_host(S.h_off.data(), nseg + 1); }
@@ -347,7 +357,7 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   // per-segment ascending sort of (score bits << 32 | index) over the compacted prefix of each segment
   DBuf<u64> seg_end(nseg, st);
   { std::vector<u32> hcn = S.cn.to_host(nseg); std::vector<u64> he(nseg); for (u32 i = 0; i < nseg; i++) he[i] = S.h_off[i] + hcn[i]; seg_end.from_host(he.data(), nseg); CUDA_CHECK(cudaStreamSynchronize(st)); }
-  { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); KERNEL_CHECK(); }
+  { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); CUB_CHECK(); }
   u32 cap = (u32)std::min<u64>(N + nseg, 0x7fffffffu); Cn.rec.alloc(cap, st); DBuf<u32> nout(1, st); nout.zero();
   k_backtrack<<<cdiv(nseg, 128), 128, 0, st>>>(S.off.p, S.cn.p, nseg, S.c_lo.p, pred.p, dirs.p, s2i_s.p, visited.p, P, Cn.rec.p, nout.p, cap, S.score.p); KERNEL_CHECK();
   u32 nc = nout.to_host()[0]; if (nc > cap) throw std::runtime_error("chain list overflow"); Cn.n = nc; Cn.seg_score = S.score.to_host(nseg);
@@ -359,6 +369,451 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   std::vector<ChainRec> kept; kept.reserve(nc); for (auto& r : Cn.h) if (keep[r.seg]) { r.score = Cn.seg_score[r.seg]; kept.push_back(r); }
   std::sort(kept.begin(), kept.end(), [](const ChainRec& a, const ChainRec& b) { if (a.seg != b.seg) return a.seg < b.seg; if (a.t0 != b.t0) return a.t0 < b.t0; return a.ord < b.ord; });
   Cn.h.swap(kept); Cn.n = (u32)Cn.h.size();
+}
+
+// =====================================================================================================
+// K4: pseudo-alignment (SeqComparator.Index/Compare lib-seq_compare.go:115-159,:335-522; tree.Search tree/tree.go:441-527;
+//     ClearSubstrPairs; TrimSubStrPairs :553-621; Chainer2 lib-chaining2.go:152-658)
+// =====================================================================================================
+__global__ void k_tree_flags(const u32* __restrict__ vals, u64 n, u32* __restrict__ flags) { u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (i < n) flags[i] = (vals[i] >> 31) ? 0u : 1u; }
+__global__ void k_tree_scatter(const u64* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ pos, u64 n, u64* __restrict__ tkeys, u32* __restrict__ tvals) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (i < n && !(vals[i] >> 31)) { tkeys[pos[i]] = keys[i]; tvals[pos[i]] = vals[i]; } }
+__global__ void k_tree_offsets(const u32* __restrict__ pos, const u64* __restrict__ koff, int nq, u64 total_k, u32 total_t, u32* __restrict__ toff) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x; if (q <= nq) toff[q] = (q == nq || koff[q] >= total_k) ? total_t : pos[koff[q]]; }
+
+struct WinItem { u32 q, g; i32 tBegin, tEnd, W, qBegin, qEnd; u32 rc; i32 mp; u32 chain; };  // mp = min prefix for this window (lib-seq_compare.go:339-348)
+
+__device__ __forceinline__ u32 win_base(const u8* __restrict__ g2, i32 tBegin, i32 tEnd, u32 rc, i32 i) { return rc ? 3u - get_base(g2, (u64)(tEnd - i)) : get_base(g2, (u64)(tBegin + i)); }
+__device__ __forceinline__ int lcp31(u64 a, u64 b) { return a == b ? 31 : min(31, (__clzll(a ^ b) >> 1) - 1); }   // K = 31: LZ/2 + K - 32
+
+// tree.Search emulated on the sorted table, incl. the uint8 wrap in the mismatch branch (tree/tree.go:498-501)
+__device__ bool tree_search_slow(const u64* __restrict__ a, u32 n, u64 key, int p, u32* rlo, u32* rhi) {
+  const int K = 31; u32 lo = 0, hi = n; int depth = 0;
+  while (depth < K) {
+    int sh = 2 * (K - depth - 1); u64 qb = (key >> sh) & 3; u32 x = lo, y = hi;
+    while (x < y) { u32 m = (x + y) >> 1; if (((a[m] >> sh) & 3) < qb) x = m + 1; else y = m; } u32 l = x; y = hi;
+    while (x < y) { u32 m = (x + y) >> 1; if (((a[m] >> sh) & 3) <= qb) x = m + 1; else y = m; } u32 h = x;
+    if (l == h) return false;
+    int nodeEnd = lcp31(a[l], a[h - 1]), nk = nodeEnd - depth, mm = lcp31(key, a[l]);
+    if (mm >= nodeEnd) { depth = nodeEnd; lo = l; hi = h; if (depth >= p) { *rlo = lo; *rhi = hi; return true; } continue; }
+    int atleast = p - depth; bool hit; if (atleast <= nk) hit = mm >= depth + atleast; else { u64 nxt = (key >> (2 * (K - depth - atleast))) & ((1ull << (2 * atleast)) - 1); hit = (nxt == 0); }
+    if (hit) { *rlo = l; *rhi = h; return true; } return false;
+  }
+  return false;
+}
+// keys sharing >= p leading bases with `key`: [lo,hi) in the sorted table (fast path = range search; the radix-tree quirk only
+// adds results when the range is empty and bases [p-2,p) of the key are AA)
+__device__ __forceinline__ bool tree_search(const u64* __restrict__ a, u32 n, u64 key, int p, u32* rlo, u32* rhi) {
+  const int K = 31; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 x = 0, y = n;
+  while (x < y) { u32 m = (x + y) >> 1; if (a[m] < left) x = m + 1; else y = m; }
+  u32 e = x; while (e < n && a[e] <= right) e++;
+  if (e > x) { *rlo = x; *rhi = e; return true; }
+  if (p >= 2 && ((key >> (2 * (K - p))) & 0xF) == 0) return tree_search_slow(a, n, key, p, rlo, rhi);
+  return false;
+}
+
+// one CTA per window; threads over target positions. EMIT=false: count anchors; EMIT=true: write them (packed like seed anchors).
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_pa_anchors(const WinItem* __restrict__ items, u32 nitems, const u8* __restrict__ g2bit, const u64* __restrict__ g_off, const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff,
+                                                    u32* __restrict__ counts, const u64* __restrict__ aoff, u64* __restrict__ a_lo) {
+  typedef cub::BlockScan<u32, 128> Scan; __shared__ typename Scan::TempStorage tmp; __shared__ u32 s_base;
+  u32 it = blockIdx.x; if (it >= nitems) return; WinItem w = items[it]; const int K = 31; const u8* g2 = g2bit + g_off[w.g]; const u64* tk = tkeys + toff[w.q]; const u32* tv = tvals + toff[w.q]; u32 tn = toff[w.q + 1] - toff[w.q];
+  i32 np = w.W - K + 1; u32 total = 0; if (threadIdx.x == 0) s_base = 0; __syncthreads();
+  const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
+  for (i32 t0 = 0; t0 < np; t0 += 128) {
+    i32 idx = t0 + (i32)threadIdx.x; u32 c = 0; u64 km = 0, kr = 0; bool ok = false; u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0; bool f1 = false, f2 = false;
+    if (idx < np) { for (int j = 0; j < K; j++) { u64 b = win_base(g2, w.tBegin, w.tEnd, w.rc, idx + j); km = (km << 2) | b; kr = (kr >> 2) | ((3 - b) << 60); }
+      ok = !(km == 0 || km == ccc || km == ggg || km == ttt); }
+    if (ok && tn) {
+      f1 = tree_search(tk, tn, km, w.mp, &l1, &h1);
+      if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
+      f2 = tree_search(tk, tn, kr, w.mp, &l2, &h2);
+      if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
+    }
+    if (!EMIT) { total += c; }
+    else {
+      u32 ex, agg; Scan(tmp).ExclusiveSum(c, ex, agg); u64 wpos = aoff[it] + s_base + ex; __syncthreads(); if (threadIdx.x == 0) s_base += agg;
+      if (c) {
+        if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; a_lo[wpos++] = pack_lo((i32)p, (u32)lp, idx, 0, 0); }
+        if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; a_lo[wpos++] = pack_lo((i32)p, (u32)lp, idx + K - lp, 1, 1); }
+      }
+      __syncthreads();
+    }
+  }
+  if (!EMIT) { typedef cub::BlockReduce<u32, 128> Red; __shared__ typename Red::TempStorage rt; u32 s = Red(rt).Sum(total); if (threadIdx.x == 0) counts[it] = s; }
+}
+
+struct C2Rec { u32 item, ord; i32 qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors; };
+struct Chain2Params { int max_gap, min_score, min_align_len, band_count, band_base, k; };
+
+// one warp per window: nested-anchor removal, trimming, banded chaining DP, region splitting. Scalar control flow is executed
+// redundantly by all lanes (uniform); the DP inner loop and arg-max scans are lane-parallel.
+__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_in, const u64* __restrict__ aoff, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
+                                                  C2Rec* __restrict__ out, u32* __restrict__ nout, u32 cap) {
+  u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31; if (it >= nitems) return;
+  u64 b = aoff[it]; u32 n = (u32)(aoff[it + 1] - b); if (n == 0) return; const u64* A = lo_in + b; u64* C = c_lo + b; const int k = P.k;
+  // ---- ClearSubstrPairs
+  if (n > 1) { u32 kept = 0;
+    for (u32 base = 0; base < n; base += 32) { u32 i = base + lane; bool keep = false;
+      if (i < n) { keep = true; if (i > 0) { u64 v = A[i]; i32 vq = a_q(v), vl = a_len(v), vt = a_t(v); i32 vQEnd = vq + vl, up = max(vQEnd - k, 0), vTEnd = vt + vl;
+          for (i32 j = (i32)i - 1; j >= 0; j--) { u64 p = A[j]; i32 pq = a_q(p); if (pq < up) break; i32 pl = a_len(p), pt = a_t(p); if (vQEnd <= pq + pl && vt >= pt && vTEnd <= pt + pl) { keep = false; break; } } } }
+      u32 bal = __ballot_sync(FULLMASK, keep); if (keep) C[kept + __popc(bal & ((1u << lane) - 1))] = A[i]; kept += __popc(bal); }
+    n = kept; } else { if (lane == 0) C[0] = A[0]; }
+  __syncwarp();
+  // ---- TrimSubStrPairs(subs, k, 100)
+  if (n >= 2) { i32 last = (i32)n - 1; u64 _p = C[0]; i32 start = 0;
+    for (i32 i = 0; i < last; i++) { u64 p = C[i + 1]; i32 pq = a_q(p), pt = a_t(p), _q = a_q(_p), _t = a_t(_p), _l = a_len(_p); i32 dist = max(abs(pq - _q), abs(pt - _t)); bool c1 = (pq == _q || pt == _t);
+      bool take = false; if ((float)dist < 100.0f) { if (c1) take = true; else { i32 g2 = abs(abs(_q - pq) - abs(_t - pt)); i32 qo = 0, to = 0; if (pq >= _q && pq <= _q + _l) qo = _q + _l - pq + 1; if (pt >= _t && pt <= _t + _l) to = _t + _l - pt + 1;   // overlap(_p, p)
+          take = (g2 > 11 && (double)max(qo, to) / (double)_l > 0.8); } }
+      if (take) { start = i; _p = p; continue; } break; }
+    _p = C[last]; i32 end = last;
+    for (i32 i = (i32)n - 2; i >= 0; i--) { u64 p = C[i]; i32 pq = a_q(p), pt = a_t(p), pl = a_len(p), _q = a_q(_p), _t = a_t(_p), _l = a_len(_p); i32 dist = max(abs(pq - _q), abs(pt - _t)); bool c1 = (pq == _q || pt == _t);
+      bool take = false; if ((float)dist < 100.0f) { if (c1) take = true; else { i32 g2 = abs(abs(pq - _q) - abs(pt - _t)); i32 qo = 0, to = 0; if (_q >= pq && _q <= pq + pl) qo = pq + pl - _q + 1; if (_t >= pt && _t <= pt + pl) to = pt + pl - _t + 1;   // overlap(p, _p)
+          take = (g2 > 11 && (double)max(qo, to) / (double)_l > 0.8); } }
+      if (take) { end = i; _p = p; continue; } break; }
+    if (start >= end) return;   // all discarded
+    C += start; n = (u32)(end - start + 1); b += start; }
+  i32* S = score + b; u32* Pd = pred + b; u64* ST = stack + b; u32 ord = 0;
+  auto emit = [&](i32 qb, i32 qe, i32 tb, i32 te, i32 aq, i32 at, i32 matched, i32 na) { if (lane == 0) { u32 wv = atomicAdd(nout, 1u); if (wv < cap) { C2Rec r; r.item = it; r.ord = ord; r.qb = qb; r.qe = qe; r.tb = tb; r.te = te; r.aligned_q = aq; r.aligned_t = at; r.matched = matched; r.n_anchors = na; out[wv] = r; } } ord++; };
+  // ---- Chainer2.Chain
+  if (n == 1) { u64 v = C[0]; i32 sl = a_len(v); if (sl >= P.min_score && sl >= P.min_align_len) emit(a_q(v), a_q(v) + sl - 1, a_t(v), a_t(v) + sl - 1, sl, 0, sl, 1); return; }
+  if (lane == 0) { S[0] = a_len(C[0]); Pd[0] = 0; } __syncwarp();
+  i32 M = 0; u32 Mi = 0;
+  for (u32 i = 1; i < n; i++) {
+    u64 av = C[i]; i32 aq = a_q(av), al = a_len(av), at = a_t(av); i32 bs = -1, bj = -1; i32 cnt = 0; bool stop = false;
+    for (i32 top = (i32)i - 1; top >= 0 && !stop; top -= 32) {
+      i32 j = top - lane; bool nonskip = false; i32 bq = 0, bl = 0, bt = 0;
+      if (j >= 0) { u64 bv = C[j]; bq = a_q(bv); bl = a_len(bv); bt = a_t(bv); nonskip = !(bq == aq || bt > at); }
+      u32 bal = __ballot_sync(FULLMASK, nonskip); i32 mycnt = cnt + __popc(bal & ((2u << lane) - 1));   // inclusive count in descending-j order
+      bool brk = nonskip && !((aq - bq - bl) <= P.band_base || mycnt <= P.band_count);
+      u32 bb = __ballot_sync(FULLMASK, brk); int firstBrk = bb ? (__ffs(bb) - 1) : 32; if (bb) stop = true;
+      i32 s = -1; bool valid = nonskip && lane < firstBrk;
+      if (valid) { i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > P.max_gap) valid = false; else s = S[j] + bl - g; }
+      i32 rs = valid ? s : INT32_MIN, rj = valid ? j : INT32_MAX;
+      for (int o = 16; o; o >>= 1) { i32 os = __shfl_xor_sync(FULLMASK, rs, o), oj = __shfl_xor_sync(FULLMASK, rj, o); if (os > rs || (os == rs && oj < rj)) { rs = os; rj = oj; } }
+      if (rj != INT32_MAX && rs >= bs) { bs = rs; bj = rj; }     // s >= m: later (smaller j) wins ties
+      cnt += __popc(bal);
+    }
+    i32 m = al; u32 mj = i; if (bj >= 0 && bs >= al) { m = bs; mj = (u32)bj; }
+    if (lane == 0) { S[i] = m; Pd[i] = mj; } if (m > M) { M = m; Mi = i; }
+    __syncwarp();
+  }
+  if (M < P.min_score) return;
+  // ---- chainARegion, recursion -> explicit stack (right region first, then left)
+  i32 sp = 0; if (lane == 0) ST[0] = ((u64)0 << 32) | n; __syncwarp(); sp = 1; bool top_level = true;
+  while (sp > 0) {
+    sp--; u64 e = ST[sp]; i32 rlo = (i32)(e >> 32), rhi = (i32)(e & 0xffffffffu); i32 len = rhi - rlo; i32 mi;
+    if (top_level) { mi = (i32)Mi; top_level = false; }
+    else { i32 bm = 0, bi = INT32_MAX; for (i32 x = rlo + lane; x < rhi; x += 32) { i32 v = S[x]; if (v > bm) { bm = v; bi = x; } }
+      for (int o = 16; o; o >>= 1) { i32 om = __shfl_xor_sync(FULLMASK, bm, o), oi = __shfl_xor_sync(FULLMASK, bi, o); if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; } }
+      if (bm < P.min_score || bi == INT32_MAX) continue; mi = bi - rlo; }
+    i32 nMatched = 0, nAQ = 0, nAT = 0, i = mi, j = 0, qb = 0, qe = 0, tb = 0, te = 0, beginOfNext = 0, nAnch = 0; bool firstA = true;
+    for (;;) { j = (i32)Pd[rlo + i] - rlo; if (j < 0) break; u64 sv = C[rlo + i]; i32 sq = a_q(sv), sl = a_len(sv), stt = a_t(sv); nAnch++;
+      if (firstA) { firstA = false; qe = sq + sl - 1; te = stt + sl - 1; qb = sq; tb = stt; nMatched += sl; } else { qb = sq; tb = stt; if (sq + sl - 1 >= beginOfNext) nMatched += beginOfNext - sq; else nMatched += sl; }
+      beginOfNext = sq;
+      if (i == j) { nAQ += qe - qb + 1; if (nAQ < P.min_align_len) break; nAT += te - tb + 1; double pid = (double)nMatched / (double)max(nAQ, nAT) * 100; if (pid < 15.0) break; emit(qb, qe, tb, te, nAQ, nAT, nMatched, nAnch); break; }
+      i = j; }
+    if (j < 0 && nAnch > 0) { nAQ += qe - qb + 1; nAT += te - tb + 1; if (nAQ >= P.min_align_len) { double pid = (double)nMatched / (double)max(nAQ, nAT) * 100; if (pid >= 15.0) emit(qb, qe, tb, te, nAQ, nAT, nMatched, nAnch); } }
+    __syncwarp();
+    if (i > 0) { if (lane == 0) ST[sp] = ((u64)(u32)rlo << 32) | (u32)(rlo + i); sp++; }                 // left, processed after the right region
+    if (mi != len - 1) { if (lane == 0) ST[sp] = ((u64)(u32)(rlo + mi + 1) << 32) | (u32)rhi; sp++; }   // right
+    __syncwarp();
+  }
+}
+
+// =====================================================================================================
+// K5: flank extension (extendMatch/_extendRight lib-index-search-util.go:34-201, Chainer3 lib-chaining3.go:111-299)
+//     and wavefront alignment (github.com/shenwei356/wfa v0.5.0 Align; penalties 4/6/2, end-to-end, WFA2 backtrace priorities)
+// =====================================================================================================
+struct HspJob {          // one Chain2Result to align (host-built, lib-index-search.go:2223-2255 / :2490-2522)
+  u32 q, g; i32 tBegin, tEnd; u32 rc; i32 qlen, tlen;          // window: target = genome[tBegin..tEnd] (reverse-complemented when rc), length tlen
+  i32 start1, end1, start2, end2;                              // query [start1,end1) and window [start2,end2) before extension
+  i32 ext, tb_arg, max_ext;                                    // _extLen2, c.TBegin, c.MaxExtLen
+};
+struct ExtOut { i32 s1, e1, s2, e2; i32 qs, qe, ts, te; };     // extension lengths and final half-open segments
+
+struct SeqView { const u8* q2; const u8* g2; i32 tBegin, tEnd; u32 rc; const u8* qm; };
+__device__ __forceinline__ u32 qcmp(const SeqView& v, i32 i) { return get_base(v.q2, (u64)i) | (((u32)(v.qm[i >> 3] >> (i & 7)) & 1u) << 2); }   // 4..7 = never equal to a target base
+__device__ __forceinline__ u32 qbase(const SeqView& v, i32 i) { return get_base(v.q2, (u64)i); }
+__device__ __forceinline__ u32 tbase(const SeqView& v, i32 i) { return win_base(v.g2, v.tBegin, v.tEnd, v.rc, i); }
+
+// number of equal 2-mer pairs between q[qa..qa+n1) and t[ta..ta+n2) (dirq/dirt = +1 forward, -1 reversed flank)
+__device__ u32 ext_count(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt) {
+  if (n1 < 2 || n2 < 2) return 0; u32 c1[16], c2[16]; for (int i = 0; i < 16; i++) c1[i] = c2[i] = 0;
+  for (i32 i = 0; i + 1 < n1; i++) c1[(qbase(v, qa + dq * i) << 2) | qbase(v, qa + dq * (i + 1))]++;
+  for (i32 i = 0; i + 1 < n2; i++) c2[(tbase(v, ta + dt * i) << 2) | tbase(v, ta + dt * (i + 1))]++;
+  u32 t = 0; for (int i = 0; i < 16; i++) t += c1[i] * c2[i]; return t;
+}
+// _extendRight: anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10, BandCount 20), best chain end + 1
+__device__ void ext_run(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i32* __restrict__ sc, u16* __restrict__ pj, i32* e1, i32* e2) {
+  *e1 = *e2 = 0; if (n1 < 2 || n2 < 2) return; u32 n = 0;
+  for (i32 i1 = 0; i1 + 1 < n1; i1++) { u32 c = (qbase(v, qa + dq * i1) << 2) | qbase(v, qa + dq * (i1 + 1)); for (i32 i2 = 0; i2 + 1 < n2; i2++) if (((tbase(v, ta + dt * i2) << 2) | tbase(v, ta + dt * (i2 + 1))) == c) anc[n++] = (u16)((i1 << 8) | i2); }
+  if (n == 0) return;
+  i32 M = 0; u32 Mi = 0;
+  for (u32 i = 0; i < n; i++) { i32 aq = anc[i] >> 8, at = anc[i] & 255; i32 m = 2 - max(aq, at) - abs(aq - at); u32 mj = i; i32 cnt = 0;   // Len - distance2(origin) - gap2(origin)
+    for (i32 j = (i32)i - 1; j >= 0; j--) { i32 bq = anc[j] >> 8, bt = anc[j] & 255; if (bq == aq || bt > at) continue; cnt++; if (!((aq - bq - 2) <= 10 || cnt <= 20)) break;
+      i32 d = max(abs(aq - bq), abs(at - bt)); if (d > 10) continue; i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > 5) continue; i32 s = sc[j] + 2 - d - g; if (s >= m) { m = s; mj = (u32)j; } }
+    sc[i] = m; pj[i] = (u16)mj; if (i >= 1 && m > M) { M = m; Mi = i; } }
+  if (M < 1) return;
+  i32 i = (i32)Mi, nMatched = 0, beginOfNext = 0, qb = 0, qe = 0, tb = 0, te = 0; bool firstA = true;
+  for (;;) { i32 j = pj[i]; i32 sq = anc[i] >> 8, stt = anc[i] & 255;
+    if (firstA) { firstA = false; qe = sq + 1; te = stt + 1; qb = sq; tb = stt; nMatched += 2; } else { qb = sq; tb = stt; if (sq + 1 >= beginOfNext) nMatched += beginOfNext - sq; else nMatched += 2; }
+    beginOfNext = sq;
+    if (i == j) { i32 nAQ = qe - qb + 1; if (nAQ < 2) return; i32 nAT = te - tb + 1; double pid = (double)nMatched / (double)max(nAQ, nAT) * 100; if (pid < 15.0) return; *e1 = qe + 1; *e2 = te + 1; return; }
+    i = j; }
+}
+__device__ __forceinline__ void ext_sides(const HspJob& J, i32* rext, i32* lext) {   // extension lengths for the 3' and 5' sides (0 = no attempt)
+  *rext = 0; *lext = 0;
+  if (J.end1 + 2 < J.qlen && J.end2 + 2 < J.tlen) { i32 e = J.rc ? min(J.ext, J.tb_arg) : min(J.ext, J.max_ext); if (e > 2) *rext = e; }
+  if (J.start1 > 2 && J.start2 > 2) { i32 e = J.rc ? min(J.ext, J.max_ext) : min(J.ext, J.tb_arg); if (e > 2) *lext = e; }
+}
+// one thread per (job, side). COUNT: scratch sizes; else run.
+template <bool COUNT>
+__global__ void k_extend(const HspJob* __restrict__ jobs, u32 njobs, const u8* __restrict__ qpacked, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
+                         u32* __restrict__ counts, const u64* __restrict__ soff, u16* __restrict__ anc, i32* __restrict__ sc, u16* __restrict__ pj, i32* __restrict__ res /*2 per (job,side)*/) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs * 2) return; u32 jb = t >> 1; int side = t & 1; HspJob J = jobs[jb];
+  SeqView v; v.q2 = qpacked + qboff[J.q]; v.qm = nullptr; v.g2 = g2bit + g_off[J.g]; v.tBegin = J.tBegin; v.tEnd = J.tEnd; v.rc = J.rc;
+  i32 rext, lext; ext_sides(J, &rext, &lext); i32 qa, n1, ta, n2; int d;
+  if (side == 0) { if (!rext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } qa = J.end1; n1 = min(J.end1 + rext, J.qlen) - J.end1; ta = J.end2; n2 = min(J.end2 + rext, J.tlen) - J.end2; d = 1; }
+  else { if (!lext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } i32 s1 = max(J.start1 - lext, 0), s2 = max(J.start2 - lext, 0); qa = J.start1 - 1; n1 = J.start1 - s1; ta = J.start2 - 1; n2 = J.start2 - s2; d = -1; }
+  if (COUNT) { counts[t] = ext_count(v, qa, n1, d, ta, n2, d); }
+  else { u64 o = soff[t]; i32 e1, e2; ext_run(v, qa, n1, d, ta, n2, d, anc + o, sc + o, pj + o, &e1, &e2); res[2 * t] = e1; res[2 * t + 1] = e2; }
+}
+__global__ void k_extend_final(const HspJob* __restrict__ jobs, u32 njobs, const i32* __restrict__ res, ExtOut* __restrict__ out) {
+  u32 jb = blockIdx.x * blockDim.x + threadIdx.x; if (jb >= njobs) return; HspJob J = jobs[jb]; ExtOut o; o.e1 = res[4 * jb]; o.e2 = res[4 * jb + 1]; o.s1 = res[4 * jb + 2]; o.s2 = res[4 * jb + 3];
+  i32 start1 = J.start1, end1 = J.end1, start2 = J.start2, end2 = J.end2;
+  if (o.e1 > 0 || o.e2 > 0) { end1 += o.e1; end2 += o.e2; } if (o.s1 > 0 || o.s2 > 0) { start1 -= o.s1; start2 -= o.s2; }
+  if (start1 < 0 || start2 < 0) { start1 = J.start1; start2 = J.start2; } if (end1 > J.qlen || end2 > J.tlen) { end1 = J.end1; end2 = J.end2; }
+  o.qs = start1; o.qe = end1; o.ts = start2; o.te = end2; out[jb] = o;
+}
+
+// ---------------- WFA
+#define WF_NULL (-1073741824)
+struct WfaOut { i32 qbegin, qend, tbegin, tend, alen, matches, gaps, bscore, has_m, wscore, status; u32 ops_n; u64 ops_off; };   // status 0 ok, 1 workspace overflow
+struct WfDir { i32 lo, hi; u32 base; u32 nullmask; };   // nullmask bit0 M, bit1 I, bit2 D null; base = index of M offsets; I at base+w, D at base+2w
+
+// One warp per alignment; persistent warps pull jobs from a queue. Wavefront offsets live in a per-warp HBM slab
+// (directory + offsets), lanes own diagonals, extension compares bases straight from the 2-bit genome / query arrays.
+__global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 njobs, u32* __restrict__ next_job,
+                                             const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
+                                             i32* __restrict__ slabs, u64 slab_words, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+  const int X = 4, OE = 8, E = 2, STEP = 2; int lane = threadIdx.x & 31; u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i32* slab = slabs + (u64)warp * slab_words;
+  for (;;) {
+    u32 ji = 0; if (lane == 0) ji = atomicAdd(next_job, 1u); ji = __shfl_sync(FULLMASK, ji, 0); if (ji >= njobs) return; u32 jb = job_ids[ji];
+    HspJob J = jobs[jb]; ExtOut ex = ext[jb]; SeqView v; v.q2 = qpacked + qboff[J.q]; v.qm = qamask + qboff[J.q]; v.g2 = g2bit + g_off[J.g]; v.tBegin = J.tBegin; v.tEnd = J.tEnd; v.rc = J.rc;
+    const i32 q0 = ex.qs, t0 = ex.ts, plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen;
+    WfaOut R; R.qbegin = R.qend = R.tbegin = R.tend = R.alen = R.matches = R.gaps = R.bscore = R.has_m = 0; R.wscore = 0; R.status = 0; R.ops_n = 0; R.ops_off = 0;
+    // slab layout: [directory: ndir x 4 words][offsets ...]
+    const u32 ndir = (u32)((4 * (i64)max(plen, tlen) + 16) / STEP + 2); WfDir* dir = (WfDir*)slab; u64 used = (u64)ndir * 4; bool overflow = used + 64 > slab_words;
+    i32* offs = slab;
+    auto extend = [&](i32 k, i32 h) { i32 vv = h - k; while (vv < plen && h < tlen && qcmp(v, q0 + vv) == tbase(v, t0 + h)) { vv++; h++; } return h; };
+    auto getw = [&](i32 sidx, int comp, i32 k) -> i32 { if (sidx < 0) return WF_NULL; WfDir d = dir[sidx]; if ((d.nullmask >> comp) & 1) return WF_NULL; if (k < d.lo || k > d.hi) return WF_NULL; return offs[d.base + (u32)comp * (u32)(d.hi - d.lo + 1) + (u32)(k - d.lo)]; };
+    i32 s = 0; bool done = false;
+    if (!overflow) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = 0; d.base = (u32)used; d.nullmask = 6; dir[0] = d; offs[used] = extend(0, 0); } used += 3; __syncwarp(); done = (getw(0, 0, kend) >= tlen); }
+    while (!done && !overflow) {
+      s += STEP; i32 si = s / STEP; if ((u32)si >= ndir) { overflow = true; break; }
+      i32 ix = (s - X) / STEP, io = (s - OE) / STEP, ie = (s - E) / STEP; bool hx = s - X >= 0, ho = s - OE >= 0, he = s - E >= 0;
+      WfDir dx, dop, de; dx.nullmask = 7; dop.nullmask = 7; de.nullmask = 7; dx.lo = dx.hi = dop.lo = dop.hi = de.lo = de.hi = 0; if (hx) dx = dir[ix]; if (ho) dop = dir[io]; if (he) de = dir[ie];
+      bool nx = dx.nullmask & 1, no = dop.nullmask & 1, ni = (de.nullmask >> 1) & 1, nd = (de.nullmask >> 2) & 1;
+      if (nx && no && ni && nd) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = -1; d.base = 0; d.nullmask = 7; dir[si] = d; } __syncwarp(); continue; }
+      i32 lo = INT32_MAX, hi = INT32_MIN; if (!nx) { lo = min(lo, dx.lo); hi = max(hi, dx.hi); } if (!no) { lo = min(lo, dop.lo - 1); hi = max(hi, dop.hi + 1); } if (!ni || !nd) { lo = min(lo, de.lo - 1); hi = max(hi, de.hi + 1); }
+      u32 w = (u32)(hi - lo + 1); if (used + 3ull * w + 64 > slab_words) { overflow = true; break; }
+      u32 base = (u32)used; bool anyM = false, anyI = false, anyD = false;
+      for (i32 k = lo + lane; k <= hi; k += 32) {
+        i32 a = getw(io, 0, k - 1), b2 = getw(ie, 1, k - 1); i32 ins = max(a, b2); ins = (ins <= WF_NULL) ? WF_NULL : ins + 1;
+        a = getw(io, 0, k + 1); b2 = getw(ie, 2, k + 1); i32 del = max(a, b2);
+        i32 mis = getw(ix, 0, k); mis = (mis <= WF_NULL) ? WF_NULL : mis + 1;
+        if (!(ins > WF_NULL && ins >= 0 && ins - k >= 0 && ins <= tlen && ins - k <= plen)) ins = WF_NULL;
+        if (!(del > WF_NULL && del >= 0 && del - k >= 0 && del <= tlen && del - k <= plen)) del = WF_NULL;
+        if (!(mis > WF_NULL && mis >= 0 && mis - k >= 0 && mis <= tlen && mis - k <= plen)) mis = WF_NULL;
+        i32 mm = max(mis, max(ins, del)); if (mm > WF_NULL) { mm = extend(k, mm); anyM = true; } anyI |= ins > WF_NULL; anyD |= del > WF_NULL;
+        offs[base + (u32)(k - lo)] = mm; offs[base + w + (u32)(k - lo)] = ins; offs[base + 2 * w + (u32)(k - lo)] = del;
+      }
+      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD);
+      if (lane == 0) { WfDir d; d.lo = lo; d.hi = hi; d.base = base; d.nullmask = (anyM ? 0 : 1) | (anyI ? 0 : 2) | (anyD ? 0 : 4); dir[si] = d; }
+      used += 3ull * w; __syncwarp();
+      done = (getw(si, 0, kend) >= tlen);
+    }
+    if (overflow) { if (lane == 0) { R.status = 1; outs[jb] = R; } __syncwarp(); continue; }
+    // ---- backtrace (lane 0): WFA2 priority mismatch(9) > D ext(6) > D open(5) > I ext(2) > I open(1); statistics over first-M..last-M
+    if (lane == 0) {
+      R.wscore = s; i32 k = kend, off = tlen, sc = s; int mat = 0; i32 vv = off - k, h = off; u64* ops = (u64*)(slab + ((used + 1) & ~1ull)); u64 ops_room = (slab_words - ((used + 1) & ~1ull)) / 2; u32 nops = 0; bool ops_over = false;
+      int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
+      auto flush = [&]() { if (want_ops && curn) { if (nops < ops_room) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
+      auto put = [&](int op, i32 cntp, i32 vend, i32 hend) {   // op run of cntp ending (exclusive) at query vend / target hend
+        if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
+        if (op == 'M') { if (R.has_m) { R.alen += p_alen; R.gaps += p_gaps; R.bscore += p_bs; } else { R.has_m = 1; R.qend = vend; R.tend = hend; } p_alen = p_gaps = p_bs = 0; R.alen += cntp; R.matches += cntp; R.bscore += 2 * cntp; R.qbegin = vend - cntp + 1; R.tbegin = hend - cntp + 1; }
+        else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; }
+        prev = op; };
+      while (vv > 0 && h > 0 && sc > 0) {
+        i32 s_mis = sc - X, s_open = sc - OE, s_ext = sc - E; i64 c_mis = INT64_MIN, c_io = INT64_MIN, c_ie = INT64_MIN, c_do = INT64_MIN, c_de = INT64_MIN;
+        auto pig = [](i32 o, int type) -> i64 { return o <= WF_NULL ? INT64_MIN : (((i64)o << 4) | type); };
+        if (mat == 0) { i32 o = (s_mis >= 0) ? getw(s_mis / STEP, 0, k) : WF_NULL; c_mis = pig(o <= WF_NULL ? WF_NULL : o + 1, 9); }
+        if (mat == 0 || mat == 1) { i32 o = (s_open >= 0) ? getw(s_open / STEP, 0, k - 1) : WF_NULL; c_io = pig(o <= WF_NULL ? WF_NULL : o + 1, 1); o = (s_ext >= 0) ? getw(s_ext / STEP, 1, k - 1) : WF_NULL; c_ie = pig(o <= WF_NULL ? WF_NULL : o + 1, 2); }
+        if (mat == 0 || mat == 2) { c_do = pig((s_open >= 0) ? getw(s_open / STEP, 0, k + 1) : WF_NULL, 5); c_de = pig((s_ext >= 0) ? getw(s_ext / STEP, 2, k + 1) : WF_NULL, 6); }
+        i64 best = max(c_mis, max(max(c_io, c_ie), max(c_do, c_de))); if (best == INT64_MIN) { R.status = 2; break; }
+        if (mat == 0) { i32 mo = (i32)(best >> 4); i32 nm = off - mo; put('M', nm, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
+        int type = (int)(best & 15);
+        switch (type) { case 9: sc = s_mis; mat = 0; put('X', 1, off - k, off); off--; break;
+          case 1: sc = s_open; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: sc = s_ext; mat = 1; put('I', 1, off - k, off); k--; off--; break;
+          case 5: sc = s_open; mat = 0; put('D', 1, off - k, off); k++; break; case 6: sc = s_ext; mat = 2; put('D', 1, off - k, off); k++; break; }
+        vv = off - k; h = off;
+      }
+      if (R.status == 0) { if (sc == 0) put('M', off, off - k, off); else { if (vv > 0) put('D', vv, vv, h); if (h > 0) put('I', h, 0, h); } }
+      flush();
+      if (want_ops && R.status == 0) { if (ops_over) R.status = 1; else { u64 o = atomicAdd((unsigned long long*)ops_cursor, (unsigned long long)nops); if (o + nops <= ops_cap) { for (u32 i = 0; i < nops; i++) ops_pool[o + i] = ops[i]; R.ops_off = o; R.ops_n = nops; } else R.status = 3; } }
+      outs[jb] = R;
+    }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================================
+// host orchestration of K4/K5 + finishing (lib-index-search.go:1834-2932)
+// =====================================================================================================
+struct StageTimer { cudaEvent_t ev[10]; cudaStream_t st; int n = 0; StageTimer(cudaStream_t s) : st(s) { for (auto& e : ev) cudaEventCreate(&e); } ~StageTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+  void mark() { cudaEventRecord(ev[n++], st); } float ms(int a, int b) { float f = 0; cudaEventElapsedTime(&f, ev[a], ev[b]); return f; } };
+
+static void build_tree_tables(lmg_index* ix, QBatch& B, DBuf<u64>& tkeys, DBuf<u32>& tvals, DBuf<u32>& toff) {
+  cudaStream_t st = ix->st; u64 n = B.total_k; toff.alloc(B.nq + 2, st); if (n == 0) { toff.zero(); tkeys.alloc(2, st); tvals.alloc(2, st); return; }
+  DBuf<u32> flags(n + 1, st), pos(n + 1, st); k_tree_flags<<<cdiv((i64)n, 256), 256, 0, st>>>(B.qvals.p, n, flags.p); KERNEL_CHECK(); CUDA_CHECK(cudaMemsetAsync(flags.p + n, 0, 4, st));
+  size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, flags.p, pos.p, (int)(n + 1), st); cub::DeviceScan::ExclusiveSum(ix->tmp.get(tb), tb, flags.p, pos.p, (int)(n + 1), st); CUB_CHECK();
+  u32 total; CUDA_CHECK(cudaMemcpyAsync(&total, pos.p + n, 4, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st));
+  tkeys.alloc((u64)total + 2, st); tvals.alloc((u64)total + 2, st); k_tree_scatter<<<cdiv((i64)n, 256), 256, 0, st>>>(B.qkeys.p, B.qvals.p, pos.p, n, tkeys.p, tvals.p); KERNEL_CHECK();
+  k_tree_offsets<<<cdiv(B.nq + 1, 128), 128, 0, st>>>(pos.p, B.koff.p, B.nq, n, total, toff.p); KERNEL_CHECK(); CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+struct HostHsp { i32 qb, qe, tb, te, aligned_q, tpo, max_ext; int job = -1; bool dead = false; i32 alen = 0, matched = 0, gaps = 0, score = 0, bitscore = 0; double evalue = 0, af = 0, pident = 0; std::string cigar; };
+struct HostCluster { u32 seg; u32 item; bool rc, variantA; int nseeds, iseq; std::vector<HostHsp> hsps; double sim = 0; bool has = false; };
+
+struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<std::string> seqids; };
+
+static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
+  cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
+  QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
+  sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); T.mark();   // [1] sketch
+  Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); T.mark();              // [2] probe
+  Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); T.mark();                // [3] chain
+  for (int i = 0; i < 8; i++) ix->ms[i] = 0;
+  auto finish_times = [&](int upto) { const int map_[6] = {0, 1, 2, 3, 4, 5}; (void)map_; CUDA_CHECK(cudaStreamSynchronize(st)); for (int i = 0; i < upto; i++) ix->ms[i] = T.ms(i, i + 1); ix->ms[7] = T.ms(0, upto); ix->counters[6] = B.total_bases; ix->counters[7] = (u64)B.nq; };
+  if (Cn.n == 0) { T.mark(); finish_times(4); return; }
+  // ---- windows (lib-index-search.go:1987-2051)
+  const int K = I.k, extLen = prm->ext_len; std::vector<WinItem> items(Cn.n);
+  for (u32 c = 0; c < Cn.n; c++) { const ChainRec& r = Cn.h[c]; u64 key = S.h_key[r.seg]; WinItem w; w.q = (u32)(key >> 36); w.g = (u32)((key >> 2) & 0x3FFFFFFFFull); w.chain = c;
+    i32 qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); i32 qb = r.q0, tb = r.t0, qe = r.q1 + r.len1 - 1, te = r.t1 + r.len1 - 1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1;
+    bool rc = (r.nseeds == 1) ? (qrc != trc) : (tb > r.t1); i32 tBegin, tEnd;
+    if (rc) { tBegin = r.t1 - extLen; if (tBegin < 0) tBegin = 0; tEnd = tb + r.len1 - 1 + extLen; } else { tBegin = tb - extLen; if (tBegin < 0) tBegin = 0; tEnd = te + extLen; }
+    w.qBegin = qb - std::min(qb, extLen); w.qEnd = qe + std::min(qlen - qe - 1, extLen);
+    i32 nBases = (i32)I.seq_sizes[w.g].size() ? 0 : 0; (void)nBases; i32 nb = 0; { const auto& ss = I.seq_sizes[w.g]; i64 t = 0; for (size_t x = 0; x < ss.size(); x++) t += ss[x]; t += (i64)(ss.size() - 1) * I.contig_interval; nb = (i32)t; }
+    i32 start = std::max(tBegin, 0), end = tEnd; if (end >= nb - 1) end = nb - 1; if (end < start) end = start; i32 sl = end - start + 1; if (sl < tEnd - tBegin + 1) tEnd -= tEnd - tBegin + 1 - sl;   // SubSeq3 clamp + :2045-2047
+    w.tBegin = tBegin; w.tEnd = tEnd; w.W = sl; w.rc = rc; w.mp = 11 + (sl >= 1000000 ? 8 : sl >= 250000 ? 6 : sl >= 50000 ? 4 : sl >= 10000 ? 2 : 0); items[c] = w; }
+  u32 nit = Cn.n; DBuf<WinItem> d_items(nit, st); d_items.from_host(items.data(), nit);
+  DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff);
+  // ---- K4 anchors: count, scan, emit, per-window sort
+  DBuf<u32> cnt(nit + 1, st); k_pa_anchors<false><<<nit, 128, 0, st>>>(d_items.p, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, cnt.p, nullptr, nullptr); KERNEL_CHECK();
+  std::vector<u32> hcnt = cnt.to_host(nit); std::vector<u64> haoff(nit + 1, 0); for (u32 i = 0; i < nit; i++) haoff[i + 1] = haoff[i] + hcnt[i]; u64 NA = haoff[nit];
+  std::vector<C2Rec> c2;
+  if (NA > 0) {
+    if (NA >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchors in one batch; use smaller batches");
+    DBuf<u64> aoff(nit + 1, st); aoff.from_host(haoff.data(), nit + 1); DBuf<u64> lo0(NA, st), lo1(NA, st);
+    k_pa_anchors<true><<<nit, 128, 0, st>>>(d_items.p, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, nullptr, aoff.p, lo0.p); KERNEL_CHECK();
+    { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)NA, (int)nit, aoff.p, aoff.p + 1, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)NA, (int)nit, aoff.p, aoff.p + 1, st); CUB_CHECK(); }
+    Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
+    DBuf<i32> sc(NA, st); DBuf<u32> pred(NA, st); DBuf<u64> stack(NA, st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
+    k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, aoff.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK();
+    u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
+    std::sort(c2.begin(), c2.end(), [](const C2Rec& a, const C2Rec& b) { if (a.item != b.item) return a.item < b.item; if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
+  }
+  tkeys.free(); tvals.free(); T.mark();                                                                  // [4] pseudo-align
+  if (c2.empty()) { T.mark(); finish_times(5); return; }
+  // ---- contig mapping, clusters, jobs (lib-index-search.go:2083-2469) — host, sequential per (query, genome)
+  std::vector<HostCluster> clusters; std::vector<HspJob> jobs; size_t ci = 0; const int contigInterval = I.contig_interval;
+  { u32 c = 0; while (c < nit) { u32 seg = Cn.h[c].seg; u32 cEnd = c; while (cEnd < nit && Cn.h[cEnd].seg == seg) cEnd++;
+      std::set<std::array<int, 6>> keys; int iSeq = 0, iSeqPre = -1;
+      for (u32 it = c; it < cEnd; it++) { const WinItem& w = items[it]; const auto& SS = I.seq_sizes[w.g]; const int numSeqs = (int)SS.size(); const bool rc = w.rc; const i32 tBegin = w.tBegin, tEnd = w.tEnd, tlenSeq = w.W;
+        size_t c0 = ci; while (ci < c2.size() && c2[ci].item == it) ci++; if (ci == c0) continue;
+        iSeqPre = -1; HostCluster cur; cur.seg = seg; cur.item = it; cur.rc = rc; cur.nseeds = Cn.h[it].nseeds; cur.variantA = false; cur.iseq = 0;
+        auto convert = [&](HostHsp& h, const C2Rec& r, int tpo, int iS) { h.qb = r.qb; h.qe = r.qe; h.aligned_q = r.aligned_q; h.tpo = tpo;
+          if (rc) { h.tb = tBegin - tpo + (tlenSeq - r.te - 1); if (h.tb < 0) { h.qe += h.tb; h.aligned_q += h.tb; h.tb = 0; } h.te = tBegin - tpo + (tlenSeq - r.tb - 1); if (h.te > (i32)SS[iS] - 1) { h.qb += h.te - ((i32)SS[iS] - 1); h.te = (i32)SS[iS] - 1; } }
+          else { h.tb = tBegin - tpo + r.tb; if (h.tb < 0) { h.qb -= h.tb; h.aligned_q += h.tb; h.tb = 0; } h.te = tBegin - tpo + r.te; if (h.te > (i32)SS[iS] - 1) { h.qe -= h.te - ((i32)SS[iS] - 1); h.te = (i32)SS[iS] - 1; } }
+          h.max_ext = (i32)SS[iS] - 1 - h.te; };
+        auto flush = [&](bool variantA, int iS) { if (cur.hsps.empty()) return; cur.variantA = variantA; cur.iseq = iS; i32 qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]);
+          for (HostHsp& h : cur.hsps) { if (h.qb >= h.qe + 1) { h.dead = true; continue; } i32 start, end; if (rc) { start = tEnd - h.te - h.tpo; end = tEnd - h.tb - h.tpo + 1; } else { start = h.tpo + h.tb - tBegin; end = h.tpo + h.te - tBegin + 1; }
+            if (start >= end) { h.dead = true; continue; } if (start < 0 || end > tlenSeq || h.qb < 0 || h.qe + 1 > qlen) { h.dead = true; continue; }
+            int ext2 = prm->ext_len2; if (h.aligned_q > 1000000) ext2 += 80; else if (h.aligned_q > 250000) ext2 += 40; else if (h.aligned_q > 50000) ext2 += 20; else if (h.aligned_q > 10000) ext2 += 10;
+            HspJob J; J.q = w.q; J.g = w.g; J.tBegin = tBegin; J.tEnd = tEnd; J.rc = rc; J.qlen = qlen; J.tlen = tlenSeq; J.start1 = h.qb; J.end1 = h.qe + 1; J.start2 = start; J.end2 = end; J.ext = ext2; J.tb_arg = h.tb; J.max_ext = h.max_ext; h.job = (int)jobs.size(); jobs.push_back(J); }
+          clusters.push_back(cur); cur.hsps.clear(); };
+        for (size_t x = c0; x < ci; x++) { const C2Rec& r = c2[x]; iSeq = 0; int tpoB = 0, tpoE = 0;
+          if (numSeqs > 1) { iSeq = -1; int _b, _e; if (rc) { _b = tEnd - r.te + K; _e = tEnd - r.tb - K; } else { _b = tBegin + r.tb + K; _e = tBegin + r.te - K; }
+            if (_b >= _e) { if (rc) { _b = tEnd - r.te; _e = tEnd - r.tb; } else { _b = tBegin + r.tb; _e = tBegin + r.te; } }
+            for (int j = 0; j < numSeqs; j++) { int l = (int)SS[j]; tpoE += l - 1; if (_b + K >= tpoB && _e - K <= tpoE) { iSeq = j; break; } else if (_e < tpoB) { iSeq = -1; break; } tpoE += contigInterval + 1; tpoB = tpoE; }
+            if (iSeq < 0) continue;
+            if (iSeqPre >= 0 && iSeq != iSeqPre) { int iSeq0 = iSeq; iSeq = iSeqPre; HostHsp h; convert(h, r, tpoB, iSeq); flush(true, iSeq); iSeqPre = -1;
+              std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (!keys.count(key)) { cur.hsps.push_back(h); keys.insert(key); } iSeq = iSeq0; continue; } }
+          iSeqPre = iSeq; HostHsp h; convert(h, r, tpoB, iSeq); std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (!keys.count(key)) { cur.hsps.push_back(h); keys.insert(key); } }
+        if (iSeq >= 0) flush(false, iSeq); }
+      c = cEnd; } }
+  // ---- K5: extension + WFA
+  u32 nj = (u32)jobs.size(); std::vector<ExtOut> hext; std::vector<WfaOut> hw; std::vector<u64> hops;
+  if (nj) {
+    DBuf<HspJob> d_jobs(nj, st); d_jobs.from_host(jobs.data(), nj); DBuf<u32> ecnt(2 * (u64)nj + 1, st); DBuf<i32> eres(4 * (u64)nj, st);
+    k_extend<true><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p, nullptr, nullptr, nullptr, nullptr, nullptr); KERNEL_CHECK();
+    std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); std::vector<u64> hso(2 * (u64)nj + 1, 0); for (u64 i = 0; i < 2 * (u64)nj; i++) hso[i + 1] = hso[i] + hec[i]; u64 ES = hso.back();
+    DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i32> esc(ES + 2, st);
+    k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK();
+    DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
+    // WFA rounds with growing per-warp slabs
+    DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids(nj); std::iota(ids.begin(), ids.end(), 0u); hw.resize(nj);
+    u64 ops_cap = 0; if (prm->output_seq) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
+    size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
+    u64 slab_words = 1ull << 20;  // 4 MB per warp to start
+    for (int round = 0; round < 6 && !ids.empty(); round++) {
+      u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)ix->sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
+      if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
+      DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
+      k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, prm->output_seq); KERNEL_CHECK();
+      std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
+      ids.swap(again); slab_words *= 8;
+    }
+    if (!ids.empty()) throw std::runtime_error("WFA workspace exhausted after 6 rounds");
+    if (prm->output_seq) { u64 used = ops_cur.to_host()[0]; hops = ops_pool.to_host(used); }
+  }
+  T.mark();                                                                                              // [5] extend + wfa
+  // ---- finishing: scores, filters, ordering, rows (lib-index-search.go:2266-2357, :2701-2932; search.go:437-533)
+  const double lnK = std::log(0.41), totalBases = (double)I.total_bases;
+  for (HostCluster& cl : clusters) { i32 qlen = 0; if (!cl.hsps.empty()) { } const WinItem& w = items[cl.item]; qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); double maxSim = 0; bool has = false;
+    for (HostHsp& h : cl.hsps) { if (h.dead) continue; const WfaOut& o = hw[h.job]; const ExtOut& e = hext[h.job]; i32 ql = e.qe - e.qs, tl = e.te - e.ts;
+      if (!o.has_m) { h.dead = true; continue; }   // trimOps == nil -> evalue MaxFloat64 > max_evalue
+      int _s = o.bscore; if (_s & 1) _s--; double bs = (0.625 * (double)_s - lnK) / M_LN2; h.score = o.bscore; h.bitscore = (int)bs; h.evalue = totalBases * std::pow(2, -bs) * (double)ql; if (h.evalue > prm->max_evalue) { h.dead = true; continue; }
+      h.qb -= e.s1; h.qe += e.e1; h.qb = h.qb + o.qbegin - 1; h.qe = h.qe - (ql - o.qend);
+      if (cl.rc) { h.tb -= e.e2; h.te += e.s2; h.tb = h.tb + (tl - o.tend); h.te = cl.variantA ? (h.te - o.tbegin - 1) : (h.te - (o.tbegin - 1)); } else { h.tb -= e.s2; h.te += e.e2; h.tb = h.tb + o.tbegin - 1; h.te = h.te - (tl - o.tend); }
+      h.aligned_q = h.qe - h.qb + 1; h.alen = o.alen; h.matched = o.matches; h.gaps = o.gaps; h.af = (double)h.aligned_q / (double)qlen * 100; if (h.af > 100) h.af = 100; h.pident = (double)h.matched / (double)o.alen * 100;
+      if (h.af < prm->min_qcov_hsp || h.pident < prm->min_pident) { h.dead = true; continue; }
+      if (prm->output_seq) { // ops were written last-op-first; trim to first M..last M; swap I/D for SAM (:2331-2338)
+        std::vector<u64> ops(hops.begin() + o.ops_off, hops.begin() + o.ops_off + o.ops_n); std::reverse(ops.begin(), ops.end()); int a = -1, b = -1; for (size_t i = 0; i < ops.size(); i++) if ((ops[i] >> 32) == 'M') { if (a < 0) a = (int)i; b = (int)i; }
+        for (int i = a; i >= 0 && i <= b; i++) { char c = (char)(ops[i] >> 32); if (c == 'D') c = 'I'; else if (c == 'I') c = 'D'; h.cigar += std::to_string((u32)(ops[i] & 0xffffffffu)); h.cigar.push_back(c); } }
+      double sim = (double)h.bitscore * h.pident; if (sim > maxSim) maxSim = sim; has = true; }
+    cl.has = has; cl.sim = maxSim; }
+  // group clusters per segment -> genomes -> queries
+  struct GenomeOut { u32 seg; std::vector<const HostCluster*> sds; double af; };
+  std::vector<GenomeOut> gouts; { size_t x = 0; while (x < clusters.size()) { u32 seg = clusters[x].seg; GenomeOut g; g.seg = seg; g.af = 0; size_t y = x; while (y < clusters.size() && clusters[y].seg == seg) { if (clusters[y].has) g.sds.push_back(&clusters[y]); y++; } x = y; if (g.sds.empty()) continue;
+      u32 q = (u32)(S.h_key[seg] >> 36); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
+      int cov = 0; if (reg.size() == 1) cov = reg[0][1] - reg[0][0] + 1; else if (!reg.empty()) { std::stable_sort(reg.begin(), reg.end(), [](const std::array<int, 2>& a, const std::array<int, 2>& b) { return a[0] < b[0]; }); int s0 = reg[0][0], e0 = reg[0][1]; for (size_t i = 1; i < reg.size(); i++) { if (reg[i][0] > e0) { cov += e0 - s0 + 1; s0 = reg[i][0]; e0 = reg[i][1]; continue; } if (reg[i][1] <= e0) continue; e0 = reg[i][1]; } cov += e0 - s0 + 1; }
+      g.af = (double)cov / (double)qlen * 100; if (g.af > 100) g.af = 100; if (g.af < prm->min_qcov_genome) continue;
+      std::stable_sort(g.sds.begin(), g.sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); gouts.push_back(std::move(g)); } }
+  { size_t x = 0; while (x < gouts.size()) { u32 q = (u32)(S.h_key[gouts[x].seg] >> 36); size_t y = x; while (y < gouts.size() && (u32)(S.h_key[gouts[y].seg] >> 36) == q) y++;
+      std::vector<GenomeOut*> rs; for (size_t z = x; z < y; z++) rs.push_back(&gouts[z]);
+      auto bgi_of = [&](const GenomeOut* g) { return I.genome_bgi[(u32)((S.h_key[g->seg] >> 2) & 0x3FFFFFFFFull)]; };
+      std::stable_sort(rs.begin(), rs.end(), [&](GenomeOut* a, GenomeOut* b) { return (bgi_of(a) & 131071) < (bgi_of(b) & 131071); });    // :1848-1853
+      std::stable_sort(rs.begin(), rs.end(), [](GenomeOut* a, GenomeOut* b) { return a->sds[0]->sim > b->sds[0]->sim; });                  // :2919-2921
+      for (GenomeOut* g : rs) { u32 gd = (u32)((S.h_key[g->seg] >> 2) & 0x3FFFFFFFFull);
+        std::vector<const HostCluster*> ord; std::vector<char> used(g->sds.size(), 0);   // SortBySeqID :1042-1096
+        for (size_t i = 0; i < g->sds.size(); i++) { if (used[i]) continue; for (size_t j = i; j < g->sds.size(); j++) if (!used[j] && g->sds[j]->iseq == g->sds[i]->iseq) { used[j] = 1; ord.push_back(g->sds[j]); } }
+        int cls = 1, j = 1; for (const HostCluster* sd : ord) { for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[gd].size(); r.chunk_idx = 0; r.n_chunks = 1; r.seq_len = (i32)I.seq_sizes[gd][sd->iseq];
+            r.cls = cls; r.hsp = j; r.qb = h.qb; r.qe = h.qe; r.tb = h.tb; r.te = h.te; r.rc = sd->rc; r.alen = h.alen; r.matches = h.matched; r.gaps = h.gaps; r.score = h.score; r.bitscore = h.bitscore; r.evalue = h.evalue; r.qcov_hsp = h.af; r.pident = h.pident; r.qcov_gnm = g->af;
+            r.cigar_off = R.pool.size(); r.cigar_len = (u32)h.cigar.size(); R.pool += h.cigar; R.rows.push_back(r); R.seqids.push_back(I.seq_ids[gd][sd->iseq]); j++; } cls++; } }
+      x = y; } }
+  T.mark(); finish_times(7);                                                                             // [6] finish (host)
 }
 
 // =====================================================================================================
@@ -383,7 +838,7 @@ int lmg_index_info(const lmg_index* ix, lmg_info* o) { const Image& I = ix->img;
 int lmg_genome_name(const lmg_index* ix, uint64_t genome, const char** name) { auto it = ix->img.bgi2dense.find(genome); if (it == ix->img.bgi2dense.end()) { *name = ""; return -1; } *name = ix->img.genome_names[it->second].c_str(); return 0; }
 void lmg_index_close(lmg_index* ix) { if (!ix) return; cudaSetDevice(ix->img.device); cudaStreamSynchronize(ix->st); ix->img.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } cudaStreamDestroy(ix->st); delete ix; }
 void lmg_free(void* p) { free(p); }
-int lmg_last_timing(const lmg_index* ix, double* ms8, uint64_t* c8) { for (int i = 0; i < 8; i++) { if (ms8) ms8[i] = ix->ms[i]; if (c8) c8[i] = ix->counters[i]; } return 0; }
+int lmg_last_timing(const lmg_index* ix, double* ms16, uint64_t* c16) { for (int i = 0; i < 16; i++) { if (ms16) ms16[i] = ix->ms[i]; if (c16) c16[i] = ix->counters[i]; } if (c16) c16[15] = g_launches; return 0; }
 
 int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* kmers, uint32_t* nlocs, uint32_t* minloc, uint64_t* suf, uint64_t suf_cap, uint64_t* n_suf) {
   try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
@@ -412,6 +867,45 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
       c.q0 = r.q0; c.t0 = r.t0; c.len0 = r.len0; c.q1 = r.q1; c.t1 = r.t1; c.len1 = r.len1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1; c.rc = (r.nseeds == 1) ? (qrc != trc) : (r.t0 > r.t1); }
     *out = o; *n_out = C.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
+
+#define LMG_HAVE_SEARCH 1
+int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
+  catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
+int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
+int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) { if (row >= r->seqids.size()) return -1; *seqid = r->seqids[row].c_str(); return 0; }
+void lmg_results_free(lmg_results* r) { delete r; }
+
+#define LMG_HAVE_WFA 1
+int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t n, char** cigars, uint64_t* cigars_len) {
+  try { CUDA_CHECK(cudaSetDevice(device)); cudaStream_t st = 0; std::vector<u8> qp, tp, qmk; std::vector<u64> qo(n + 1), to(n + 1); std::vector<HspJob> jobs(n); std::vector<ExtOut> ex(n);
+    auto pack = [](const u8* s, u64 len, std::vector<u8>& out) { while (out.size() & 15) out.push_back(0); u64 o = out.size(); out.resize(o + (len + 3) / 4 + 16, 0); for (u64 i = 0; i < len; i++) out[o + (i >> 2)] |= (u8)(base2bit(s[i]) << (6 - 2 * (i & 3))); return o; };
+    u64 opsCap = 0;
+    for (int i = 0; i < n; i++) { u64 ql = off[2 * i + 1] - off[2 * i], tl = off[2 * i + 2] - off[2 * i + 1]; qo[i] = pack(seqs + off[2 * i], ql, qp); qmk.resize(qp.size(), 0); for (u64 x = 0; x < ql; x++) { u8 c = seqs[off[2 * i] + x] & 0xDF; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) qmk[qo[i] + (x >> 3)] |= (u8)(1u << (x & 7)); } to[i] = pack(seqs + off[2 * i + 1], tl, tp);
+      HspJob J; memset(&J, 0, sizeof J); J.q = i; J.g = i; J.tBegin = 0; J.tEnd = (i32)tl - 1; J.rc = 0; J.qlen = (i32)ql; J.tlen = (i32)tl; jobs[i] = J; ExtOut e; memset(&e, 0, sizeof e); e.qs = 0; e.qe = (i32)ql; e.ts = 0; e.te = (i32)tl; ex[i] = e; opsCap += ql + tl + 4; }
+    qp.resize(qp.size() + 64, 0); tp.resize(tp.size() + 64, 0); qmk.resize(qp.size(), 0);
+    DBuf<u8> dq(qp.size(), st), dt(tp.size(), st), dqm(qmk.size(), st); dqm.from_host(qmk.data(), qmk.size()); dq.from_host(qp.data(), qp.size()); dt.from_host(tp.data(), tp.size()); DBuf<u64> dqo(n + 1, st), dto(n + 1, st); dqo.from_host(qo.data(), n + 1); dto.from_host(to.data(), n + 1);
+    DBuf<HspJob> dj(n, st); dj.from_host(jobs.data(), n); DBuf<ExtOut> de(n, st); de.from_host(ex.data(), n); DBuf<WfaOut> dout(n, st); DBuf<u64> pool(opsCap + 2, st), cur(1, st); cur.zero();
+    std::vector<u32> ids(n); std::iota(ids.begin(), ids.end(), 0u); std::vector<WfaOut> hw(n); u64 slab_words = 1ull << 18;
+    for (int round = 0; round < 6 && !ids.empty(); round++) { u32 m = (u32)ids.size(); u32 warps = std::max(4u, (std::min<u32>(1024, m) / 4) * 4); DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> dids(m, st); dids.from_host(ids.data(), m); DBuf<u32> next(1, st); next.zero();
+      k_wfa<<<warps / 4, 128, 0, st>>>(dj.p, de.p, dids.p, m, next.p, dq.p, dqm.p, dqo.p, dt.p, dto.p, slabs.p, slab_words, dout.p, pool.p, cur.p, opsCap, 1); KERNEL_CHECK();
+      std::vector<WfaOut> o = dout.to_host(n); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; } ids.swap(again); slab_words *= 8; }
+    if (!ids.empty()) throw std::runtime_error("WFA workspace exhausted");
+    std::vector<u64> ops = pool.to_host(cur.to_host()[0]); std::string out;
+    for (int i = 0; i < n; i++) { for (i64 x = (i64)hw[i].ops_n - 1; x >= 0; x--) { u64 op = ops[hw[i].ops_off + x]; out += std::to_string((u32)(op & 0xffffffffu)); out.push_back((char)(op >> 32)); } out.push_back('\n'); }
+    char* c = (char*)malloc(out.size() + 1); memcpy(c, out.data(), out.size() + 1); *cigars = c; *cigars_len = out.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
+
+struct lmg_queries { QBatch B; };
+int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_queries** out) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; upload_queries(ix, seqs, off, n, Q->B); CUDA_CHECK(cudaStreamSynchronize(ix->st)); *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+int lmg_search_staged(lmg_index* ix, const lmg_params* p, lmg_queries* q, lmg_results** out) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R; return 0; }
+  catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
+void lmg_queries_free(lmg_index* ix, lmg_queries* q) { if (!q) return; cudaSetDevice(ix->img.device); delete q; }
 }  // extern "C"
 
 // ---- not yet implemented entry points (fail loudly)

@@ -48,3 +48,56 @@ def test_chains_top_n(gpu_small, oracle_small, small_queries):
     gc = gpu_small.chains(seqs, gpu_small.default_params(**p))
     oc = oracle_small.chains(seqs, oracle_small.default_params(**p))
     assert gc.tobytes() == oc.tobytes()
+
+
+def _rows_equal(gr, orr, gs, os_, gc=None, oc=None):
+    assert len(gr) == len(orr), "row count differs: gpu %d oracle %d" % (len(gr), len(orr))
+    for f in gr.dtype.names:
+        if f in ("cigar_off", "pad", "pad0"):
+            continue
+        if gr.dtype[f].kind == "f":
+            assert np.array_equal(gr[f], orr[f]), "float column %s differs (must be bit-identical: same double ops on host)" % f
+        else:
+            assert np.array_equal(gr[f], orr[f]), "column %s differs" % f
+    assert gs == os_
+    if gc is not None:
+        assert gc == oc
+
+
+def test_search_rows_match_oracle(gpu_small, oracle_small, small_queries):
+    ids, seqs = small_queries
+    gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1))
+    orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
+    assert len(orr) > 50
+    _rows_equal(gr, orr, gs, os_, gc, oc)
+
+
+def test_search_filters_match_oracle(gpu_small, oracle_small, small_queries):
+    ids, seqs = small_queries
+    kw = dict(min_qcov_hsp=50.0, min_pident=80.0, min_qcov_genome=60.0, top_n_genomes=3, max_evalue=1e-20)
+    gr, gs, _ = gpu_small.search(seqs, gpu_small.default_params(**kw))
+    orr, os_, _ = oracle_small.search(seqs, oracle_small.default_params(**kw))
+    _rows_equal(gr, orr, gs, os_)
+
+
+def test_wfa_batch_matches_oracle(oracle_small):
+    import random
+    from lexicmap_b200.api import wfa_batch
+    rnd = random.Random(7)
+    pairs = []
+    for n in (1, 5, 40, 300, 1500):
+        for div in (0.0, 0.02, 0.1, 0.25):
+            q = "".join(rnd.choice("ACGT") for _ in range(n))
+            t = []
+            for c in q:
+                r = rnd.random()
+                if r < div / 3:
+                    continue
+                if r < 2 * div / 3:
+                    t.append(rnd.choice("ACGT"))
+                if r < div:
+                    c = rnd.choice("ACGT")
+                t.append(c)
+            pairs.append((q, "".join(t) or "A"))
+    pairs += [("ACGT", "TTTT"), ("A", "ACGTACGT"), ("ACGTACGTAA", "A"), ("AAAAAAAAAA", "AAAAA"), ("ACGTTTGACA" * 30, "ACGTTGACA" * 30)]
+    assert wfa_batch(pairs) == oracle_small.wfa(pairs)
