@@ -173,13 +173,14 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = int(idx.timing()[1][15])
-    ms_steps, stage_ms, probe_ms, nrows = [], np.zeros(8), [], 0
+    ms_steps, stage_ms, probe_ms, nrows, wall_ms, e2e_lib_ms, e2e_stage = [], np.zeros(8), [], 0, [], [], np.zeros(8)
     for _ in range(a.steps):
         nrows = idx.search_staged(staged, prm, collect=False)
         ms, cnt = idx.timing()
         ms_steps.append(ms[7])
         stage_ms += ms[:8]
         probe_ms.append(ms[8])
+        wall_ms.append(ms[9])
     sync_all()
     launches = (int(idx.timing()[1][15]) - launches0) // max(a.steps, 1)
     # ---- e2e leg: host buffers in, rows out, every step
@@ -190,6 +191,8 @@ def main():
         torch.cuda.synchronize()
         if i >= a.warmup:
             e2e_ms.append((time.perf_counter() - t) * 1e3)
+            e2e_lib_ms.append(idx.timing()[0][9])
+            e2e_stage += idx.timing()[0][:8]
     sampler.stop = True
     sampler.join(timeout=2)
     t_val = float(np.mean(ms_steps))
@@ -228,6 +231,7 @@ def main():
            "roofline": {"bound": "hbm", "kernel": "k_probe_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_probe * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},
+           "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage]},
            "clocks": sampler.summary()}
     print(json.dumps(out))
     idx.free_staged(staged)

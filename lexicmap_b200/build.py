@@ -48,7 +48,7 @@ def build_tools(force=False):
         _run([GXX, "-O3", "-march=x86-64-v3", "-fopenmp", "-std=c++17", src, "-o", TOOLS, "-lz"])
     cli = os.path.join(CSRC, "search_cli.cpp")
     if os.path.exists(cli) and (force or _newer(CLI, [cli, LIB])):
-        _run([GXX, "-O2", "-std=c++17", cli, "-o", CLI, "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-llexicmap_gpu", "-Wl,-rpath," + HERE])
+        _run([GXX, "-O2", "-std=c++17", cli, "-o", CLI, "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-llexicmap_gpu", "-lz", "-Wl,-rpath,$ORIGIN/.."])
     return TOOLS
 
 

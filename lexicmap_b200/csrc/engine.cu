@@ -870,7 +870,8 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
 
 #define LMG_HAVE_SEARCH 1
 int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R;
+    ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
@@ -902,7 +903,8 @@ int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, 
   try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; upload_queries(ix, seqs, off, n, Q->B); CUDA_CHECK(cudaStreamSynchronize(ix->st)); *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int lmg_search_staged(lmg_index* ix, const lmg_params* p, lmg_queries* q, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R; return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R;
+    ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 void lmg_queries_free(lmg_index* ix, lmg_queries* q) { if (!q) return; cudaSetDevice(ix->img.device); delete q; }

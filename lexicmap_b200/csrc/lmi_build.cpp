@@ -280,6 +280,16 @@ int main(int argc, char** argv) {
       int F, S, G, mc = 20; unsigned long long sd; std::string synth = arg(argc, argv, "--synth", ""); if (sscanf(synth.c_str(), "%d,%d,%d,%llu,%d", &F, &S, &G, &sd, &mc) < 4) die("--synth F,S,G,seed[,max_contigs]");
       std::string out = arg(argc, argv, "--out", "refs"); mkdir_p(out);
       for (int gi = 0; gi < F * S; gi++) { InGenome g = synth_genome(gi / S, gi % S, S, G, sd, mc); FILE* f = fopen((out + "/" + g.id + ".fa").c_str(), "w"); for (size_t c = 0; c < g.seqs.size(); c++) fprintf(f, ">%s\n%s\n", g.seq_ids[c].c_str(), g.seqs[c].c_str()); fclose(f); }
+    } else if (cmd == "kat") {   // the dataset of the reference's known-answer test kv/kv-data_test.go:30-59
+      std::string out = arg(argc, argv, "--out", "t.kv"); const int k = 5, lenPrefix = 2; uint64_t prefix = 0b0111ull << ((k - lenPrefix) << 1), n = 1ull << ((k - lenPrefix) << 1);
+      KvWriter w(out, k, 0, 1 << lenPrefix, lenPrefix, 2, true); std::vector<KvEntry> e; for (uint64_t i = 0; i < n; i++) e.push_back({prefix | i, {i}}); for (int j = 0; j < (1 << lenPrefix); j++) w.write_mask(e); w.close();
+    } else if (cmd == "kv-dump") {   // decode a chunk with the product decoder: mask, key, values..., and the anchor table
+      KvChunk c = read_kv_chunk(arg(argc, argv, "--file", "")); printf("k=%d mask_offset=%d chunk_size=%d mask_prefix=%d anchor_prefix=%d use7=%d\n", c.k, c.mask_offset, c.chunk_size, c.mask_prefix, c.anchor_prefix, (int)c.use7);
+      for (int m = 0; m < c.chunk_size; m++) { const KvMaskData& md = c.masks[m]; for (size_t t = 0; t < md.keys.size(); t++) { printf("K\t%d\t%llu", m, (unsigned long long)md.keys[t]); for (uint32_t v = md.val_off[t]; v < md.val_off[t + 1]; v++) printf("\t%llu", (unsigned long long)md.vals[v]); printf("\n"); }
+        for (size_t a = 0; a < c.anchor_start[m].size(); a++) if (c.anchor_start[m][a] != 0xFFFFFFFFu) printf("A\t%d\t%zu\t%u\n", m, a, c.anchor_start[m][a]); }
+    } else if (cmd == "varint-test") {   // util/varint-GB_test.go:54-100 restated: round trip + control-byte length
+      uint64_t s = strtoull(arg(argc, argv, "--seed", "1"), 0, 10); int bad = 0; for (int it = 0; it < 2000000; it++) { uint64_t a = splitmix64(s) >> (splitmix64(s) & 63), b = splitmix64(s) >> (splitmix64(s) & 63), x, y; uint8_t buf[16], ctrl; int n = put_u64s(buf, a, b, &ctrl);
+        int m = get_u64s(ctrl, buf, &x, &y); if (x != a || y != b || n != m || n != ((ctrl >> 3) & 7) + (ctrl & 7) + 2) bad++; } printf("varint mismatches: %d\n", bad); return bad ? 1 : 0;
     } else die("unknown command " + cmd);
   } catch (std::exception& e) { fprintf(stderr, "[lmi-tools] error: %s\n", e.what()); return 1; }
   return 0;

@@ -229,9 +229,16 @@ char* lmo_wfa_batch(const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_
   char* c = (char*)malloc(o.size() + 1); memcpy(c, o.data(), o.size() + 1); *out_len = o.size(); return c;
 }
 // on-disk seed lookup for one (mask,kmer): KAT helper (kv-data_test.go:208-283). Returns number of results; lens/values optional.
-int lmo_kv_search(void* hh, int mask, uint64_t kmer, int p, int reversed, uint8_t* lens, uint64_t* first_values, int cap) {
-  Handle* h = (Handle*)hh; std::vector<KvHit> hits; for (const KvChunkFile& c : h->ix.chunks) if (mask >= c.chunk_index && mask < c.chunk_index + c.chunk_size) kv_probe(c, mask - c.chunk_index, kmer, p, reversed, 0, hits);
+// standalone handle over one kv-data file (no .lmi directory) for the known-answer test
+void* lmo_open_kv(const char* file) { try { Handle* h = new Handle; h->ix.chunks.resize(1); h->ix.chunks[0].data = slurp(file); Index::read_kv_index(std::string(file) + ".idx", h->ix.chunks[0]); h->ix.k = h->ix.chunks[0].k; return h; } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
+int lmo_kv_search(void* hh, int mask, uint64_t kmer, int p, int reversed, int check_flag, uint8_t* lens, uint64_t* first_values, int cap) {
+  Handle* h = (Handle*)hh; std::vector<KvHit> hits; for (const KvChunkFile& c : h->ix.chunks) if (mask >= c.chunk_index && mask < c.chunk_index + c.chunk_size) kv_probe(c, mask - c.chunk_index, kmer, p, reversed, 0, hits, check_flag != 0);
   for (int i = 0; i < (int)hits.size() && i < cap; i++) { if (lens) lens[i] = hits[i].len; if (first_values) first_values[i] = hits[i].values[0]; } return (int)hits.size();
 }
+// tree.Search emulation on an explicit key list (sorted by the caller): returns the reported range
+int lmo_tree_search(const uint64_t* keys, int n, int k, uint64_t key, int p, int* lo, int* hi) { QueryTable T; T.k = k; T.keys.assign(keys, keys + n); size_t a = 0, b = 0; bool ok = tree_search(T, key, p, &a, &b); *lo = (int)a; *hi = (int)b; return ok; }
+// genome.Reader.SubSeq3 (genome/genome.go:931-1143)
+int lmo_subseq(void* hh, uint64_t bgi, int start, int end, char* out, int cap) { Handle* h = (Handle*)hh; const GenomeBatchFile& gb = h->ix.batches[bgi >> 17]; GenomeMeta gm = genome_meta(gb, (int)(bgi & 131071)); std::string s = subseq3(gb, (int)(bgi & 131071), gm, start, end); int n = std::min<int>(cap, (int)s.size()); memcpy(out, s.data(), n); return (int)s.size(); }
+int lmo_dust(uint64_t kmer, int k) { return dust(kmer, k); }
 void lmo_free(void* p) { free(p); }
 }

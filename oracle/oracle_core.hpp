@@ -163,7 +163,7 @@ static inline bool low_complexity(uint64_t kmer, int k) {  // lib-index-search.g
 struct KvHit { int iquery, iquery2; uint8_t len; bool is_suffix; std::vector<uint64_t> values; };
 
 // one probe: scan the mask's records from the anchor offset, exactly as the Go code walks the file
-static inline void kv_probe(const KvChunkFile& c, int iq /*mask index within chunk*/, uint64_t kmer, int p, bool reversed, int iquery2, std::vector<KvHit>& out) {
+static inline void kv_probe(const KvChunkFile& c, int iq /*mask index within chunk*/, uint64_t kmer, int p, bool reversed, int iquery2, std::vector<KvHit>& out, bool check_flag = true) {
   const std::vector<uint64_t>& index = c.indexes[iq]; if (index.empty() || kmer == 0) return;   // :285-296
   const int k = c.k; const uint8_t shift = (uint8_t)(k - 32); const uint8_t rvflag = reversed ? 1 : 0; const int vb = c.use7 ? 7 : 8;
   uint64_t left, right; if (p < k) { int s2 = (k - p) << 1; uint64_t mask = (1ull << s2) - 1; left = kmer & ~mask; right = ((kmer >> s2) << s2) | mask; } else { left = right = kmer; }  // :298-304
@@ -171,7 +171,7 @@ static inline void kv_probe(const KvChunkFile& c, int iq /*mask index within chu
   size_t i = (size_t)(anchor << 1) + 2; uint64_t offset = index[i + 1]; bool is2nd = offset & 1; offset >>= 1; if (offset == 0) return;  // :349-355
   const uint8_t* d = c.data.data(); size_t pos = (size_t)offset; bool first = true, found = false; uint64_t _offset = 0, kmer1, kmer2;
   auto take = [&](uint64_t km, uint64_t nval, bool save) {  // value block of one k-mer (:460-529 / :553-622)
-    if (save) { if ((d[pos + vb - 1] & 1) != rvflag) save = false; }   // first value's reverse flag decides (:466-488)
+    if (save && check_flag) { if ((d[pos + vb - 1] & 1) != rvflag) save = false; }   // first value's reverse flag decides (:466-488)
     if (save) { KvHit h; h.iquery = iq + c.chunk_index; h.iquery2 = iquery2; h.len = (uint8_t)((uint8_t)(lz64(kmer ^ km) >> 1) + shift); h.is_suffix = reversed;
       for (uint64_t j = 0; j < nval; j++) h.values.push_back(rd_be(d + pos + j * vb, vb)); out.push_back(std::move(h)); }
     pos += (size_t)nval * vb;

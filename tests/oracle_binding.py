@@ -84,7 +84,12 @@ class Oracle:
             f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         L.lmo_wfa_batch.restype = C.c_void_p
         L.lmo_wfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
-        L.lmo_kv_search.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.lmo_kv_search.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.lmo_open_kv.restype = C.c_void_p
+        L.lmo_open_kv.argtypes = [C.c_char_p]
+        L.lmo_tree_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.lmo_subseq.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.lmo_dust.argtypes = [C.c_uint64, C.c_int]
         L.lmo_free.argtypes = [C.c_void_p]
         self.h = L.lmo_open(lmi_dir.encode()) if lmi_dir else None
         if lmi_dir and not self.h:
@@ -164,10 +169,26 @@ class Oracle:
         self.lib.lmo_free(ptr)
         return s.split("\n")[:-1]
 
-    def kv_search(self, mask, kmer, p, reversed_=False, cap=4096):
+    def open_kv(self, file):
+        self.h = self.lib.lmo_open_kv(file.encode())
+        if not self.h:
+            raise RuntimeError(self.lib.lmo_last_error().decode())
+
+    def tree_search(self, keys, k, key, p):
+        a = np.asarray(keys, dtype=np.uint64)
+        lo, hi = C.c_int(), C.c_int()
+        ok = self.lib.lmo_tree_search(a.ctypes.data, len(a), k, int(key), p, C.byref(lo), C.byref(hi))
+        return bool(ok), lo.value, hi.value
+
+    def subseq(self, bgi, start, end):
+        buf = C.create_string_buffer(end - start + 2)
+        n = self.lib.lmo_subseq(self.h, int(bgi), start, end, buf, end - start + 1)
+        return buf.raw[:n].decode()
+
+    def kv_search(self, mask, kmer, p, reversed_=False, check_flag=True, cap=4096):
         lens = np.zeros(cap, np.uint8)
         vals = np.zeros(cap, np.uint64)
-        n = self.lib.lmo_kv_search(self.h, mask, int(kmer), p, int(reversed_), lens.ctypes.data, vals.ctypes.data, cap)
+        n = self.lib.lmo_kv_search(self.h, mask, int(kmer), p, int(reversed_), int(check_flag), lens.ctypes.data, vals.ctypes.data, cap)
         return n, lens[:min(n, cap)], vals[:min(n, cap)]
 
 
