@@ -6,25 +6,47 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <algorithm>
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int64_t i64;
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
 
-// stream-ordered device buffer
+// Per-index bump arena for the per-batch device buffers: cudaMallocAsync pools showed sporadic 200-300 ms stalls when multi-GB
+// blocks had to be re-mapped between calls; a grow-only arena that is reset after every batch is deterministic.
+struct Arena {
+  struct Chunk { char* base; size_t size; };
+  std::vector<Chunk> chunks; size_t cur = 0, off = 0;
+  static size_t al(size_t b) { return (b + 511) & ~(size_t)511; }
+  void* alloc(size_t bytes) {
+    bytes = al(bytes + 64);
+    while (cur < chunks.size() && off + bytes > chunks[cur].size) { cur++; off = 0; }
+    if (cur >= chunks.size()) { size_t tot = 0; for (auto& c : chunks) tot += c.size; size_t sz = std::max(bytes, std::max<size_t>(tot, (size_t)1 << 30)); Chunk c; c.size = sz;
+      cudaError_t e = cudaMalloc((void**)&c.base, sz); if (e != cudaSuccess) { cudaGetLastError(); c.size = sz = bytes; e = cudaMalloc((void**)&c.base, sz); }
+      if (e != cudaSuccess) throw std::runtime_error(std::string("device arena: cudaMalloc failed: ") + cudaGetErrorString(e)); chunks.push_back(c); cur = chunks.size() - 1; off = 0; }
+    void* p = chunks[cur].base + off; off += bytes; return p;
+  }
+  void free(void* p, size_t bytes) { bytes = al(bytes + 64); if (cur < chunks.size() && (char*)p + bytes == chunks[cur].base + off) off -= bytes; }   // LIFO frees are recycled
+  void reset() { cur = 0; off = 0; if (chunks.size() > 1) { size_t tot = 0; for (auto& c : chunks) { tot += c.size; cudaFree(c.base); } chunks.clear(); Chunk c; c.size = tot; if (cudaMalloc((void**)&c.base, tot) == cudaSuccess) chunks.push_back(c); else cudaGetLastError(); } }
+  void release() { for (auto& c : chunks) cudaFree(c.base); chunks.clear(); cur = off = 0; }
+};
+static thread_local Arena* g_arena = nullptr;
+struct ArenaScope { Arena* prev; ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; } ~ArenaScope() { g_arena = prev; } };
+
+// device buffer: from the current arena when one is active, otherwise stream-ordered cudaMallocAsync
 template <class T> struct DBuf {
-  T* p = nullptr; size_t n = 0; cudaStream_t st = 0;
+  T* p = nullptr; size_t n = 0; cudaStream_t st = 0; Arena* ar = nullptr;
   DBuf() {}
   DBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
-  void alloc(size_t n_, cudaStream_t s) { free(); n = n_; st = s; if (n) CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T) + 64, s)); }
-  void free() { if (p) { cudaFreeAsync(p, st); p = nullptr; n = 0; } }
+  void alloc(size_t n_, cudaStream_t s) { free(); n = n_; st = s; if (!n) return; if (g_arena) { ar = g_arena; p = (T*)ar->alloc(n * sizeof(T)); } else { ar = nullptr; CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T) + 64, s)); } }
+  void free() { if (p) { if (ar) ar->free(p, n * sizeof(T)); else cudaFreeAsync(p, st); p = nullptr; n = 0; ar = nullptr; } }
   void zero() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
   void fill_ff() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0xff, n * sizeof(T), st)); }
   ~DBuf() { free(); }
   DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
-  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+  DBuf(DBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; ar = o.ar; o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; st = o.st; ar = o.ar; o.p = nullptr; o.n = 0; } return *this; }
   std::vector<T> to_host(size_t cnt = (size_t)-1) const { if (cnt == (size_t)-1) cnt = n; std::vector<T> h(cnt); if (cnt) { CUDA_CHECK(cudaMemcpyAsync(h.data(), p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st)); } return h; }
   void from_host(const T* h, size_t cnt) { if (cnt) CUDA_CHECK(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st)); }
 };

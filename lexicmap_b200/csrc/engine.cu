@@ -170,10 +170,12 @@ struct QBatch {  // device-side query batch
 
 struct lmg_index {
   Image img; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[2] = {nullptr, nullptr};
+  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[2] = {nullptr, nullptr}; Arena arena;
 };
 
 static thread_local std::string g_err;
+// activates the index's arena for the calling thread and rewinds it when the batch is done (all DBufs of the batch are dead by then)
+struct ArenaReset { lmg_index* ix; ArenaScope sc; ArenaReset(lmg_index* i) : ix(i), sc(&i->arena) {} ~ArenaReset() { cudaStreamSynchronize(ix->st); ix->arena.reset(); } };
 
 static void upload_queries(lmg_index* ix, const u8* seqs, const u64* off, int nq, QBatch& B) {
   cudaStream_t st = ix->st; const int k = ix->img.k; B.nq = nq; B.h_off.assign(off, off + nq + 1); B.total_bases = off[nq] - off[0];
@@ -443,15 +445,65 @@ __global__ void __launch_bounds__(128) k_pa_anchors(const WinItem* __restrict__ 
   if (!EMIT) { typedef cub::BlockReduce<u32, 128> Red; __shared__ typename Red::TempStorage rt; u32 s = Red(rt).Sum(total); if (threadIdx.x == 0) counts[it] = s; }
 }
 
+// ---- K4 v2: per-query hash index over the 11-base prefixes of the table (the default minimum prefix), window staged in shared memory
+// slot = prefix22 << 42 | start24 << 18 | count18 ; empty = ~0
+#define TH_EMPTY 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ u32 th_hash(u32 prefix, u32 mask) { return (prefix * 2654435761u >> 7) & mask; }
+__global__ void k_tree_hash_build(const u64* __restrict__ tkeys, const u32* __restrict__ toff, const u64* __restrict__ hoff, int nq, u64* __restrict__ table) {
+  int q = blockIdx.y; if (q >= nq) return; u32 t0 = toff[q], n = toff[q + 1] - t0; u64 h0 = hoff[q]; u32 H = (u32)(hoff[q + 1] - h0); if (!n || !H) return; const u64* a = tkeys + t0; u64* T = table + h0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { u32 p = (u32)(a[i] >> 40); if (i > 0 && (u32)(a[i - 1] >> 40) == p) continue; u32 c = 1; while (i + c < n && (u32)(a[i + c] >> 40) == p) c++;
+    if (c >= (1u << 18) || i >= (1u << 24)) c = 0;   // does not fit the slot: count 0 = "use binary search"
+    u64 slot = ((u64)p << 42) | ((u64)(i & 0xFFFFFF) << 18) | c; u32 h = th_hash(p, H - 1); for (;;) { unsigned long long old = atomicCAS((unsigned long long*)&T[h], TH_EMPTY, slot); if (old == TH_EMPTY) break; h = (h + 1) & (H - 1); } }
+}
+__device__ __forceinline__ bool th_lookup(const u64* __restrict__ T, u32 H, u32 prefix, u32* start, u32* count) {   // false = prefix absent
+  u32 h = th_hash(prefix, H - 1); for (;;) { u64 s = T[h]; if (s == TH_EMPTY) return false; if ((u32)(s >> 42) == prefix) { *start = (u32)(s >> 18) & 0xFFFFFF; *count = (u32)s & 0x3FFFF; return true; } h = (h + 1) & (H - 1); }
+}
+// keys sharing >= p bases: hash path when p == 11, else binary search; identical result set to tree_search()
+__device__ __forceinline__ bool tree_search_h(const u64* __restrict__ a, u32 n, const u64* __restrict__ T, u32 H, u64 key, int p, u32* rlo, u32* rhi) {
+  if (p == 11 && H) { u32 st, c; if (th_lookup(T, H, (u32)(key >> 40), &st, &c)) { if (c) { *rlo = st; *rhi = st + c; return true; } return tree_search(a, n, key, p, rlo, rhi); }
+    if (((key >> 40) & 0xF) == 0) return tree_search_slow(a, n, key, p, rlo, rhi); return false; }
+  return tree_search(a, n, key, p, rlo, rhi);
+}
+// one CTA per window. The oriented window is packed into shared memory (16 bases per word) once; every thread extracts its 31-mer
+// with three word loads. Anchors go to a per-window region of capacity cap[it]; counts[it] is exact even when it overflows.
+__global__ void __launch_bounds__(128) k_pa_anchors2(const WinItem* __restrict__ items, const u32* __restrict__ item_ids, u32 nitems, const u8* __restrict__ g2bit, const u64* __restrict__ g_off, const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff,
+                                                     const u64* __restrict__ htab, const u64* __restrict__ hoff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u64 dbg_total) {
+  __shared__ u32 s_base; extern __shared__ u32 sw[];
+  u32 bi = blockIdx.x; if (bi >= nitems) return; u32 it = item_ids ? item_ids[bi] : bi; WinItem w = items[it]; const int K = 31; const u8* g2 = g2bit + g_off[w.g]; const u64* tk = tkeys + toff[w.q]; const u32* tv = tvals + toff[w.q]; u32 tn = toff[w.q + 1] - toff[w.q];
+  const u64* HT = htab + hoff[w.q]; u32 H = (u32)(hoff[w.q + 1] - hoff[w.q]); const u64 base0 = abeg[it]; const u32 cap = acap[it];
+  i32 nw = (w.W + 15) / 16 + 2;
+  for (i32 x = threadIdx.x; x < nw; x += 128) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
+  if (threadIdx.x == 0) s_base = 0; __syncthreads();
+  i32 np = w.W - K + 1; const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
+  for (i32 t0 = 0; t0 < np; t0 += 128) {
+    i32 idx = t0 + (i32)threadIdx.x; u32 c = 0; u64 km = 0, kr = 0; bool ok = false; u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0; bool f1 = false, f2 = false;
+    if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; km = v >> 2;
+      kr = kmer_reverse62(~km & ttt, K); ok = !(km == 0 || km == ccc || km == ggg || km == ttt); }
+    if (ok && tn) {
+      f1 = tree_search_h(tk, tn, HT, H, km, w.mp, &l1, &h1);
+      if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
+      f2 = tree_search_h(tk, tn, HT, H, kr, w.mp, &l2, &h2);
+      if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
+    }
+    u32 wpos = 0; if (c) wpos = atomicAdd(&s_base, c);   // order inside a window is irrelevant (sorted next); s_base ends as the exact count
+    if (c && (u64)wpos + c <= (u64)cap) { u64* out = a_lo + base0 + wpos;
+      {
+      if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx, 0, 0); }
+      if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx + K - lp, 1, 1); } } }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[it] = s_base;
+}
+
 struct C2Rec { u32 item, ord; i32 qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors; };
 struct Chain2Params { int max_gap, min_score, min_align_len, band_count, band_base, k; };
 
 // one warp per window: nested-anchor removal, trimming, banded chaining DP, region splitting. Scalar control flow is executed
 // redundantly by all lanes (uniform); the DP inner loop and arg-max scans are lane-parallel.
-__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_in, const u64* __restrict__ aoff, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
+__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_in, const u64* __restrict__ abeg, const u64* __restrict__ aend, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
                                                   C2Rec* __restrict__ out, u32* __restrict__ nout, u32 cap) {
   u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31; if (it >= nitems) return;
-  u64 b = aoff[it]; u32 n = (u32)(aoff[it + 1] - b); if (n == 0) return; const u64* A = lo_in + b; u64* C = c_lo + b; const int k = P.k;
+  u64 b = abeg[it]; u32 n = (u32)(aend[it] - b); if (n == 0) return; const u64* A = lo_in + b; u64* C = c_lo + b; const int k = P.k;
   // ---- ClearSubstrPairs
   if (n > 1) { u32 kept = 0;
     for (u32 base = 0; base < n; base += 32) { u32 i = base + lane; bool keep = false;
@@ -668,6 +720,137 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
   }
 }
 
+// ---------------- WFA fast path: packed sequences, shared-memory wavefront ring, directory-free HBM layout
+// Per job the query / target segments are first re-packed (k_wfa_prep) into 64-bit words (32 bases each, first base in the top
+// bits; a third word stream marks ambiguous query bases) so that wavefront extension compares 32 bases per XOR+CLZ.
+// Wavefronts live in HBM as u16 offsets in a fixed-stride layout: level L (score 2L), component c, diagonal k at
+// slab[L*3*WFS + c*WFS + k + WFK0]; every level writes [glo-PAD, ghi+PAD] (NULL outside its reach) so neither the forward pass nor
+// the backtrace needs bounds checks or a directory. The last 5 M levels and 2 I/D levels are mirrored in shared memory (ring).
+// Jobs that do not fit (|k| >= 128, score >= 2*WF_LMAX, sequences >= 65000) report status 1 and go to the general kernel k_wfa.
+#define WF_WMAX 256
+#define WF_PAD 8
+#define WFS (WF_WMAX + 2 * WF_PAD)
+#define WFK0 (WF_WMAX / 2 + WF_PAD)
+#define WF_LMAX 2048
+#define WF_OPSMAX 4096
+#define WF_WARPS 8
+struct WfaSeg { u64 qw, tw; };   // word offsets of the job's packed query / target (query: 2 streams: bases at qw, ambiguity at qw + nqw)
+
+__global__ void k_wfa_prep(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, u32 njobs, const u64* __restrict__ woff /*2 per job +1*/, const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff,
+                           const u8* __restrict__ g2bit, const u64* __restrict__ g_off, u64* __restrict__ words) {
+  u32 jb = blockIdx.x; if (jb >= njobs) return; HspJob J = jobs[jb]; ExtOut e = ext[jb]; const u8* q2 = qpacked + qboff[J.q]; const u8* qm = qamask + qboff[J.q]; const u8* g2 = g2bit + g_off[J.g];
+  i32 plen = e.qe - e.qs, tlen = e.te - e.ts; u32 nq = (u32)((plen + 31) / 32 + 2), nt = (u32)((tlen + 31) / 32 + 2); u64* Q = words + woff[2 * jb]; u64* A = Q + nq; u64* T = words + woff[2 * jb + 1];
+  for (u32 w = threadIdx.x; w < nq; w += blockDim.x) { u64 b = 0, a = 0; for (int j = 0; j < 32; j++) { i32 i = (i32)w * 32 + j; u64 c = 0, am = 0; if (i < plen) { i32 p = e.qs + i; c = get_base(q2, (u64)p); am = ((qm[p >> 3] >> (p & 7)) & 1) ? 3 : 0; } b = (b << 2) | c; a = (a << 2) | am; } Q[w] = b; A[w] = a; }
+  for (u32 w = threadIdx.x; w < nt; w += blockDim.x) { u64 b = 0; for (int j = 0; j < 32; j++) { i32 i = (i32)w * 32 + j; u64 c = (i < tlen) ? win_base(g2, J.tBegin, J.tEnd, J.rc, e.ts + i) : 0; b = (b << 2) | c; } T[w] = b; }
+}
+__device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos) { u32 i = (u32)pos >> 5, sh = ((u32)pos & 31) * 2; u64 a = W[i]; if (sh == 0) return a; return (a << sh) | (W[i + 1] >> (64 - sh)); }
+
+__global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, u32 njobs, u32* __restrict__ next_job,
+                                                          u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+  __shared__ u16 ring[WF_WARPS][9][WFS];   // 0-4: M levels (L%5), 5-6: I (L%2), 7-8: D (L%2)
+  const int X2 = 2, OE2 = 4, E2 = 1;        // penalties 4 / 8 / 2 in units of levels (score = 2*level)
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u32 warp = blockIdx.x * WF_WARPS + wib; u16* slab = slabs + (u64)warp * WF_LMAX * 3 * WFS; u16 (*R)[WFS] = ring[wib]; u64* ops = ops_scratch + (u64)warp * WF_OPSMAX;
+  for (;;) {
+    u32 jb = 0; if (lane == 0) jb = atomicAdd(next_job, 1u); jb = __shfl_sync(FULLMASK, jb, 0); if (jb >= njobs) return;
+    ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
+    const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1];
+    WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
+    if (plen >= 65000 || tlen >= 65000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = (fetch64(Q, v) ^ fetch64(T, h)) | fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
+    // level 0
+    i32 glo = 0, ghi = 0; i32 hlo[4], hhi[4]; u32 hnull[4];   // history of levels L-1..L-4: lo, hi, null bits (1 M, 2 I, 4 D)
+    for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
+    { i32 h0 = 0; if (lane == 0) h0 = extend(0, 0); h0 = __shfl_sync(FULLMASK, h0, 0);
+      for (i32 k = -WF_PAD + lane; k <= WF_PAD; k += 32) { u16 mv = (k == 0) ? (u16)h0 : (u16)0xFFFF; R[0][k + WFK0] = mv; slab[k + WFK0] = mv; slab[WFS + k + WFK0] = 0xFFFF; slab[2 * WFS + k + WFK0] = 0xFFFF; R[5][k + WFK0] = 0xFFFF; R[7][k + WFK0] = 0xFFFF; }
+      hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; __syncwarp();
+      if (kend == 0 && h0 >= tlen) { /* done at score 0 */ } }
+    i32 L = 0; bool done = (kend == 0 && (i32)R[0][WFK0] >= tlen && R[0][WFK0] != 0xFFFF), overflow = false;
+    while (!done) {
+      L++; if (L >= WF_LMAX) { overflow = true; break; }
+      // sources: M[L-2] (mismatch), M[L-4] (gap open), I/D[L-1] (gap extend); history index = distance-1
+      bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
+      i32 lo = INT32_MAX, hi = INT32_MIN; bool allnull = nx && no && ni && nd;
+      if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); }
+        glo = min(glo, lo); ghi = max(ghi, hi); if (glo <= -(WF_WMAX / 2) || ghi >= WF_WMAX / 2) { overflow = true; break; } }
+      const u16* M2 = R[(L + 5 - X2) % 5]; const u16* M4 = R[(L + 5 - OE2) % 5]; const u16* I1 = R[5 + ((L + 1) & 1)]; const u16* D1 = R[7 + ((L + 1) & 1)];
+      u16* Mo = R[L % 5]; u16* Io = R[5 + (L & 1)]; u16* Do = R[7 + (L & 1)]; u16* G = slab + (u64)L * 3 * WFS; bool anyM = false, anyI = false, anyD = false;
+      for (i32 k = glo - WF_PAD + lane; k <= ghi + WF_PAD; k += 32) {
+        u16 om = 0xFFFF, oi = 0xFFFF, od = 0xFFFF; int x = k + WFK0;
+        if (!allnull && k >= lo && k <= hi) {
+          i32 a = (L >= OE2) ? (i32)M4[x - 1] : 0xFFFF, b = (i32)I1[x - 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 ins = max(a, b); ins = (ins < 0) ? -1 : ins + 1;
+          a = (L >= OE2) ? (i32)M4[x + 1] : 0xFFFF; b = (i32)D1[x + 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 del = max(a, b);
+          i32 mis = (L >= X2) ? (i32)M2[x] : 0xFFFF; mis = (mis == 0xFFFF) ? -1 : mis + 1;
+          if (!(ins >= 0 && ins - k >= 0 && ins <= tlen && ins - k <= plen)) ins = -1;
+          if (!(del >= 0 && del - k >= 0 && del <= tlen && del - k <= plen)) del = -1;
+          if (!(mis >= 0 && mis - k >= 0 && mis <= tlen && mis - k <= plen)) mis = -1;
+          i32 mm = max(mis, max(ins, del)); if (mm >= 0) { mm = extend(k, mm); anyM = true; om = (u16)mm; } if (ins >= 0) { anyI = true; oi = (u16)ins; } if (del >= 0) { anyD = true; od = (u16)del; }
+        }
+        Mo[x] = om; Io[x] = oi; Do[x] = od; G[x] = om; G[WFS + x] = oi; G[2 * WFS + x] = od;
+      }
+      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD);
+      for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
+      hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
+      __syncwarp();
+      if (!allnull && kend >= lo && kend <= hi) { u16 v = Mo[kend + WFK0]; done = (v != 0xFFFF && (i32)v >= tlen); }
+    }
+    if (overflow) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    if (lane == 0) {   // backtrace, identical decision rule to k_wfa
+      WfaOut& Rr = Rz; Rr.wscore = 2 * L; i32 k = kend, off = tlen, lv = L; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
+      auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
+      auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
+        if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
+        else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
+      auto ld = [&](i32 lvl, int comp, i32 kk) -> i32 { if (lvl < 0) return -1; u16 v = slab[(u64)lvl * 3 * WFS + comp * WFS + kk + WFK0]; return v == 0xFFFF ? -1 : (i32)v; };
+      auto pig = [](i32 o, int type) -> i64 { return o < 0 ? INT64_MIN : (((i64)o << 4) | type); };
+      while (vv > 0 && h > 0 && lv > 0) {
+        i32 l_mis = lv - X2, l_open = lv - OE2, l_ext = lv - E2; i64 c_mis = INT64_MIN, c_io = INT64_MIN, c_ie = INT64_MIN, c_do = INT64_MIN, c_de = INT64_MIN;
+        i32 v_mis = -1, v_io = -1, v_ie = -1, v_do = -1, v_de = -1;
+        if (mat == 0) v_mis = ld(l_mis, 0, k); if (mat == 0 || mat == 1) { v_io = ld(l_open, 0, k - 1); v_ie = ld(l_ext, 1, k - 1); } if (mat == 0 || mat == 2) { v_do = ld(l_open, 0, k + 1); v_de = ld(l_ext, 2, k + 1); }
+        if (mat == 0) c_mis = pig(v_mis < 0 ? -1 : v_mis + 1, 9); if (mat == 0 || mat == 1) { c_io = pig(v_io < 0 ? -1 : v_io + 1, 1); c_ie = pig(v_ie < 0 ? -1 : v_ie + 1, 2); } if (mat == 0 || mat == 2) { c_do = pig(v_do, 5); c_de = pig(v_de, 6); }
+        i64 best = max(c_mis, max(max(c_io, c_ie), max(c_do, c_de))); if (best == INT64_MIN) { Rr.status = 2; break; }
+        if (mat == 0) { i32 mo = (i32)(best >> 4); i32 nm = off - mo; put('M', nm, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
+        int type = (int)(best & 15);
+        switch (type) { case 9: lv = l_mis; mat = 0; put('X', 1, off - k, off); off--; break;
+          case 1: lv = l_open; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: lv = l_ext; mat = 1; put('I', 1, off - k, off); k--; off--; break;
+          case 5: lv = l_open; mat = 0; put('D', 1, off - k, off); k++; break; case 6: lv = l_ext; mat = 2; put('D', 1, off - k, off); k++; break; }
+        vv = off - k; h = off;
+      }
+      if (Rr.status == 0) { if (lv == 0) put('M', off, off - k, off); else { if (vv > 0) put('D', vv, vv, h); if (h > 0) put('I', h, 0, h); } }
+      flush();
+      if (want_ops && Rr.status == 0) { if (ops_over) Rr.status = 1; else { u64 o = atomicAdd((unsigned long long*)ops_cursor, (unsigned long long)nops); if (o + nops <= ops_cap) { for (u32 i = 0; i < nops; i++) ops_pool[o + i] = ops[i]; Rr.ops_off = o; Rr.ops_n = nops; } else Rr.status = 3; } }
+      outs[jb] = Rr;
+    }
+    __syncwarp();
+  }
+}
+
+static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
+                        int want_ops, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters) {
+    // WFA: fast kernel (packed words + smem ring) for every job, then the general kernel for whatever did not fit
+    DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
+    u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
+    { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
+      DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st);
+      k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p); KERNEL_CHECK();
+      u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (nj + WF_WARPS - 1) / WF_WARPS); u64 nwarps = (u64)blocks * WF_WARPS;
+      DBuf<u16> fslabs(nwarps * WF_LMAX * 3 * WFS, st); DBuf<u64> oscr(want_ops ? nwarps * WF_OPSMAX : 8, st); DBuf<u32> next(1, st); next.zero();
+      k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, nj, next.p, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+      std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
+      counters[9] = nj; counters[10] = ids.size(); }
+    size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
+    u64 slab_words = 1ull << 20;  // 4 MB per warp to start
+    for (int round = 0; round < 6 && !ids.empty(); round++) {
+      u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
+      if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
+      DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
+      k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+      std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
+      ids.swap(again); slab_words *= 8;
+    }
+    if (!ids.empty()) throw std::runtime_error("WFA workspace exhausted after 6 rounds");
+    if (want_ops) { u64 used = ops_cur.to_host()[0]; hops = ops_pool.to_host(used); }
+}
+
 // =====================================================================================================
 // host orchestration of K4/K5 + finishing (lib-index-search.go:1834-2932)
 // =====================================================================================================
@@ -709,18 +892,28 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     w.tBegin = tBegin; w.tEnd = tEnd; w.W = sl; w.rc = rc; w.mp = 11 + (sl >= 1000000 ? 8 : sl >= 250000 ? 6 : sl >= 50000 ? 4 : sl >= 10000 ? 2 : 0); items[c] = w; }
   u32 nit = Cn.n; DBuf<WinItem> d_items(nit, st); d_items.from_host(items.data(), nit);
   DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff);
-  // ---- K4 anchors: count, scan, emit, per-window sort
-  DBuf<u32> cnt(nit + 1, st); k_pa_anchors<false><<<nit, 128, 0, st>>>(d_items.p, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, cnt.p, nullptr, nullptr); KERNEL_CHECK();
-  std::vector<u32> hcnt = cnt.to_host(nit); std::vector<u64> haoff(nit + 1, 0); for (u32 i = 0; i < nit; i++) haoff[i + 1] = haoff[i] + hcnt[i]; u64 NA = haoff[nit];
+  // ---- K4 anchors: per-query prefix hash, one pass into capacity-bounded regions (exact rerun for the rare overflow), per-window sort
+  std::vector<u32> htoff = toff.to_host(B.nq + 1); std::vector<u64> hhoff(B.nq + 1, 0); for (int q = 0; q < B.nq; q++) { u32 n = htoff[q + 1] - htoff[q]; u64 H = 0; if (n) { H = 16; while (H < 2ull * n) H <<= 1; } hhoff[q + 1] = hhoff[q] + H; }
+  DBuf<u64> hoff(B.nq + 1, st); hoff.from_host(hhoff.data(), B.nq + 1); DBuf<u64> htab(hhoff[B.nq] + 2, st); htab.fill_ff();
+  { u32 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, htoff[q + 1] - htoff[q]); if (maxn) { dim3 g((unsigned)std::max(1, std::min(32, cdiv(maxn, 256))), B.nq); k_tree_hash_build<<<g, 256, 0, st>>>(tkeys.p, toff.p, hoff.p, B.nq, htab.p); KERNEL_CHECK(); } }
+  std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>(2ll * std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
+  size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
+  CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smemW, 1024)));
+  DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
+  for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than 2*W+256: capacities become the exact counts
+    for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
+    if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
+    dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
+    k_pa_anchors2<<<nit, 128, smemW, st>>>(d_items.p, nullptr, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK();
+    hcnt = cnt.to_host(nit); bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
+    if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
   std::vector<C2Rec> c2;
   if (NA > 0) {
-    if (NA >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchors in one batch; use smaller batches");
-    DBuf<u64> aoff(nit + 1, st); aoff.from_host(haoff.data(), nit + 1); DBuf<u64> lo0(NA, st), lo1(NA, st);
-    k_pa_anchors<true><<<nit, 128, 0, st>>>(d_items.p, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, nullptr, aoff.p, lo0.p); KERNEL_CHECK();
-    { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)NA, (int)nit, aoff.p, aoff.p + 1, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)NA, (int)nit, aoff.p, aoff.p + 1, st); CUB_CHECK(); }
+    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); DBuf<u64> lo1(habeg[nit] + 2, st);
+    { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); CUB_CHECK(); }
     Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
-    DBuf<i32> sc(NA, st); DBuf<u32> pred(NA, st); DBuf<u64> stack(NA, st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
-    k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, aoff.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK();
+    DBuf<i32> sc(habeg[nit], st); DBuf<u32> pred(habeg[nit], st); DBuf<u64> stack(habeg[nit], st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
+    k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK();
     u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
     std::sort(c2.begin(), c2.end(), [](const C2Rec& a, const C2Rec& b) { if (a.item != b.item) return a.item < b.item; if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
@@ -762,21 +955,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i32> esc(ES + 2, st);
     k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK();
     DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
-    // WFA rounds with growing per-warp slabs
-    DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids(nj); std::iota(ids.begin(), ids.end(), 0u); hw.resize(nj);
-    u64 ops_cap = 0; if (prm->output_seq) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
-    size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
-    u64 slab_words = 1ull << 20;  // 4 MB per warp to start
-    for (int round = 0; round < 6 && !ids.empty(); round++) {
-      u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)ix->sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
-      if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
-      DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
-      k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, prm->output_seq); KERNEL_CHECK();
-      std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
-      ids.swap(again); slab_words *= 8;
-    }
-    if (!ids.empty()) throw std::runtime_error("WFA workspace exhausted after 6 rounds");
-    if (prm->output_seq) { u64 used = ops_cur.to_host()[0]; hops = ops_pool.to_host(used); }
+    wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, hw, hops, ix->counters);
   }
   T.mark();                                                                                              // [5] extend + wfa
   // ---- finishing: scores, filters, ordering, rows (lib-index-search.go:2266-2357, :2701-2932; search.go:437-533)
@@ -836,12 +1015,12 @@ int lmg_index_open(const char* dir, int device, int shard, int n_shards, lmg_ind
 int lmg_index_info(const lmg_index* ix, lmg_info* o) { const Image& I = ix->img; o->k = I.k; o->masks = I.m; o->chunks = I.info.chunks; o->partitions = I.info.partitions; o->genomes = I.G; o->genome_batches = I.info.genome_batches;
   o->contig_interval = I.contig_interval; o->mask_prefix = I.mask_prefix; o->anchor_prefix = I.anchor_prefix; o->input_bases = I.total_bases; o->seed_keys = I.E; o->seed_values = I.V; o->image_bytes = I.bytes; return 0; }
 int lmg_genome_name(const lmg_index* ix, uint64_t genome, const char** name) { auto it = ix->img.bgi2dense.find(genome); if (it == ix->img.bgi2dense.end()) { *name = ""; return -1; } *name = ix->img.genome_names[it->second].c_str(); return 0; }
-void lmg_index_close(lmg_index* ix) { if (!ix) return; cudaSetDevice(ix->img.device); cudaStreamSynchronize(ix->st); ix->img.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } cudaStreamDestroy(ix->st); delete ix; }
+void lmg_index_close(lmg_index* ix) { if (!ix) return; cudaSetDevice(ix->img.device); cudaStreamSynchronize(ix->st); ix->img.release(); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } cudaStreamDestroy(ix->st); delete ix; }
 void lmg_free(void* p) { free(p); }
 int lmg_last_timing(const lmg_index* ix, double* ms16, uint64_t* c16) { for (int i = 0; i < 16; i++) { if (ms16) ms16[i] = ix->ms[i]; if (c16) c16[i] = ix->counters[i]; } if (c16) c16[15] = g_launches; return 0; }
 
 int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* kmers, uint32_t* nlocs, uint32_t* minloc, uint64_t* suf, uint64_t suf_cap, uint64_t* n_suf) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
     const int m = ix->img.m, k = ix->img.k; auto hc = cap.to_host(); auto hv = B.qvals.to_host(); auto ho = owner.to_host(); u64 ns = 0; std::vector<std::array<u64, 4>> trip;
     for (int q = 0; q < n; q++) { trip.clear();
       for (int i = 0; i < m; i++) { const Capture& c = hc[(u64)q * m + i]; u64 o = (u64)q * m + i; kmers[o] = c.kmer; nlocs[o] = c.kmer ? c.n : 0; u32 mn = 0xffffffffu; if (c.kmer) for (u32 t = 0; t < c.n; t++) mn = std::min(mn, hv[B.h_koff[q] + c.lo + t] & 0x7fffffffu); minloc[o] = c.kmer ? mn : 0;
@@ -851,7 +1030,7 @@ int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int3
 }
 
 int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_anchor** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
     Anchors A; seed_probe(ix, B, p, cap, owner, A, true); auto hi = A.hi.to_host(A.n), lo = A.lo.to_host(A.n); lmg_anchor* o = (lmg_anchor*)malloc(sizeof(lmg_anchor) * (A.n + 1));
     for (u64 i = 0; i < A.n; i++) { lmg_anchor& a = o[i]; u32 g = (u32)((hi[i] >> 2) & 0x3FFFFFFFFull); a.genome = ix->img.genome_bgi[g]; a.query = (u32)(hi[i] >> 36); a.qbegin = (i32)(lo[i] >> 36); a.len = (u8)(63 - ((lo[i] >> 30) & 63)); a.tbegin = (i32)((lo[i] >> 2) & 0x0FFFFFFF); a.qrc = (lo[i] >> 1) & 1; a.trc = lo[i] & 1; a.pad = 0; }
     *out = o; *n_out = A.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
@@ -860,7 +1039,7 @@ int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
 
 #define LMG_HAVE_CHAIN 1
 int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_chain** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
     Anchors A; seed_probe(ix, B, p, cap, owner, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
     lmg_chain* o = (lmg_chain*)malloc(sizeof(lmg_chain) * (C.n + 1));
     for (u32 i = 0; i < C.n; i++) { const ChainRec& r = C.h[i]; lmg_chain& c = o[i]; u64 key = S.h_key[r.seg]; c.query = (u32)(key >> 36); c.genome = ix->img.genome_bgi[(u32)((key >> 2) & 0x3FFFFFFFFull)]; c.score = r.score; c.n_seeds = r.nseeds;
@@ -870,7 +1049,7 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
 
 #define LMG_HAVE_SEARCH 1
 int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R;
+  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R;
     ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
@@ -887,13 +1066,9 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
       HspJob J; memset(&J, 0, sizeof J); J.q = i; J.g = i; J.tBegin = 0; J.tEnd = (i32)tl - 1; J.rc = 0; J.qlen = (i32)ql; J.tlen = (i32)tl; jobs[i] = J; ExtOut e; memset(&e, 0, sizeof e); e.qs = 0; e.qe = (i32)ql; e.ts = 0; e.te = (i32)tl; ex[i] = e; opsCap += ql + tl + 4; }
     qp.resize(qp.size() + 64, 0); tp.resize(tp.size() + 64, 0); qmk.resize(qp.size(), 0);
     DBuf<u8> dq(qp.size(), st), dt(tp.size(), st), dqm(qmk.size(), st); dqm.from_host(qmk.data(), qmk.size()); dq.from_host(qp.data(), qp.size()); dt.from_host(tp.data(), tp.size()); DBuf<u64> dqo(n + 1, st), dto(n + 1, st); dqo.from_host(qo.data(), n + 1); dto.from_host(to.data(), n + 1);
-    DBuf<HspJob> dj(n, st); dj.from_host(jobs.data(), n); DBuf<ExtOut> de(n, st); de.from_host(ex.data(), n); DBuf<WfaOut> dout(n, st); DBuf<u64> pool(opsCap + 2, st), cur(1, st); cur.zero();
-    std::vector<u32> ids(n); std::iota(ids.begin(), ids.end(), 0u); std::vector<WfaOut> hw(n); u64 slab_words = 1ull << 18;
-    for (int round = 0; round < 6 && !ids.empty(); round++) { u32 m = (u32)ids.size(); u32 warps = std::max(4u, (std::min<u32>(1024, m) / 4) * 4); DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> dids(m, st); dids.from_host(ids.data(), m); DBuf<u32> next(1, st); next.zero();
-      k_wfa<<<warps / 4, 128, 0, st>>>(dj.p, de.p, dids.p, m, next.p, dq.p, dqm.p, dqo.p, dt.p, dto.p, slabs.p, slab_words, dout.p, pool.p, cur.p, opsCap, 1); KERNEL_CHECK();
-      std::vector<WfaOut> o = dout.to_host(n); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; } ids.swap(again); slab_words *= 8; }
-    if (!ids.empty()) throw std::runtime_error("WFA workspace exhausted");
-    std::vector<u64> ops = pool.to_host(cur.to_host()[0]); std::string out;
+    DBuf<HspJob> dj(n, st); dj.from_host(jobs.data(), n); DBuf<ExtOut> de(n, st); de.from_host(ex.data(), n); (void)opsCap;
+    cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); std::vector<WfaOut> hw; std::vector<u64> ops; u64 counters[16] = {0};
+    wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, hw, ops, counters); std::string out;
     for (int i = 0; i < n; i++) { for (i64 x = (i64)hw[i].ops_n - 1; x >= 0; x--) { u64 op = ops[hw[i].ops_off + x]; out += std::to_string((u32)(op & 0xffffffffu)); out.push_back((char)(op >> 32)); } out.push_back('\n'); }
     char* c = (char*)malloc(out.size() + 1); memcpy(c, out.data(), out.size() + 1); *cigars = c; *cigars_len = out.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
@@ -903,7 +1078,7 @@ int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, 
   try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; upload_queries(ix, seqs, off, n, Q->B); CUDA_CHECK(cudaStreamSynchronize(ix->st)); *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int lmg_search_staged(lmg_index* ix, const lmg_params* p, lmg_queries* q, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R;
+  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R;
     ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
