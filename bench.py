@@ -173,7 +173,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = int(idx.timing()[1][15])
-    ms_steps, stage_ms, probe_ms, nrows, wall_ms, e2e_lib_ms, e2e_stage = [], np.zeros(8), [], 0, [], [], np.zeros(8)
+    ms_steps, stage_ms, probe_ms, nrows, wall_ms, e2e_lib_ms, e2e_stage, kern_ms, kcnt = [], np.zeros(8), [], 0, [], [], np.zeros(8), np.zeros(16), None
     for _ in range(a.steps):
         nrows = idx.search_staged(staged, prm, collect=False)
         ms, cnt = idx.timing()
@@ -181,6 +181,8 @@ def main():
         stage_ms += ms[:8]
         probe_ms.append(ms[8])
         wall_ms.append(ms[9])
+        kern_ms += ms
+        kcnt = cnt
     sync_all()
     launches = (int(idx.timing()[1][15]) - launches0) // max(a.steps, 1)
     # ---- e2e leg: host buffers in, rows out, every step
@@ -231,7 +233,9 @@ def main():
            "roofline": {"bound": "hbm", "kernel": "k_probe_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_probe * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},
-           "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage]},
+           "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage],
+                     "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep", 10), ("wfa_fast", 11), ("wfa_general", 12), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
+                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11])},
            "clocks": sampler.summary()}
     print(json.dumps(out))
     idx.free_staged(staged)

@@ -38,6 +38,8 @@ typedef struct lmg_params {
   int32_t output_seq;        /* -a/--all: fill CIGAR/qseq/sseq/align */
   double  min_pident;        /* -i/--align-min-match-pident 70 */
   double  min_qcov_hsp;      /* -q/--min-qcov-per-hsp 0 */
+  int32_t wfa_adaptive;      /* 1 = WFA adaptive wavefront reduction (MinWFLen 10, MaxDistDiff 50) as the reference enables at lib-index-search.go:1911; 0 = exact */
+  int32_t reserved;
 } lmg_params;
 
 typedef struct lmg_info {          /* IndexInfo, lib-index-build.go:1914-1932 */
@@ -113,7 +115,7 @@ int  lmg_anchor_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, 
 /* ClearSubstrPairs + Chainer.Chain (lib-index-search.go:864-990, lib-chaining.go:122-633) */
 int  lmg_chain_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, const uint64_t* seq_off, int32_t n, lmg_chain** out, uint64_t* n_out);
 /* WFA batch (wfa.Aligner.Align): pairs of ASCII sequences -> CIGAR strings in wfa convention, '\n' separated */
-int  lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off /*2n+1*/, int32_t n, char** cigars, uint64_t* cigars_len);
+int  lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off /*2n+1*/, int32_t n, int32_t adaptive, char** cigars, uint64_t* cigars_len);
 void lmg_free(void* p);
 
 #ifdef __cplusplus

@@ -14,7 +14,7 @@ class Params(C.Structure):  # lmg_params
                 ("max_gap", C.c_float), ("max_distance", C.c_float), ("ext_len", C.c_int32), ("ext_len2", C.c_int32),
                 ("min_qcov_genome", C.c_double), ("max_evalue", C.c_double),
                 ("align_max_gap", C.c_int32), ("align_min_len", C.c_int32), ("align_band", C.c_int32), ("output_seq", C.c_int32),
-                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double)]
+                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double), ("wfa_adaptive", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Info(C.Structure):  # lmg_info
@@ -60,7 +60,7 @@ def load_library():
     L.lmg_mask_batch.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, u64p]
     L.lmg_anchor_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_chain_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
-    L.lmg_wfa_batch.argtypes = [C.c_int, vp, vp, C.c_int32, C.POINTER(vp), u64p]
+    L.lmg_wfa_batch.argtypes = [C.c_int, vp, vp, C.c_int32, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_free.argtypes = [vp]
     _lib = L
     return L
@@ -223,14 +223,14 @@ class Index:
         return self._stage(self.lib.lmg_chain_batch, CHAIN_DTYPE, seqs, params)
 
 
-def wfa_batch(pairs, device=0):
+def wfa_batch(pairs, device=0, adaptive=1):
     L = load_library()
     flat = []
     for q, t in pairs:
         flat += [q, t]
     buf, off = pack_queries(flat)
     ptr, n = C.c_void_p(), C.c_uint64()
-    if L.lmg_wfa_batch(device, buf.ctypes.data, off.ctypes.data, len(pairs), C.byref(ptr), C.byref(n)) != 0:
+    if L.lmg_wfa_batch(device, buf.ctypes.data, off.ctypes.data, len(pairs), adaptive, C.byref(ptr), C.byref(n)) != 0:
         raise RuntimeError(L.lmg_last_error().decode())
     s = C.string_at(ptr, n.value).decode()
     L.lmg_free(ptr)

@@ -174,6 +174,7 @@ struct lmg_index {
 };
 
 static thread_local std::string g_err;
+struct KTimer { cudaEvent_t a, b; cudaStream_t st; double* dst; KTimer(cudaStream_t s, double* d) : st(s), dst(d) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); } ~KTimer() { cudaEventRecord(b, st); cudaEventSynchronize(b); float f = 0; cudaEventElapsedTime(&f, a, b); *dst += f; cudaEventDestroy(a); cudaEventDestroy(b); } };
 // activates the index's arena for the calling thread and rewinds it when the batch is done (all DBufs of the batch are dead by then)
 struct ArenaReset { lmg_index* ix; ArenaScope sc; ArenaReset(lmg_index* i) : ix(i), sc(&i->arena) {} ~ArenaReset() { cudaStreamSynchronize(ix->st); ix->arena.reset(); } };
 
@@ -591,10 +592,10 @@ __device__ __forceinline__ u32 tbase(const SeqView& v, i32 i) { return win_base(
 
 // number of equal 2-mer pairs between q[qa..qa+n1) and t[ta..ta+n2) (dirq/dirt = +1 forward, -1 reversed flank)
 __device__ u32 ext_count(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt) {
-  if (n1 < 2 || n2 < 2) return 0; u32 c1[16], c2[16]; for (int i = 0; i < 16; i++) c1[i] = c2[i] = 0;
-  for (i32 i = 0; i + 1 < n1; i++) c1[(qbase(v, qa + dq * i) << 2) | qbase(v, qa + dq * (i + 1))]++;
-  for (i32 i = 0; i + 1 < n2; i++) c2[(tbase(v, ta + dt * i) << 2) | tbase(v, ta + dt * (i + 1))]++;
-  u32 t = 0; for (int i = 0; i < 16; i++) t += c1[i] * c2[i]; return t;
+  if (n1 < 2 || n2 < 2) return 0; u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;   // 16 byte-wide counters per sequence packed in two words (flanks <= 130 bases)
+  u32 p = qbase(v, qa); for (i32 i = 1; i < n1; i++) { u32 c = qbase(v, qa + dq * i); u32 m = (p << 2) | c; if (m < 8) a0 += 1ull << (8 * m); else a1 += 1ull << (8 * (m - 8)); p = c; }
+  p = tbase(v, ta); for (i32 i = 1; i < n2; i++) { u32 c = tbase(v, ta + dt * i); u32 m = (p << 2) | c; if (m < 8) b0 += 1ull << (8 * m); else b1 += 1ull << (8 * (m - 8)); p = c; }
+  u32 t = 0; for (int i = 0; i < 8; i++) { t += (u32)((a0 >> (8 * i)) & 255) * (u32)((b0 >> (8 * i)) & 255) + (u32)((a1 >> (8 * i)) & 255) * (u32)((b1 >> (8 * i)) & 255); } return t;
 }
 // _extendRight: anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10, BandCount 20), best chain end + 1
 __device__ void ext_run(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i32* __restrict__ sc, u16* __restrict__ pj, i32* e1, i32* e2) {
@@ -642,13 +643,13 @@ __global__ void k_extend_final(const HspJob* __restrict__ jobs, u32 njobs, const
 // ---------------- WFA
 #define WF_NULL (-1073741824)
 struct WfaOut { i32 qbegin, qend, tbegin, tend, alen, matches, gaps, bscore, has_m, wscore, status; u32 ops_n; u64 ops_off; };   // status 0 ok, 1 workspace overflow
-struct WfDir { i32 lo, hi; u32 base; u32 nullmask; };   // nullmask bit0 M, bit1 I, bit2 D null; base = index of M offsets; I at base+w, D at base+2w
+struct WfDir { i32 lo, hi; u32 base; u32 nullmask; i32 elo, ehi; };   // [lo,hi] = stored range (M at base, I at base+w, D at base+2w); [elo,ehi] = effective range after adaptive reduction; nullmask bit0 M, bit1 I, bit2 D
 
 // One warp per alignment; persistent warps pull jobs from a queue. Wavefront offsets live in a per-warp HBM slab
 // (directory + offsets), lanes own diagonals, extension compares bases straight from the 2-bit genome / query arrays.
 __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 njobs, u32* __restrict__ next_job,
                                              const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
-                                             i32* __restrict__ slabs, u64 slab_words, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+                                             i32* __restrict__ slabs, u64 slab_words, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int adaptive) {
   const int X = 4, OE = 8, E = 2, STEP = 2; int lane = threadIdx.x & 31; u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i32* slab = slabs + (u64)warp * slab_words;
   for (;;) {
     u32 ji = 0; if (lane == 0) ji = atomicAdd(next_job, 1u); ji = __shfl_sync(FULLMASK, ji, 0); if (ji >= njobs) return; u32 jb = job_ids[ji];
@@ -656,19 +657,19 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
     const i32 q0 = ex.qs, t0 = ex.ts, plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen;
     WfaOut R; R.qbegin = R.qend = R.tbegin = R.tend = R.alen = R.matches = R.gaps = R.bscore = R.has_m = 0; R.wscore = 0; R.status = 0; R.ops_n = 0; R.ops_off = 0;
     // slab layout: [directory: ndir x 4 words][offsets ...]
-    const u32 ndir = (u32)((4 * (i64)max(plen, tlen) + 16) / STEP + 2); WfDir* dir = (WfDir*)slab; u64 used = (u64)ndir * 4; bool overflow = used + 64 > slab_words;
+    const u32 ndir = (u32)((4 * (i64)max(plen, tlen) + 16) / STEP + 2); WfDir* dir = (WfDir*)slab; u64 used = (u64)ndir * 6; bool overflow = used + 64 > slab_words;
     i32* offs = slab;
     auto extend = [&](i32 k, i32 h) { i32 vv = h - k; while (vv < plen && h < tlen && qcmp(v, q0 + vv) == tbase(v, t0 + h)) { vv++; h++; } return h; };
     auto getw = [&](i32 sidx, int comp, i32 k) -> i32 { if (sidx < 0) return WF_NULL; WfDir d = dir[sidx]; if ((d.nullmask >> comp) & 1) return WF_NULL; if (k < d.lo || k > d.hi) return WF_NULL; return offs[d.base + (u32)comp * (u32)(d.hi - d.lo + 1) + (u32)(k - d.lo)]; };
     i32 s = 0; bool done = false;
-    if (!overflow) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = 0; d.base = (u32)used; d.nullmask = 6; dir[0] = d; offs[used] = extend(0, 0); } used += 3; __syncwarp(); done = (getw(0, 0, kend) >= tlen); }
+    if (!overflow) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = 0; d.elo = 0; d.ehi = 0; d.base = (u32)used; d.nullmask = 6; dir[0] = d; offs[used] = extend(0, 0); } used += 3; __syncwarp(); done = (getw(0, 0, kend) >= tlen); }
     while (!done && !overflow) {
       s += STEP; i32 si = s / STEP; if ((u32)si >= ndir) { overflow = true; break; }
       i32 ix = (s - X) / STEP, io = (s - OE) / STEP, ie = (s - E) / STEP; bool hx = s - X >= 0, ho = s - OE >= 0, he = s - E >= 0;
-      WfDir dx, dop, de; dx.nullmask = 7; dop.nullmask = 7; de.nullmask = 7; dx.lo = dx.hi = dop.lo = dop.hi = de.lo = de.hi = 0; if (hx) dx = dir[ix]; if (ho) dop = dir[io]; if (he) de = dir[ie];
+      WfDir dx, dop, de; dx.nullmask = 7; dop.nullmask = 7; de.nullmask = 7; dx.lo = dx.hi = dop.lo = dop.hi = de.lo = de.hi = 0; dx.elo = dx.ehi = dop.elo = dop.ehi = de.elo = de.ehi = 0; if (hx) dx = dir[ix]; if (ho) dop = dir[io]; if (he) de = dir[ie];
       bool nx = dx.nullmask & 1, no = dop.nullmask & 1, ni = (de.nullmask >> 1) & 1, nd = (de.nullmask >> 2) & 1;
-      if (nx && no && ni && nd) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = -1; d.base = 0; d.nullmask = 7; dir[si] = d; } __syncwarp(); continue; }
-      i32 lo = INT32_MAX, hi = INT32_MIN; if (!nx) { lo = min(lo, dx.lo); hi = max(hi, dx.hi); } if (!no) { lo = min(lo, dop.lo - 1); hi = max(hi, dop.hi + 1); } if (!ni || !nd) { lo = min(lo, de.lo - 1); hi = max(hi, de.hi + 1); }
+      if (nx && no && ni && nd) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = -1; d.elo = 0; d.ehi = -1; d.base = 0; d.nullmask = 7; dir[si] = d; } __syncwarp(); continue; }
+      i32 lo = INT32_MAX, hi = INT32_MIN; if (!nx) { lo = min(lo, dx.elo); hi = max(hi, dx.ehi); } if (!no) { lo = min(lo, dop.elo - 1); hi = max(hi, dop.ehi + 1); } if (!ni || !nd) { lo = min(lo, de.elo - 1); hi = max(hi, de.ehi + 1); }
       u32 w = (u32)(hi - lo + 1); if (used + 3ull * w + 64 > slab_words) { overflow = true; break; }
       u32 base = (u32)used; bool anyM = false, anyI = false, anyD = false;
       for (i32 k = lo + lane; k <= hi; k += 32) {
@@ -681,8 +682,22 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
         i32 mm = max(mis, max(ins, del)); if (mm > WF_NULL) { mm = extend(k, mm); anyM = true; } anyI |= ins > WF_NULL; anyD |= del > WF_NULL;
         offs[base + (u32)(k - lo)] = mm; offs[base + w + (u32)(k - lo)] = ins; offs[base + 2 * w + (u32)(k - lo)] = del;
       }
-      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD);
-      if (lane == 0) { WfDir d; d.lo = lo; d.hi = hi; d.base = base; d.nullmask = (anyM ? 0 : 1) | (anyI ? 0 : 2) | (anyD ? 0 : 4); dir[si] = d; }
+      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD); __syncwarp();
+      i32 elo = lo, ehi = hi;
+      if (adaptive && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction (MinWFLen 10, MaxDistDiff 50), target diagonal preserved
+        i32 mind = INT32_MAX; for (i32 k = lo + lane; k <= hi; k += 32) { i32 o = offs[base + (u32)(k - lo)]; if (o > WF_NULL) mind = min(mind, max(plen - (o - k), tlen - o)); }
+        for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o));
+        i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
+        for (i32 b0 = lo; b0 < top_limit && !found; b0 += 32) { i32 k = b0 + lane; bool okk = false; if (k < top_limit) { i32 o = offs[base + (u32)(k - lo)]; okk = (o > WF_NULL) && (max(plen - (o - k), tlen - o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nlo = b0 + __ffs(bal) - 1; found = true; } }
+        if (!found && top_limit > lo) nlo = top_limit;
+        i32 bottom_limit = max(kend, nlo); i32 nhi = hi; found = false;
+        for (i32 b0 = hi; b0 > bottom_limit && !found; b0 -= 32) { i32 k = b0 - lane; bool okk = false; if (k > bottom_limit) { i32 o = offs[base + (u32)(k - lo)]; okk = (o > WF_NULL) && (max(plen - (o - k), tlen - o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nhi = b0 - (__ffs(bal) - 1); found = true; } }
+        if (!found && hi > bottom_limit) nhi = bottom_limit;
+        if (nlo != lo || nhi != hi) { for (i32 k = lo + lane; k <= hi; k += 32) if (k < nlo || k > nhi) { offs[base + (u32)(k - lo)] = WF_NULL; offs[base + w + (u32)(k - lo)] = WF_NULL; offs[base + 2 * w + (u32)(k - lo)] = WF_NULL; }
+          __syncwarp(); bool aM = false, aI = false, aD = false; for (i32 k = nlo + lane; k <= nhi; k += 32) { aM |= offs[base + (u32)(k - lo)] > WF_NULL; aI |= offs[base + w + (u32)(k - lo)] > WF_NULL; aD |= offs[base + 2 * w + (u32)(k - lo)] > WF_NULL; }
+          anyM = __any_sync(FULLMASK, aM); anyI = __any_sync(FULLMASK, aI); anyD = __any_sync(FULLMASK, aD); elo = nlo; ehi = nhi; }
+      }
+      if (lane == 0) { WfDir d; d.lo = lo; d.hi = hi; d.elo = elo; d.ehi = ehi; d.base = base; d.nullmask = (anyM ? 0 : 1) | (anyI ? 0 : 2) | (anyD ? 0 : 4); dir[si] = d; }
       used += 3ull * w; __syncwarp();
       done = (getw(si, 0, kend) >= tlen);
     }
@@ -746,7 +761,7 @@ __global__ void k_wfa_prep(const HspJob* __restrict__ jobs, const ExtOut* __rest
 __device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos) { u32 i = (u32)pos >> 5, sh = ((u32)pos & 31) * 2; u64 a = W[i]; if (sh == 0) return a; return (a << sh) | (W[i + 1] >> (64 - sh)); }
 
 __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, u32 njobs, u32* __restrict__ next_job,
-                                                          u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+                                                          u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int adaptive) {
   __shared__ u16 ring[WF_WARPS][9][WFS];   // 0-4: M levels (L%5), 5-6: I (L%2), 7-8: D (L%2)
   const int X2 = 2, OE2 = 4, E2 = 1;        // penalties 4 / 8 / 2 in units of levels (score = 2*level)
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u32 warp = blockIdx.x * WF_WARPS + wib; u16* slab = slabs + (u64)warp * WF_LMAX * 3 * WFS; u16 (*R)[WFS] = ring[wib]; u64* ops = ops_scratch + (u64)warp * WF_OPSMAX;
@@ -757,24 +772,25 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
     if (plen >= 65000 || tlen >= 65000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
     auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = (fetch64(Q, v) ^ fetch64(T, h)) | fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
-    // level 0
-    i32 glo = 0, ghi = 0; i32 hlo[4], hhi[4]; u32 hnull[4];   // history of levels L-1..L-4: lo, hi, null bits (1 M, 2 I, 4 D)
-    for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
+    // level 0. History of levels L-1..L-4: effective lo/hi (after reduction), null bits (1 M, 2 I, 4 D). Every level writes the diagonals
+    // [min(lo, rlo) - PAD, max(hi, rhi) + PAD] where [rlo,rhi] spans the effective ranges of the last 4 non-null levels, so later levels and
+    // the backtrace can read k-1 / k+1 of any source level without bounds checks.
+    i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
     { i32 h0 = 0; if (lane == 0) h0 = extend(0, 0); h0 = __shfl_sync(FULLMASK, h0, 0);
       for (i32 k = -WF_PAD + lane; k <= WF_PAD; k += 32) { u16 mv = (k == 0) ? (u16)h0 : (u16)0xFFFF; R[0][k + WFK0] = mv; slab[k + WFK0] = mv; slab[WFS + k + WFK0] = 0xFFFF; slab[2 * WFS + k + WFK0] = 0xFFFF; R[5][k + WFK0] = 0xFFFF; R[7][k + WFK0] = 0xFFFF; }
-      hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; __syncwarp();
-      if (kend == 0 && h0 >= tlen) { /* done at score 0 */ } }
-    i32 L = 0; bool done = (kend == 0 && (i32)R[0][WFK0] >= tlen && R[0][WFK0] != 0xFFFF), overflow = false;
+      hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; __syncwarp(); }
+    i32 L = 0; bool done = (kend == 0 && R[0][WFK0] != 0xFFFF && (i32)R[0][WFK0] >= tlen), overflow = false;
     while (!done) {
       L++; if (L >= WF_LMAX) { overflow = true; break; }
-      // sources: M[L-2] (mismatch), M[L-4] (gap open), I/D[L-1] (gap extend); history index = distance-1
       bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; bool allnull = nx && no && ni && nd;
-      if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); }
-        glo = min(glo, lo); ghi = max(ghi, hi); if (glo <= -(WF_WMAX / 2) || ghi >= WF_WMAX / 2) { overflow = true; break; } }
+      if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
+      i32 rlo = INT32_MAX, rhi = INT32_MIN; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { rlo = min(rlo, hlo[i]); rhi = max(rhi, hhi[i]); }
+      i32 wl = min(allnull ? INT32_MAX : lo, rlo), wh = max(allnull ? INT32_MIN : hi, rhi); if (wl > wh) { wl = 0; wh = 0; }
+      if (wl <= -(WF_WMAX / 2) || wh >= WF_WMAX / 2) { overflow = true; break; }
       const u16* M2 = R[(L + 5 - X2) % 5]; const u16* M4 = R[(L + 5 - OE2) % 5]; const u16* I1 = R[5 + ((L + 1) & 1)]; const u16* D1 = R[7 + ((L + 1) & 1)];
       u16* Mo = R[L % 5]; u16* Io = R[5 + (L & 1)]; u16* Do = R[7 + (L & 1)]; u16* G = slab + (u64)L * 3 * WFS; bool anyM = false, anyI = false, anyD = false;
-      for (i32 k = glo - WF_PAD + lane; k <= ghi + WF_PAD; k += 32) {
+      for (i32 k = wl - WF_PAD + lane; k <= wh + WF_PAD; k += 32) {
         u16 om = 0xFFFF, oi = 0xFFFF, od = 0xFFFF; int x = k + WFK0;
         if (!allnull && k >= lo && k <= hi) {
           i32 a = (L >= OE2) ? (i32)M4[x - 1] : 0xFFFF, b = (i32)I1[x - 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 ins = max(a, b); ins = (ins < 0) ? -1 : ins + 1;
@@ -787,7 +803,20 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
         }
         Mo[x] = om; Io[x] = oi; Do[x] = od; G[x] = om; G[WFS + x] = oi; G[2 * WFS + x] = od;
       }
-      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD);
+      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD); __syncwarp();
+      if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa and the oracle
+        i32 mind = INT32_MAX; for (i32 k = lo + lane; k <= hi; k += 32) { u16 o = Mo[k + WFK0]; if (o != 0xFFFF) mind = min(mind, max(plen - ((i32)o - k), tlen - (i32)o)); }
+        for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o));
+        i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
+        for (i32 b0 = lo; b0 < top_limit && !found; b0 += 32) { i32 k = b0 + lane; bool okk = false; if (k < top_limit) { u16 o = Mo[k + WFK0]; okk = (o != 0xFFFF) && (max(plen - ((i32)o - k), tlen - (i32)o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nlo = b0 + __ffs(bal) - 1; found = true; } }
+        if (!found && top_limit > lo) nlo = top_limit;
+        i32 bottom_limit = max(kend, nlo); i32 nhi = hi; found = false;
+        for (i32 b0 = hi; b0 > bottom_limit && !found; b0 -= 32) { i32 k = b0 - lane; bool okk = false; if (k > bottom_limit) { u16 o = Mo[k + WFK0]; okk = (o != 0xFFFF) && (max(plen - ((i32)o - k), tlen - (i32)o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nhi = b0 - (__ffs(bal) - 1); found = true; } }
+        if (!found && hi > bottom_limit) nhi = bottom_limit;
+        if (nlo != lo || nhi != hi) { for (i32 k = lo + lane; k <= hi; k += 32) if (k < nlo || k > nhi) { int x = k + WFK0; Mo[x] = 0xFFFF; Io[x] = 0xFFFF; Do[x] = 0xFFFF; G[x] = 0xFFFF; G[WFS + x] = 0xFFFF; G[2 * WFS + x] = 0xFFFF; }
+          __syncwarp(); bool aM = false, aI = false, aD = false; for (i32 k = nlo + lane; k <= nhi; k += 32) { int x = k + WFK0; aM |= Mo[x] != 0xFFFF; aI |= Io[x] != 0xFFFF; aD |= Do[x] != 0xFFFF; }
+          anyM = __any_sync(FULLMASK, aM); anyI = __any_sync(FULLMASK, aI); anyD = __any_sync(FULLMASK, aD); lo = nlo; hi = nhi; }
+      }
       for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
       __syncwarp();
@@ -825,16 +854,16 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
 }
 
 static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
-                        int want_ops, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters) {
+                        int want_ops, int adaptive, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters, double* ms) {
     // WFA: fast kernel (packed words + smem ring) for every job, then the general kernel for whatever did not fit
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
       DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st);
-      k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p); KERNEL_CHECK();
+      { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p); KERNEL_CHECK(); }
       u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (nj + WF_WARPS - 1) / WF_WARPS); u64 nwarps = (u64)blocks * WF_WARPS;
       DBuf<u16> fslabs(nwarps * WF_LMAX * 3 * WFS, st); DBuf<u64> oscr(want_ops ? nwarps * WF_OPSMAX : 8, st); DBuf<u32> next(1, st); next.zero();
-      k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, nj, next.p, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+      { KTimer kt(st, &ms[11]); k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, nj, next.p, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); }
       std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
       counters[9] = nj; counters[10] = ids.size(); }
     size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
@@ -843,7 +872,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
       if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
       DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
-      k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+      { KTimer kt(st, &ms[12]); k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); } counters[11] += n;
       std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
       ids.swap(again); slab_words *= 8;
     }
@@ -877,7 +906,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); T.mark();   // [1] sketch
   Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); T.mark();              // [2] probe
   Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); T.mark();                // [3] chain
-  for (int i = 0; i < 8; i++) ix->ms[i] = 0;
+  for (int i = 0; i < 16; i++) if (i != 8 && i != 9) ix->ms[i] = 0; ix->counters[11] = 0;
   auto finish_times = [&](int upto) { const int map_[6] = {0, 1, 2, 3, 4, 5}; (void)map_; CUDA_CHECK(cudaStreamSynchronize(st)); for (int i = 0; i < upto; i++) ix->ms[i] = T.ms(i, i + 1); ix->ms[7] = T.ms(0, upto); ix->counters[6] = B.total_bases; ix->counters[7] = (u64)B.nq; };
   if (Cn.n == 0) { T.mark(); finish_times(4); return; }
   // ---- windows (lib-index-search.go:1987-2051)
@@ -904,7 +933,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
     if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
-    k_pa_anchors2<<<nit, 128, smemW, st>>>(d_items.p, nullptr, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK();
+    { KTimer kt(st, &ix->ms[14]); k_pa_anchors2<<<nit, 128, smemW, st>>>(d_items.p, nullptr, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); }
     hcnt = cnt.to_host(nit); bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
     if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
   std::vector<C2Rec> c2;
@@ -913,7 +942,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); CUB_CHECK(); }
     Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
     DBuf<i32> sc(habeg[nit], st); DBuf<u32> pred(habeg[nit], st); DBuf<u64> stack(habeg[nit], st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
-    k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK();
+    { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
     u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
     std::sort(c2.begin(), c2.end(), [](const C2Rec& a, const C2Rec& b) { if (a.item != b.item) return a.item < b.item; if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
@@ -950,12 +979,12 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   u32 nj = (u32)jobs.size(); std::vector<ExtOut> hext; std::vector<WfaOut> hw; std::vector<u64> hops;
   if (nj) {
     DBuf<HspJob> d_jobs(nj, st); d_jobs.from_host(jobs.data(), nj); DBuf<u32> ecnt(2 * (u64)nj + 1, st); DBuf<i32> eres(4 * (u64)nj, st);
-    k_extend<true><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p, nullptr, nullptr, nullptr, nullptr, nullptr); KERNEL_CHECK();
+    { KTimer kt(st, &ix->ms[13]); k_extend<true><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p, nullptr, nullptr, nullptr, nullptr, nullptr); KERNEL_CHECK(); }
     std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); std::vector<u64> hso(2 * (u64)nj + 1, 0); for (u64 i = 0; i < 2 * (u64)nj; i++) hso[i + 1] = hso[i] + hec[i]; u64 ES = hso.back();
     DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i32> esc(ES + 2, st);
-    k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK();
+    { KTimer kt(st, &ix->ms[13]); k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK(); }
     DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
-    wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, hw, hops, ix->counters);
+    wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, prm->wfa_adaptive, hw, hops, ix->counters, ix->ms);
   }
   T.mark();                                                                                              // [5] extend + wfa
   // ---- finishing: scores, filters, ordering, rows (lib-index-search.go:2266-2357, :2701-2932; search.go:437-533)
@@ -1001,7 +1030,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
 extern "C" {
 
 void lmg_default_params(lmg_params* p) { p->min_prefix = 15; p->min_single_prefix = 17; p->top_n_genomes = 0; p->top_n_chains = 0; p->max_gap = 50; p->max_distance = 1000; p->ext_len = 1000; p->ext_len2 = 50;
-  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; }
+  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; p->wfa_adaptive = 1; p->reserved = 0; }
 const char* lmg_last_error(void) { return g_err.c_str(); }
 
 int lmg_index_open(const char* dir, int device, int shard, int n_shards, lmg_index** out) {
@@ -1058,7 +1087,7 @@ int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) {
 void lmg_results_free(lmg_results* r) { delete r; }
 
 #define LMG_HAVE_WFA 1
-int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t n, char** cigars, uint64_t* cigars_len) {
+int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t n, int32_t adaptive, char** cigars, uint64_t* cigars_len) {
   try { CUDA_CHECK(cudaSetDevice(device)); cudaStream_t st = 0; std::vector<u8> qp, tp, qmk; std::vector<u64> qo(n + 1), to(n + 1); std::vector<HspJob> jobs(n); std::vector<ExtOut> ex(n);
     auto pack = [](const u8* s, u64 len, std::vector<u8>& out) { while (out.size() & 15) out.push_back(0); u64 o = out.size(); out.resize(o + (len + 3) / 4 + 16, 0); for (u64 i = 0; i < len; i++) out[o + (i >> 2)] |= (u8)(base2bit(s[i]) << (6 - 2 * (i & 3))); return o; };
     u64 opsCap = 0;
@@ -1067,8 +1096,8 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
     qp.resize(qp.size() + 64, 0); tp.resize(tp.size() + 64, 0); qmk.resize(qp.size(), 0);
     DBuf<u8> dq(qp.size(), st), dt(tp.size(), st), dqm(qmk.size(), st); dqm.from_host(qmk.data(), qmk.size()); dq.from_host(qp.data(), qp.size()); dt.from_host(tp.data(), tp.size()); DBuf<u64> dqo(n + 1, st), dto(n + 1, st); dqo.from_host(qo.data(), n + 1); dto.from_host(to.data(), n + 1);
     DBuf<HspJob> dj(n, st); dj.from_host(jobs.data(), n); DBuf<ExtOut> de(n, st); de.from_host(ex.data(), n); (void)opsCap;
-    cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); std::vector<WfaOut> hw; std::vector<u64> ops; u64 counters[16] = {0};
-    wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, hw, ops, counters); std::string out;
+    cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); std::vector<WfaOut> hw; std::vector<u64> ops; u64 counters[16] = {0}; double dms[16] = {0};
+    wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, adaptive, hw, ops, counters, dms); std::string out;
     for (int i = 0; i < n; i++) { for (i64 x = (i64)hw[i].ops_n - 1; x >= 0; x--) { u64 op = ops[hw[i].ops_off + x]; out += std::to_string((u32)(op & 0xffffffffu)); out.push_back((char)(op >> 32)); } out.push_back('\n'); }
     char* c = (char*)malloc(out.size() + 1); memcpy(c, out.data(), out.size() + 1); *cigars = c; *cigars_len = out.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
@@ -1097,6 +1126,6 @@ int lmg_results_seq_id(const lmg_results*, uint64_t, const char**) { return -2; 
 void lmg_results_free(lmg_results*) {}
 #endif
 #ifndef LMG_HAVE_WFA
-int lmg_wfa_batch(int, const uint8_t*, const uint64_t*, int32_t, char**, uint64_t*) { g_err = "lmg_wfa_batch: not implemented"; return -2; }
+int lmg_wfa_batch(int, const uint8_t*, const uint64_t*, int32_t, int32_t, char**, uint64_t*) { g_err = "lmg_wfa_batch: not implemented"; return -2; }
 #endif
 }

@@ -9,7 +9,7 @@ using namespace lmo;
 
 extern "C" {
 typedef struct lmo_params { int32_t min_prefix, min_single_prefix, top_n_genomes, top_n_chains; float max_gap, max_distance; int32_t ext_len, ext_len2; double min_qcov_genome, max_evalue;
-  int32_t align_max_gap, align_min_len, align_band, output_seq; double min_pident, min_qcov_hsp; } lmo_params;
+  int32_t align_max_gap, align_min_len, align_band, output_seq; double min_pident, min_qcov_hsp; int32_t wfa_adaptive, reserved; } lmo_params;
 typedef struct lmo_hsp { uint32_t query, hits; uint64_t genome; uint32_t seq_idx, n_seqs, chunk_idx, n_chunks; int32_t seq_len, cls, hsp, qb, qe, tb, te, rc, alen, matches, gaps, score, bitscore, pad0;
   double evalue, qcov_hsp, pident, qcov_gnm; uint64_t cigar_off; uint32_t cigar_len, pad; } lmo_hsp;
 typedef struct lmo_anchor { uint64_t genome; uint32_t query; int32_t qbegin, tbegin; uint8_t len, qrc, trc, pad; } lmo_anchor;
@@ -100,7 +100,7 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
           int ext2 = P.ext_len2; if (c.aligned_q > 1000000) ext2 += 80; else if (c.aligned_q > 250000) ext2 += 40; else if (c.aligned_q > 50000) ext2 += 20; else if (c.aligned_q > 10000) ext2 += 10;
           if (start < 0 || end > tlenSeq || c.qb < 0 || c.qe + 1 > qlen) { c.dead = true; continue; }  // Go would panic on the slice; never observed
           Extended ex = extend_match(s, tseq, c.qb, c.qe + 1, start, end, ext2, c.tb, c.max_ext_len, rc);
-          int ql = ex.end1 - ex.start1, tl = ex.end2 - ex.start2; WfaResult cg = wfa_align(s.data() + ex.start1, ql, tseq.data() + ex.start2, tl);
+          int ql = ex.end1 - ex.start1, tl = ex.end2 - ex.start2; WfaResult cg = wfa_align(s.data() + ex.start1, ql, tseq.data() + ex.start2, tl, P.wfa_adaptive);
           score_evalue(cg, ql, ix.total_bases, &c.score, &c.bitscore, &c.evalue); if (c.evalue > P.max_evalue) { c.dead = true; continue; }
           c.qb -= ex.s1; c.qe += ex.e1; c.qb = c.qb + cg.qbegin - 1; c.qe = c.qe - (ql - cg.qend);
           if (rc) { c.tb -= ex.e2; c.te += ex.s2; c.tb = c.tb + (tl - cg.tend); c.te = variantA ? (c.te - cg.tbegin - 1) : (c.te - (cg.tbegin - 1)); }   // :2284-2285 vs :2551-2552
@@ -164,7 +164,7 @@ struct Rows { std::vector<lmo_hsp> rows; std::string pool; std::vector<std::stri
 
 static Params to_params(const lmo_params* p) { Params P; if (!p) return P; P.min_prefix = p->min_prefix; P.min_single_prefix = p->min_single_prefix; P.top_n_genomes = p->top_n_genomes; P.top_n_chains = p->top_n_chains;
   P.max_gap = p->max_gap; P.max_distance = p->max_distance; P.ext_len = p->ext_len; P.ext_len2 = p->ext_len2; P.min_qcov_genome = p->min_qcov_genome; P.max_evalue = p->max_evalue;
-  P.align_max_gap = p->align_max_gap; P.align_min_len = p->align_min_len; P.align_band = p->align_band; P.min_pident = p->min_pident; P.min_qcov_hsp = p->min_qcov_hsp; P.output_seq = p->output_seq; return P; }
+  P.align_max_gap = p->align_max_gap; P.align_min_len = p->align_min_len; P.align_band = p->align_band; P.min_pident = p->min_pident; P.min_qcov_hsp = p->min_qcov_hsp; P.output_seq = p->output_seq; P.wfa_adaptive = p->wfa_adaptive; return P; }
 
 static void rows_of(uint32_t q, const std::vector<GenomeRes>& res, Rows& R) {  // printResult search.go:437-533
   for (const GenomeRes& r : res) { int cls = 1, j = 1;
@@ -176,7 +176,7 @@ static void rows_of(uint32_t q, const std::vector<GenomeRes>& res, Rows& R) {  /
 
 extern "C" {
 void lmo_default_params(lmo_params* p) { Params d; p->min_prefix = d.min_prefix; p->min_single_prefix = d.min_single_prefix; p->top_n_genomes = 0; p->top_n_chains = 0; p->max_gap = d.max_gap; p->max_distance = d.max_distance; p->ext_len = d.ext_len; p->ext_len2 = d.ext_len2;
-  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; }
+  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; p->wfa_adaptive = 1; p->reserved = 0; }
 static thread_local std::string g_err;
 const char* lmo_last_error() { return g_err.c_str(); }
 void* lmo_open(const char* dir) { try { Handle* h = new Handle; h->ix.open(dir); return h; } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
@@ -223,8 +223,8 @@ static void* stage(void* hh, const lmo_params* p, const uint8_t* seqs, const uin
 void* lmo_anchor_batch(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* n_out) { try { return stage(hh, p, seqs, off, n, 0, n_out); } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
 void* lmo_chain_batch(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* n_out) { try { return stage(hh, p, seqs, off, n, 1, n_out); } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
 // WFA on pairs: off[2n+1]; returns '\n'-joined CIGARs in wfa convention (not swapped), untrimmed
-char* lmo_wfa_batch(const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* out_len) {
-  std::string o; for (int i = 0; i < n; i++) { WfaResult w = wfa_align((const char*)seqs + off[2 * i], (int)(off[2 * i + 1] - off[2 * i]), (const char*)seqs + off[2 * i + 1], (int)(off[2 * i + 2] - off[2 * i + 1]));
+char* lmo_wfa_batch(const uint8_t* seqs, const uint64_t* off, int32_t n, int32_t adaptive, uint64_t* out_len) {
+  std::string o; for (int i = 0; i < n; i++) { WfaResult w = wfa_align((const char*)seqs + off[2 * i], (int)(off[2 * i + 1] - off[2 * i]), (const char*)seqs + off[2 * i + 1], (int)(off[2 * i + 2] - off[2 * i + 1]), adaptive);
     for (uint64_t op : w.ops) { o += std::to_string((uint32_t)(op & 0xffffffffu)); o.push_back((char)(op >> 32)); } o.push_back('\n'); }
   char* c = (char*)malloc(o.size() + 1); memcpy(c, o.data(), o.size() + 1); *out_len = o.size(); return c;
 }

@@ -70,6 +70,7 @@ struct Params {
   int align_max_gap = 20, align_min_len = 50, align_band = 100;
   double min_pident = 70, min_qcov_hsp = 0;
   int output_seq = 0;
+  int wfa_adaptive = 1;
 };
 
 struct Sub { int32_t q, t; uint8_t len; bool trc, qrc; };  // SubstrPair lib-index-search.go:805-817
@@ -406,7 +407,11 @@ static inline Extended extend_match(const std::string& seq1, const std::string& 
 struct WfaResult { std::vector<uint64_t> ops; int qbegin = 0, qend = 0, tbegin = 0, tend = 0; int align_len = 0, matches = 0, gaps = 0; int score = 0; };
 static const int32_t WF_NULL = INT32_MIN / 2;
 struct WF { int lo = 0, hi = -1; std::vector<int32_t> off; bool null = true; int32_t get(int k) const { return (null || k < lo || k > hi) ? WF_NULL : off[k - lo]; } };
-static inline WfaResult wfa_align(const char* q, int plen, const char* t, int tlen, int X = 4, int O = 6, int E = 2) {
+// adaptive != 0: WFA-adaptive wavefront reduction as in WFA2-lib (wavefront_heuristic_wfadaptive): after extending the M wavefront of a
+// score, if it spans >= min_wf_len diagonals, drop diagonals from both ends whose distance to the end max(plen-v, tlen-h) exceeds the
+// best one by more than max_dist_diff; the target diagonal is preserved. The reference enables wfa.DefaultAdaptiveOption
+// (lib-index-search.go:1911; MinWFLen 10, MaxDistDiff 50 per the commented alternative at :1912-1915).
+static inline WfaResult wfa_align(const char* q, int plen, const char* t, int tlen, int adaptive = 1, int min_wf_len = 10, int max_dist_diff = 50, int X = 4, int O = 6, int E = 2) {
   WfaResult R; std::vector<WF> Mw, Iw, Dw; const int kend = tlen - plen;
   auto extend = [&](int k, int32_t h) { int v = h - k; while (v < plen && h < tlen && q[v] == t[h]) { v++; h++; } return h; };
   auto at = [&](std::vector<WF>& W, int s) -> const WF* { static const WF nullwf; return (s < 0 || s >= (int)W.size()) ? &nullwf : &W[s]; };
@@ -430,6 +435,13 @@ static inline WfaResult wfa_align(const char* q, int plen, const char* t, int tl
       if (mm > WF_NULL) { mm = extend(k, mm); anyM = true; } M.off[k - lo] = mm; anyI |= ins > WF_NULL; anyD |= del > WF_NULL;
     }
     M.null = !anyM; I.null = !anyI; D.null = !anyD;
+    if (adaptive && !M.null && hi - lo + 1 >= min_wf_len) {
+      int mind = INT32_MAX; std::vector<int> dist(w); for (int k = lo; k <= hi; k++) { int32_t o = M.off[k - lo]; int d = (o > WF_NULL) ? std::max(plen - (o - k), tlen - o) : INT32_MAX; dist[k - lo] = d; mind = std::min(mind, d); }
+      int nlo = lo, nhi = hi; int top_limit = std::min(kend, hi); for (int k = lo; k < top_limit; k++) { if (dist[k - lo] != INT32_MAX && dist[k - lo] - mind <= max_dist_diff) break; nlo++; }
+      int bottom_limit = std::max(kend, nlo); for (int k = hi; k > bottom_limit; k--) { if (dist[k - lo] != INT32_MAX && dist[k - lo] - mind <= max_dist_diff) break; nhi--; }
+      if (nlo != lo || nhi != hi) { int nw = nhi - nlo + 1; for (WF* W : {&M, &I, &D}) { std::vector<int32_t> o2(W->off.begin() + (nlo - lo), W->off.begin() + (nlo - lo) + nw); W->off.swap(o2); W->lo = nlo; W->hi = nhi; }
+        bool aM = false, aI = false, aD = false; for (int i = 0; i < nw; i++) { aM |= M.off[i] > WF_NULL; aI |= I.off[i] > WF_NULL; aD |= D.off[i] > WF_NULL; } M.null = !aM; I.null = !aI; D.null = !aD; }
+    }
   }
   R.score = s;
   // backtrace (WFA2 wavefront_backtrace_affine)

@@ -17,7 +17,7 @@ class Params(C.Structure):
                 ("max_gap", C.c_float), ("max_distance", C.c_float), ("ext_len", C.c_int32), ("ext_len2", C.c_int32),
                 ("min_qcov_genome", C.c_double), ("max_evalue", C.c_double),
                 ("align_max_gap", C.c_int32), ("align_min_len", C.c_int32), ("align_band", C.c_int32), ("output_seq", C.c_int32),
-                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double)]
+                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double), ("wfa_adaptive", C.c_int32), ("reserved", C.c_int32)]
 
 
 HSP_DTYPE = np.dtype([("query", "<u4"), ("hits", "<u4"), ("genome", "<u8"), ("seq_idx", "<u4"), ("n_seqs", "<u4"), ("chunk_idx", "<u4"), ("n_chunks", "<u4"),
@@ -83,7 +83,7 @@ class Oracle:
             f.restype = C.c_void_p
             f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         L.lmo_wfa_batch.restype = C.c_void_p
-        L.lmo_wfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+        L.lmo_wfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
         L.lmo_kv_search.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.lmo_open_kv.restype = C.c_void_p
         L.lmo_open_kv.argtypes = [C.c_char_p]
@@ -158,13 +158,13 @@ class Oracle:
     def chains(self, seqs, params=None):
         return self._stage(self.lib.lmo_chain_batch, CHAIN_DTYPE, seqs, params)
 
-    def wfa(self, pairs):
+    def wfa(self, pairs, adaptive=1):
         flat = []
         for q, t in pairs:
             flat += [q, t]
         buf, off = pack_queries(flat)
         n = C.c_uint64()
-        ptr = self.lib.lmo_wfa_batch(buf.ctypes.data, off.ctypes.data, len(pairs), C.byref(n))
+        ptr = self.lib.lmo_wfa_batch(buf.ctypes.data, off.ctypes.data, len(pairs), adaptive, C.byref(n))
         s = C.string_at(ptr, n.value).decode()
         self.lib.lmo_free(ptr)
         return s.split("\n")[:-1]

@@ -100,4 +100,12 @@ def test_wfa_batch_matches_oracle(oracle_small):
                 t.append(c)
             pairs.append((q, "".join(t) or "A"))
     pairs += [("ACGT", "TTTT"), ("A", "ACGTACGT"), ("ACGTACGTAA", "A"), ("AAAAAAAAAA", "AAAAA"), ("ACGTTTGACA" * 30, "ACGTTGACA" * 30)]
-    assert wfa_batch(pairs) == oracle_small.wfa(pairs)
+    for adaptive in (1, 0):   # WFA-adaptive reduction (reference default) and the exact algorithm
+        assert wfa_batch(pairs, adaptive=adaptive) == oracle_small.wfa(pairs, adaptive), "adaptive=%d" % adaptive
+
+
+def test_search_exact_wfa_matches_oracle(gpu_small, oracle_small, small_queries):
+    ids, seqs = small_queries
+    gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1, wfa_adaptive=0))
+    orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1, wfa_adaptive=0))
+    _rows_equal(gr, orr, gs, os_, gc, oc)
