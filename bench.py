@@ -82,10 +82,13 @@ class ClockSampler(threading.Thread):
 
 
 def probe_algorithmic_bytes(cnt, masks, nq):
-    """sector-granular algorithmic bytes of one k_probe_find launch from the probe statistics."""
-    issued, with_anchor, steps, entries, hits = (int(cnt[i]) for i in range(5))
-    slots = nq * masks
-    return slots * 24 + issued * 8 + with_anchor * 16 + steps * 32 + entries * 32 + hits * 48
+    """SURVEY.md §8(d) / DESIGN.md §4, sector-granular because the access is random. Per issued probe: 12 B (query k-mer + mask id)
+    + 32 B (anchor-table sector); per probe whose anchor exists: 32 B per search step actually taken (gallop + binary search) + 16 B per
+    entry scanned in the range (key + first value); 48 B per hit record written; 16 B per anchor written. Unissued slots (no captured
+    k-mer / not the first owner of a reversed k-mer) cost their 8-byte k-mer read."""
+    issued, with_anchor, steps, entries, hits, anchors = (int(cnt[i]) for i in range(6))
+    slots = 2 * nq * masks
+    return (slots - issued) * 8 + issued * 44 + steps * 32 + entries * 16 + hits * 48 + anchors * 16
 
 
 def cpu_port_throughput(idx_dir, seqs, threads, target_s=12.0):

@@ -77,12 +77,13 @@ __device__ __forceinline__ void mbar_wait(u64* mbar, u32 phase) {
 // Also: low-complexity filter (:1222-1238), base-reversed k-mer and its suffix mask argmin_j(mask_j XOR rev) (:1322-1341),
 // and first-owner dedup of equal captured k-mers (:1288-1298).
 struct Capture { u64 kmer; u32 lo, n; u32 smask; };  // kmer==0 -> nothing captured; [lo,lo+n) = rows of the query's table; smask = suffix mask
+struct CapSoA { u64* kmer; u32 *lo, *n, *smask; };   // structure-of-arrays storage: the probe kernel reads 8 B (prefix probe) or 16 B (suffix probe) per slot
 __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, const u64* __restrict__ koff, const u64* __restrict__ masks, int m, int k, int slices,
-                                                 Capture* __restrict__ cap, u32* __restrict__ owner, u32 smem_cap_entries, int use_tma) {
-  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; __shared__ __align__(8) u64 mbar;
+                                                 CapSoA cap, u32* __restrict__ owner, u32 smem_cap_entries, int use_tma, const u32* __restrict__ mask_pstart, int mask_pbits) {
+  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024];
   int q = blockIdx.x / slices, sl = blockIdx.x % slices; u64 o = koff[q]; u32 n = (u32)(koff[q + 1] - o);
   int per = (m + slices - 1) / slices, i0 = sl * per, i1 = min(m, i0 + per);
-  if (n == 0) { for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) { Capture c; c.kmer = 0; c.lo = c.n = 0; c.smask = 0; cap[(u64)q * m + i] = c; } return; }
+  if (n == 0) { for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) { u64 w = (u64)q * m + i; cap.kmer[w] = 0; cap.lo[w] = 0; cap.n[w] = 0; cap.smask[w] = 0; } return; }
   const u64* tab = qkeys + o; bool in_smem = n <= smem_cap_entries;
   if (in_smem) {
     if (use_tma) {
@@ -93,12 +94,18 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
     } else { for (u32 t = threadIdx.x; t < n; t += blockDim.x) stab[t] = tab[t]; __syncthreads(); }
     tab = stab;
   }
+  // prefix directory over the sorted table: the descent for a mask starts inside the bucket of k-mers sharing its leading pb bits
+  // (the XOR-argmin always shares the longest available prefix), which skips the widest binary searches
+  int pb = 31 - __clz(max(n, 16u)) - 3; pb = max(4, min(pb, 10)); const int psh = 2 * k - pb; const u32 NP = 1u << pb;
+  for (u32 t = threadIdx.x; t < NP; t += blockDim.x) { pst[t] = 0xFFFFFFFFu; pen[t] = 0; } __syncthreads();
+  for (u32 t = threadIdx.x; t < n; t += blockDim.x) { u32 p = (u32)(tab[t] >> psh); if (t == 0 || (u32)(tab[t - 1] >> psh) != p) pst[p] = t; if (t + 1 == n || (u32)(tab[t + 1] >> psh) != p) pen[p] = t + 1; } __syncthreads();
+  const int msh = 2 * k - mask_pbits;
   for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    u64 mk = masks[i]; u32 lo = 0, hi = n; xor_argmin_range(tab, lo, hi, mk);
+    u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
     u64 km = tab[lo]; Capture c; c.kmer = km; c.lo = lo; c.n = hi - lo; c.smask = 0;
     if (kmer_low_complexity(km, k)) c.kmer = 0;   // km==0 is DUST-low-complexity too, as in the reference
-    else { u64 rv = kmer_reverse62(km, k); u32 a = 0, b = (u32)m; xor_argmin_range(masks, a, b, rv); c.smask = a; atomicMin(&owner[o + lo], (u32)i); }
-    cap[(u64)q * m + i] = c;
+    else { u64 rv = kmer_reverse62(km, k); u32 mp = (u32)(rv >> msh); u32 a = mask_pstart[mp], b = mask_pstart[mp + 1]; if (a == b) { a = 0; b = (u32)m; } xor_argmin_range(masks, a, b, rv); c.smask = a; atomicMin(&owner[o + lo], (u32)i); }
+    u64 w = (u64)q * m + i; cap.kmer[w] = c.kmer; cap.lo[w] = c.lo; cap.n[w] = c.n; cap.smask[w] = c.smask;
   }
 }
 
@@ -106,21 +113,22 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 // K2: seed probe (kv.Searcher.Search / Search2, kv/kv-searcher.go:190-1088) + anchors (lib-index-search.go:1357-1569)
 // =====================================================================================================
 struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 pad; };  // mask_dir = mask<<1 | dir ; [lo,lo+n) = query table rows (locs)
-struct ProbeParams { const u64 *bucket_off, *keys, *val_off, *vals; const u32* anchor_start; int m, k, NA, mask_prefix, anchor_prefix, p; };
+struct ProbeParams { const u64 *bucket_off, *keys, *val_off, *vals; const u32 *anchor_start, *anchor_bits; int m, k, NA, mask_prefix, anchor_prefix, p; };
 
 // one thread per (query, mask, direction). dir 0: captured k-mer against its own mask bucket, values must have reverse flag 0;
 // dir 1: base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
 // semantics, kv-searcher.go:466-488). Range = keys in [kmer & ~low, kmer | low] at/after the anchor start (:282-304, :349-355).
-__global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, const Capture* __restrict__ cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nprobe,
+__global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, CapSoA cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nprobe,
                                                     ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u64* __restrict__ stats) {
   u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0;
   if (t < nprobe) {
-    u64 qi = t >> 1; int dir = (int)(t & 1); u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); Capture c = cap[qi];
-    if (c.kmer != 0 && !(dir == 1 && owner[koff[q] + c.lo] != (u32)i)) {
+    u64 qi = t >> 1; int dir = (int)(t & 1); u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); Capture c; c.kmer = cap.kmer[qi]; c.lo = 0; c.n = 0; c.smask = 0; bool go = c.kmer != 0;
+    if (go && dir == 1) { c.lo = cap.lo[qi]; c.smask = cap.smask[qi]; go = owner[koff[q] + c.lo] == (u32)i; }
+    if (go) {
       u64 kmer = dir ? kmer_reverse62(c.kmer, P.k) : c.kmer; int bucket = dir ? (int)c.smask : i;
       int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low;
       u32 a = (u32)((left >> ((P.k - P.mask_prefix - P.anchor_prefix) << 1)) & (u64)(P.NA - 1));
-      u32 as = P.anchor_start[(u64)bucket * P.NA + a];
+      u64 aslot = (u64)bucket * P.NA + a; u32 as = ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) ? P.anchor_start[aslot] : 0xFFFFFFFFu;
       if (as != 0xFFFFFFFFu) {
         u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; u64 lo = b0 + as, hi = b1;
         // galloping lower_bound(left) from the anchor start
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, const Capture
         while (l < r) { u64 mid = (l + r) >> 1; if (P.keys[mid] < left) l = mid + 1; else r = mid; steps++; }
         u64 e0 = l; u32 ne = 0, na = 0; const int want = dir;
         while (e0 + ne < hi && P.keys[e0 + ne] <= right) { u64 v0 = P.val_off[e0 + ne], v1 = P.val_off[e0 + ne + 1]; if (v1 > v0 && (int)(P.vals[v0] & 1) == want) na += (u32)(v1 - v0); ne++; }
-        if (na) { have = true; h.q = q; h.mask_dir = (u32)(i << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = c.lo; h.n = c.n; h.kmer = kmer; h.nanch = na * c.n; h.pad = 0; }
+        if (na) { if (dir == 0) c.lo = cap.lo[qi]; c.n = cap.n[qi]; have = true; h.q = q; h.mask_dir = (u32)(i << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = c.lo; h.n = c.n; h.kmer = kmer; h.nanch = na * c.n; h.pad = 0; }
         if (stats) { atomicAdd((unsigned long long*)&stats[1], 1ull); atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); }
       }
       if (stats) atomicAdd((unsigned long long*)&stats[0], 1ull);
@@ -202,20 +210,21 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 }
 
 // K1b: capture
-static void sketch_capture(lmg_index* ix, QBatch& B, DBuf<Capture>& cap, DBuf<u32>& owner) {
-  cudaStream_t st = ix->st; const Image& I = ix->img; cap.alloc((u64)B.nq * I.m, st); owner.alloc(B.total_k + 2, st); owner.fill_ff();
+struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
+static void sketch_capture(lmg_index* ix, QBatch& B, CapBufs& cap, DBuf<u32>& owner) {
+  cudaStream_t st = ix->st; const Image& I = ix->img; u64 nslot = (u64)B.nq * I.m; cap.kmer.alloc(nslot, st); cap.lo.alloc(nslot, st); cap.n.alloc(nslot, st); cap.smask.alloc(nslot, st); owner.alloc(B.total_k + 2, st); owner.fill_ff();
   u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
   u32 smem_cap = (u32)std::min<u64>((ix->smem_optin - 1024) / 8, 24576);  // entries
   u32 need = (u32)std::min<u64>(maxn, smem_cap); size_t smem = ((size_t)need * 8 + 15) & ~15ull;
   CUDA_CHECK(cudaFuncSetAttribute(k_capture, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 16)));
   // slices: enough CTAs to fill 148 SMs a few times over, but keep >= 1024 masks per CTA so the staged table is reused
   int slices = std::max(1, std::min(I.m / 1024, cdiv(ix->sm_count * 8, std::max(1, B.nq))));
-  k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap.p, owner.p, need, ix->use_tma); KERNEL_CHECK();
+  k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap.soa(), owner.p, need, ix->use_tma, I.d_mask_pstart, I.mask_pbits); KERNEL_CHECK();
 }
 
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
-static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.keys = I.d_keys; P.val_off = I.d_val_off; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
+static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.keys = I.d_keys; P.val_off = I.d_val_off; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
@@ -225,7 +234,7 @@ template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>&
 static int bits_for(u64 v) { int b = 1; while ((v >> b) && b < 64) b++; return b; }
 
 // K2: probes -> anchors sorted by (query, genome, QBegin, QEnd desc, TBegin, qrc, trc)
-static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, DBuf<Capture>& cap, DBuf<u32>& owner, Anchors& A, bool stats) {
+static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, CapBufs& cap, DBuf<u32>& owner, Anchors& A, bool stats) {
   cudaStream_t st = ix->st; const Image& I = ix->img; if (prm->min_prefix < I.mask_prefix + I.anchor_prefix || prm->min_prefix > I.k) throw std::runtime_error("the minimum prefix length should be in the range of [maskPrefix+anchorPrefix, k]");  // kv-searcher.go:202
   ProbeParams P = probe_params(I, prm->min_prefix); u64 nprobe = (u64)B.nq * I.m * 2;
   DBuf<u32> nh(1, st); nh.zero(); DBuf<u64> dstats(8, st); dstats.zero();
@@ -235,7 +244,7 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, DBuf<Cap
   u64 tryCap = std::min<u64>(capHits, std::max<u64>(1u << 20, nprobe / 4));
   for (;;) { hits.alloc(tryCap, st); nh.zero(); if (stats) dstats.zero();
     if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); } cudaEventRecord(ix->kev[0], st);
-    k_probe_find<<<cdiv((i64)nprobe, 256), 256, 0, st>>>(P, cap.p, owner.p, B.koff.p, nprobe, hits.p, nh.p, stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
+    k_probe_find<<<cdiv((i64)nprobe, 256), 256, 0, st>>>(P, cap.soa(), owner.p, B.koff.p, nprobe, hits.p, nh.p, stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
     u32 h = nh.to_host()[0]; { float f = 0; cudaEventElapsedTime(&f, ix->kev[0], ix->kev[1]); ix->ms[8] = f; ix->counters[8] = nprobe; } if (h <= tryCap) { tryCap = h; break; } tryCap = capHits; }
   u32 nhit = (u32)tryCap; if (stats) { auto s = dstats.to_host(); for (int i = 0; i < 4; i++) ix->counters[i] = s[i]; ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
@@ -338,6 +347,13 @@ __global__ void k_backtrack(const u64* __restrict__ seg_off, const u32* __restri
   seg_score[seg] = maxScore;
 }
 
+// counting sort by a dense integer key, then tiny per-bucket sorts (host lists of chain / HSP records are grouped by segment / window)
+template <class T, class KeyFn, class Less> static void bucket_sort(std::vector<T>& v, u32 nkeys, KeyFn key, Less less) {
+  if (v.size() < 2) return; std::vector<u32> off(nkeys + 1, 0); for (const T& x : v) off[key(x) + 1]++; for (u32 i = 0; i < nkeys; i++) off[i + 1] += off[i];
+  std::vector<T> out(v.size()); std::vector<u32> cur(off.begin(), off.end() - 1); for (const T& x : v) out[cur[key(x)]++] = x;
+  for (u32 i = 0; i < nkeys; i++) if (off[i + 1] - off[i] > 1) std::sort(out.begin() + off[i], out.begin() + off[i + 1], less); v.swap(out);
+}
+
 struct Segments { u32 nseg = 0; DBuf<u64> key, off; DBuf<u32> cn; DBuf<u64> c_lo; DBuf<float> score; std::vector<u64> h_key, h_off; };
 struct Chains { u32 n = 0; DBuf<ChainRec> rec; std::vector<ChainRec> h; std::vector<float> seg_score; };
 
@@ -370,7 +386,7 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   if (prm->top_n_genomes > 0) { u32 s0 = 0; while (s0 < nseg) { u32 q = (u32)(S.h_key[s0] >> 36), s1 = s0; std::vector<u32> v; while (s1 < nseg && (u32)(S.h_key[s1] >> 36) == q) { if (keep[s1]) v.push_back(s1); s1++; }
       if ((int)v.size() > prm->top_n_genomes) { std::stable_sort(v.begin(), v.end(), [&](u32 a, u32 b) { return Cn.seg_score[a] > Cn.seg_score[b]; }); for (size_t t = prm->top_n_genomes; t < v.size(); t++) keep[v[t]] = 0; } s0 = s1; } }
   std::vector<ChainRec> kept; kept.reserve(nc); for (auto& r : Cn.h) if (keep[r.seg]) { r.score = Cn.seg_score[r.seg]; kept.push_back(r); }
-  std::sort(kept.begin(), kept.end(), [](const ChainRec& a, const ChainRec& b) { if (a.seg != b.seg) return a.seg < b.seg; if (a.t0 != b.t0) return a.t0 < b.t0; return a.ord < b.ord; });
+  bucket_sort(kept, nseg, [](const ChainRec& a) { return a.seg; }, [](const ChainRec& a, const ChainRec& b) { if (a.t0 != b.t0) return a.t0 < b.t0; return a.ord < b.ord; });
   Cn.h.swap(kept); Cn.n = (u32)Cn.h.size();
 }
 
@@ -494,6 +510,36 @@ __global__ void __launch_bounds__(128) k_pa_anchors2(const WinItem* __restrict__
     __syncthreads();
   }
   if (threadIdx.x == 0) counts[it] = s_base;
+}
+
+// ---- K4 v3: one CTA per QUERY. The query's sorted (k-mer, loc) table is staged in shared memory once and reused by all of the query's
+// target windows (typically one per candidate genome), so every table probe is a shared-memory binary search instead of an L2 round trip.
+// Windows are packed into shared memory one at a time. Queries whose table does not fit use k_pa_anchors2 (table in L2).
+__global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
+                                                     const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn) {
+  __shared__ u32 s_base; extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
+  const u32 q = qlist[blockIdx.x]; const u32 t0q = toff[q], tn = toff[q + 1] - t0q; const int K = 31;
+  for (u32 i = threadIdx.x; i < tn; i += 256) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
+  const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull;
+  for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
+    WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
+    __syncthreads();   // previous window fully consumed (and, first time, table loaded)
+    i32 nw = (w.W + 15) / 16 + 2;
+    for (i32 x = threadIdx.x; x < nw; x += 256) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
+    if (threadIdx.x == 0) s_base = 0; __syncthreads();
+    i32 np = w.W - K + 1;
+    for (i32 idx = threadIdx.x; idx < np; idx += 256) {
+      u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2, kr = kmer_reverse62(~km & ttt, K);
+      if (km == 0 || km == ccc || km == ggg || km == ttt || !tn) continue;
+      u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0, c = 0; bool f1 = tree_search(sk, tn, km, w.mp, &l1, &h1), f2 = tree_search(sk, tn, kr, w.mp, &l2, &h2);
+      if (f1) for (u32 u = l1; u < h1; u++) { u32 vv = sv[u]; int lp = lcp31(km, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
+      if (f2) for (u32 u = l2; u < h2; u++) { u32 vv = sv[u]; int lp = lcp31(kr, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
+      if (!c) continue; u32 wpos = atomicAdd(&s_base, c); if ((u64)wpos + c > (u64)cap) continue; u64* out = a_lo + base0 + wpos;
+      if (f1) for (u32 u = l1; u < h1; u++) { u32 vv = sv[u]; int lp = lcp31(km, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx, 0, 0); }
+      if (f2) for (u32 u = l2; u < h2; u++) { u32 vv = sv[u]; int lp = lcp31(kr, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx + K - lp, 1, 1); }
+    }
+    __syncthreads(); if (threadIdx.x == 0) counts[it] = s_base;
+  }
 }
 
 struct C2Rec { u32 item, ord; i32 qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors; };
@@ -898,12 +944,12 @@ static void build_tree_tables(lmg_index* ix, QBatch& B, DBuf<u64>& tkeys, DBuf<u
 struct HostHsp { i32 qb, qe, tb, te, aligned_q, tpo, max_ext; int job = -1; bool dead = false; i32 alen = 0, matched = 0, gaps = 0, score = 0, bitscore = 0; double evalue = 0, af = 0, pident = 0; std::string cigar; };
 struct HostCluster { u32 seg; u32 item; bool rc, variantA; int nseeds, iseq; std::vector<HostHsp> hsps; double sim = 0; bool has = false; };
 
-struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<std::string> seqids; };
+struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u32> row_genome; const Image* img = nullptr; };   // sseqid of row i = img->seq_ids[row_genome[i]][rows[i].seq_idx]
 
 static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
   QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
-  sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); T.mark();   // [1] sketch
+  sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); T.mark();   // [1] sketch
   Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); T.mark();              // [2] probe
   Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); T.mark();                // [3] chain
   for (int i = 0; i < 16; i++) if (i != 8 && i != 9) ix->ms[i] = 0; ix->counters[11] = 0;
@@ -923,17 +969,28 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff);
   // ---- K4 anchors: per-query prefix hash, one pass into capacity-bounded regions (exact rerun for the rare overflow), per-window sort
   std::vector<u32> htoff = toff.to_host(B.nq + 1); std::vector<u64> hhoff(B.nq + 1, 0); for (int q = 0; q < B.nq; q++) { u32 n = htoff[q + 1] - htoff[q]; u64 H = 0; if (n) { H = 16; while (H < 2ull * n) H <<= 1; } hhoff[q + 1] = hhoff[q] + H; }
+  // queries -> item ranges (items are ordered by (query, genome)); per-query kernel when table + window fit in shared memory
+  std::vector<u32> qbeg(B.nq, 0), qend(B.nq, 0), qlist, rest; { u32 i = 0; while (i < nit) { u32 q = items[i].q, j = i; while (j < nit && items[j].q == q) j++; qbeg[q] = i; qend[q] = j; i = j; } }
+  u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 2048, 200 * 1024);
+  for (int q = 0; q < B.nq; q++) if (qend[q] > qbeg[q]) { u32 tn = htoff[q + 1] - htoff[q]; i32 mw = 0; for (u32 i = qbeg[q]; i < qend[q]; i++) mw = std::max(mw, items[i].W); size_t need = (size_t)tn * 12 + ((size_t)(mw + 15) / 16 + 2) * 4 + 64;
+      if (need <= smem_cap3) { qlist.push_back(q); max_tn = std::max(max_tn, tn); maxW3 = std::max(maxW3, mw); } else for (u32 i = qbeg[q]; i < qend[q]; i++) rest.push_back(i); }
+  if (rest.empty()) std::fill(hhoff.begin(), hhoff.end(), 0);   // the L2-resident hash index is only needed by the fallback kernel
   DBuf<u64> hoff(B.nq + 1, st); hoff.from_host(hhoff.data(), B.nq + 1); DBuf<u64> htab(hhoff[B.nq] + 2, st); htab.fill_ff();
-  { u32 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, htoff[q + 1] - htoff[q]); if (maxn) { dim3 g((unsigned)std::max(1, std::min(32, cdiv(maxn, 256))), B.nq); k_tree_hash_build<<<g, 256, 0, st>>>(tkeys.p, toff.p, hoff.p, B.nq, htab.p); KERNEL_CHECK(); } }
+  if (!rest.empty()) { u32 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, htoff[q + 1] - htoff[q]); if (maxn) { dim3 g((unsigned)std::max(1, std::min(32, cdiv(maxn, 256))), B.nq); k_tree_hash_build<<<g, 256, 0, st>>>(tkeys.p, toff.p, hoff.p, B.nq, htab.p); KERNEL_CHECK(); } }
   std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>(2ll * std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
   size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
   CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smemW, 1024)));
   DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
+  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
+  DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
+  if (!qlist.empty()) CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than 2*W+256: capacities become the exact counts
     for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
     if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
-    { KTimer kt(st, &ix->ms[14]); k_pa_anchors2<<<nit, 128, smemW, st>>>(d_items.p, nullptr, nit, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); }
+    { KTimer kt(st, &ix->ms[14]);
+      if (!qlist.empty()) { k_pa_anchors3<<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); }
+      if (!rest.empty()) { k_pa_anchors2<<<(u32)rest.size(), 128, smemW, st>>>(d_items.p, d_rest.p, (u32)rest.size(), I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); } }
     hcnt = cnt.to_host(nit); bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
     if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
   std::vector<C2Rec> c2;
@@ -944,16 +1001,23 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     DBuf<i32> sc(habeg[nit], st); DBuf<u32> pred(habeg[nit], st); DBuf<u64> stack(habeg[nit], st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
     { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
     u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
-    std::sort(c2.begin(), c2.end(), [](const C2Rec& a, const C2Rec& b) { if (a.item != b.item) return a.item < b.item; if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
+    bucket_sort(c2, nit, [](const C2Rec& a) { return a.item; }, [](const C2Rec& a, const C2Rec& b) { if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
   tkeys.free(); tvals.free(); T.mark();                                                                  // [4] pseudo-align
   if (c2.empty()) { T.mark(); finish_times(5); return; }
+  auto hw0 = std::chrono::steady_clock::now(); static const bool dbgt = getenv("LMG_DEBUG_TIMING") != nullptr; auto lap = [&](const char* what) { if (dbgt) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host] %-18s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - hw0).count()); hw0 = n; } };
   // ---- contig mapping, clusters, jobs (lib-index-search.go:2083-2469) — host, sequential per (query, genome)
-  std::vector<HostCluster> clusters; std::vector<HspJob> jobs; size_t ci = 0; const int contigInterval = I.contig_interval;
-  { u32 c = 0; while (c < nit) { u32 seg = Cn.h[c].seg; u32 cEnd = c; while (cEnd < nit && Cn.h[cEnd].seg == seg) cEnd++;
-      std::set<std::array<int, 6>> keys; int iSeq = 0, iSeqPre = -1;
+  std::vector<HostCluster> clusters; std::vector<HspJob> jobs; const int contigInterval = I.contig_interval;
+  { // segments (query, genome) are independent: process them in parallel, concatenate in order
+    std::vector<std::pair<u32, u32>> segs; { u32 c = 0; while (c < nit) { u32 seg = Cn.h[c].seg, e = c; while (e < nit && Cn.h[e].seg == seg) e++; segs.push_back({c, e}); c = e; } }
+    std::vector<size_t> c2beg(nit + 1, c2.size()); { size_t x = c2.size(); for (i64 it = (i64)nit - 1; it >= 0; it--) { while (x > 0 && c2[x - 1].item >= (u32)it) x--; c2beg[it] = x; } }
+    const int NT = std::max(1, std::min(16, omp_get_max_threads())); std::vector<std::vector<HostCluster>> segCl(NT); std::vector<std::vector<HspJob>> segJobs(NT);
+#pragma omp parallel for schedule(static, 1) num_threads(NT)
+    for (int ti = 0; ti < NT; ti++) { std::vector<HostCluster>& clusters_l = segCl[ti]; std::vector<HspJob>& jobs_l = segJobs[ti]; size_t s0 = segs.size() * ti / NT, s1 = segs.size() * (ti + 1) / NT; std::vector<std::array<int, 6>> keys;
+     for (size_t si = s0; si < s1; si++) { u32 c = segs[si].first, cEnd = segs[si].second, seg = Cn.h[c].seg;
+      keys.clear(); int iSeq = 0, iSeqPre = -1;
       for (u32 it = c; it < cEnd; it++) { const WinItem& w = items[it]; const auto& SS = I.seq_sizes[w.g]; const int numSeqs = (int)SS.size(); const bool rc = w.rc; const i32 tBegin = w.tBegin, tEnd = w.tEnd, tlenSeq = w.W;
-        size_t c0 = ci; while (ci < c2.size() && c2[ci].item == it) ci++; if (ci == c0) continue;
+        size_t c0 = c2beg[it], ci = c2beg[it + 1]; if (ci == c0) continue;
         iSeqPre = -1; HostCluster cur; cur.seg = seg; cur.item = it; cur.rc = rc; cur.nseeds = Cn.h[it].nseeds; cur.variantA = false; cur.iseq = 0;
         auto convert = [&](HostHsp& h, const C2Rec& r, int tpo, int iS) { h.qb = r.qb; h.qe = r.qe; h.aligned_q = r.aligned_q; h.tpo = tpo;
           if (rc) { h.tb = tBegin - tpo + (tlenSeq - r.te - 1); if (h.tb < 0) { h.qe += h.tb; h.aligned_q += h.tb; h.tb = 0; } h.te = tBegin - tpo + (tlenSeq - r.tb - 1); if (h.te > (i32)SS[iS] - 1) { h.qb += h.te - ((i32)SS[iS] - 1); h.te = (i32)SS[iS] - 1; } }
@@ -963,18 +1027,20 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
           for (HostHsp& h : cur.hsps) { if (h.qb >= h.qe + 1) { h.dead = true; continue; } i32 start, end; if (rc) { start = tEnd - h.te - h.tpo; end = tEnd - h.tb - h.tpo + 1; } else { start = h.tpo + h.tb - tBegin; end = h.tpo + h.te - tBegin + 1; }
             if (start >= end) { h.dead = true; continue; } if (start < 0 || end > tlenSeq || h.qb < 0 || h.qe + 1 > qlen) { h.dead = true; continue; }
             int ext2 = prm->ext_len2; if (h.aligned_q > 1000000) ext2 += 80; else if (h.aligned_q > 250000) ext2 += 40; else if (h.aligned_q > 50000) ext2 += 20; else if (h.aligned_q > 10000) ext2 += 10;
-            HspJob J; J.q = w.q; J.g = w.g; J.tBegin = tBegin; J.tEnd = tEnd; J.rc = rc; J.qlen = qlen; J.tlen = tlenSeq; J.start1 = h.qb; J.end1 = h.qe + 1; J.start2 = start; J.end2 = end; J.ext = ext2; J.tb_arg = h.tb; J.max_ext = h.max_ext; h.job = (int)jobs.size(); jobs.push_back(J); }
-          clusters.push_back(cur); cur.hsps.clear(); };
+            HspJob J; J.q = w.q; J.g = w.g; J.tBegin = tBegin; J.tEnd = tEnd; J.rc = rc; J.qlen = qlen; J.tlen = tlenSeq; J.start1 = h.qb; J.end1 = h.qe + 1; J.start2 = start; J.end2 = end; J.ext = ext2; J.tb_arg = h.tb; J.max_ext = h.max_ext; h.job = (int)jobs_l.size(); jobs_l.push_back(J); }
+          clusters_l.push_back(cur); cur.hsps.clear(); };
         for (size_t x = c0; x < ci; x++) { const C2Rec& r = c2[x]; iSeq = 0; int tpoB = 0, tpoE = 0;
           if (numSeqs > 1) { iSeq = -1; int _b, _e; if (rc) { _b = tEnd - r.te + K; _e = tEnd - r.tb - K; } else { _b = tBegin + r.tb + K; _e = tBegin + r.te - K; }
             if (_b >= _e) { if (rc) { _b = tEnd - r.te; _e = tEnd - r.tb; } else { _b = tBegin + r.tb; _e = tBegin + r.te; } }
             for (int j = 0; j < numSeqs; j++) { int l = (int)SS[j]; tpoE += l - 1; if (_b + K >= tpoB && _e - K <= tpoE) { iSeq = j; break; } else if (_e < tpoB) { iSeq = -1; break; } tpoE += contigInterval + 1; tpoB = tpoE; }
             if (iSeq < 0) continue;
             if (iSeqPre >= 0 && iSeq != iSeqPre) { int iSeq0 = iSeq; iSeq = iSeqPre; HostHsp h; convert(h, r, tpoB, iSeq); flush(true, iSeq); iSeqPre = -1;
-              std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (!keys.count(key)) { cur.hsps.push_back(h); keys.insert(key); } iSeq = iSeq0; continue; } }
-          iSeqPre = iSeq; HostHsp h; convert(h, r, tpoB, iSeq); std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (!keys.count(key)) { cur.hsps.push_back(h); keys.insert(key); } }
-        if (iSeq >= 0) flush(false, iSeq); }
-      c = cEnd; } }
+              std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (std::find(keys.begin(), keys.end(), key) == keys.end()) { cur.hsps.push_back(h); keys.push_back(key); } iSeq = iSeq0; continue; } }
+          iSeqPre = iSeq; HostHsp h; convert(h, r, tpoB, iSeq); std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (std::find(keys.begin(), keys.end(), key) == keys.end()) { cur.hsps.push_back(h); keys.push_back(key); } }
+        if (iSeq >= 0) flush(false, iSeq); } } }
+    size_t ncl = 0, njb = 0; for (size_t si = 0; si < segCl.size(); si++) { ncl += segCl[si].size(); njb += segJobs[si].size(); } clusters.reserve(ncl); jobs.reserve(njb);
+    for (size_t si = 0; si < segCl.size(); si++) { int jo = (int)jobs.size(); for (HostCluster& cl : segCl[si]) { for (HostHsp& h : cl.hsps) if (h.job >= 0) h.job += jo; clusters.push_back(std::move(cl)); } jobs.insert(jobs.end(), segJobs[si].begin(), segJobs[si].end()); } }
+  lap("contig mapping");
   // ---- K5: extension + WFA
   u32 nj = (u32)jobs.size(); std::vector<ExtOut> hext; std::vector<WfaOut> hw; std::vector<u64> hops;
   if (nj) {
@@ -983,13 +1049,15 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); std::vector<u64> hso(2 * (u64)nj + 1, 0); for (u64 i = 0; i < 2 * (u64)nj; i++) hso[i + 1] = hso[i] + hec[i]; u64 ES = hso.back();
     DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i32> esc(ES + 2, st);
     { KTimer kt(st, &ix->ms[13]); k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK(); }
-    DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
+    lap("extend kernels"); DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
     wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, prm->wfa_adaptive, hw, hops, ix->counters, ix->ms);
   }
+  lap("K5 total");
   T.mark();                                                                                              // [5] extend + wfa
   // ---- finishing: scores, filters, ordering, rows (lib-index-search.go:2266-2357, :2701-2932; search.go:437-533)
   const double lnK = std::log(0.41), totalBases = (double)I.total_bases;
-  for (HostCluster& cl : clusters) { i32 qlen = 0; if (!cl.hsps.empty()) { } const WinItem& w = items[cl.item]; qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); double maxSim = 0; bool has = false;
+#pragma omp parallel for schedule(static) num_threads(std::max(1, std::min(16, omp_get_max_threads())))
+  for (i64 cli = 0; cli < (i64)clusters.size(); cli++) { HostCluster& cl = clusters[cli]; i32 qlen = 0; const WinItem& w = items[cl.item]; qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); double maxSim = 0; bool has = false;
     for (HostHsp& h : cl.hsps) { if (h.dead) continue; const WfaOut& o = hw[h.job]; const ExtOut& e = hext[h.job]; i32 ql = e.qe - e.qs, tl = e.te - e.ts;
       if (!o.has_m) { h.dead = true; continue; }   // trimOps == nil -> evalue MaxFloat64 > max_evalue
       int _s = o.bscore; if (_s & 1) _s--; double bs = (0.625 * (double)_s - lnK) / M_LN2; h.score = o.bscore; h.bitscore = (int)bs; h.evalue = totalBases * std::pow(2, -bs) * (double)ql; if (h.evalue > prm->max_evalue) { h.dead = true; continue; }
@@ -1002,14 +1070,21 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
         for (int i = a; i >= 0 && i <= b; i++) { char c = (char)(ops[i] >> 32); if (c == 'D') c = 'I'; else if (c == 'I') c = 'D'; h.cigar += std::to_string((u32)(ops[i] & 0xffffffffu)); h.cigar.push_back(c); } }
       double sim = (double)h.bitscore * h.pident; if (sim > maxSim) maxSim = sim; has = true; }
     cl.has = has; cl.sim = maxSim; }
-  // group clusters per segment -> genomes -> queries
+  lap("score clusters");
+  // group clusters per segment -> genomes -> queries; whole queries are independent, so static chunks of queries run in parallel
   struct GenomeOut { u32 seg; std::vector<const HostCluster*> sds; double af; };
-  std::vector<GenomeOut> gouts; { size_t x = 0; while (x < clusters.size()) { u32 seg = clusters[x].seg; GenomeOut g; g.seg = seg; g.af = 0; size_t y = x; while (y < clusters.size() && clusters[y].seg == seg) { if (clusters[y].has) g.sds.push_back(&clusters[y]); y++; } x = y; if (g.sds.empty()) continue;
-      u32 q = (u32)(S.h_key[seg] >> 36); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
-      int cov = 0; if (reg.size() == 1) cov = reg[0][1] - reg[0][0] + 1; else if (!reg.empty()) { std::stable_sort(reg.begin(), reg.end(), [](const std::array<int, 2>& a, const std::array<int, 2>& b) { return a[0] < b[0]; }); int s0 = reg[0][0], e0 = reg[0][1]; for (size_t i = 1; i < reg.size(); i++) { if (reg[i][0] > e0) { cov += e0 - s0 + 1; s0 = reg[i][0]; e0 = reg[i][1]; continue; } if (reg[i][1] <= e0) continue; e0 = reg[i][1]; } cov += e0 - s0 + 1; }
-      g.af = (double)cov / (double)qlen * 100; if (g.af > 100) g.af = 100; if (g.af < prm->min_qcov_genome) continue;
-      std::stable_sort(g.sds.begin(), g.sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); gouts.push_back(std::move(g)); } }
-  { size_t x = 0; while (x < gouts.size()) { u32 q = (u32)(S.h_key[gouts[x].seg] >> 36); size_t y = x; while (y < gouts.size() && (u32)(S.h_key[gouts[y].seg] >> 36) == q) y++;
+  const int NTF = std::max(1, std::min(16, omp_get_max_threads())); std::vector<size_t> cut(NTF + 1, clusters.size()); cut[0] = 0;
+  for (int t = 1; t < NTF; t++) { size_t x = clusters.size() * t / NTF; while (x > 0 && x < clusters.size() && (u32)(S.h_key[clusters[x].seg] >> 36) == (u32)(S.h_key[clusters[x - 1].seg] >> 36)) x++; cut[t] = std::max(x, cut[t - 1]); }
+  std::vector<std::vector<lmg_hsp>> trows(NTF); std::vector<std::string> tpool(NTF); std::vector<std::vector<u32>> trg(NTF);
+#pragma omp parallel for schedule(static, 1) num_threads(NTF)
+  for (int ti = 0; ti < NTF; ti++) {
+    std::vector<GenomeOut> gouts; std::vector<lmg_hsp>& rows = trows[ti]; std::string& pool = tpool[ti]; std::vector<u32>& rg = trg[ti];
+    { size_t x = cut[ti]; while (x < cut[ti + 1]) { u32 seg = clusters[x].seg; GenomeOut g; g.seg = seg; g.af = 0; size_t y = x; while (y < cut[ti + 1] && clusters[y].seg == seg) { if (clusters[y].has) g.sds.push_back(&clusters[y]); y++; } x = y; if (g.sds.empty()) continue;
+        u32 q = (u32)(S.h_key[seg] >> 36); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
+        int cov = 0; if (reg.size() == 1) cov = reg[0][1] - reg[0][0] + 1; else if (!reg.empty()) { std::stable_sort(reg.begin(), reg.end(), [](const std::array<int, 2>& a, const std::array<int, 2>& b) { return a[0] < b[0]; }); int s0 = reg[0][0], e0 = reg[0][1]; for (size_t i = 1; i < reg.size(); i++) { if (reg[i][0] > e0) { cov += e0 - s0 + 1; s0 = reg[i][0]; e0 = reg[i][1]; continue; } if (reg[i][1] <= e0) continue; e0 = reg[i][1]; } cov += e0 - s0 + 1; }
+        g.af = (double)cov / (double)qlen * 100; if (g.af > 100) g.af = 100; if (g.af < prm->min_qcov_genome) continue;
+        std::stable_sort(g.sds.begin(), g.sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); gouts.push_back(std::move(g)); } }
+    size_t x = 0; while (x < gouts.size()) { u32 q = (u32)(S.h_key[gouts[x].seg] >> 36); size_t y = x; while (y < gouts.size() && (u32)(S.h_key[gouts[y].seg] >> 36) == q) y++;
       std::vector<GenomeOut*> rs; for (size_t z = x; z < y; z++) rs.push_back(&gouts[z]);
       auto bgi_of = [&](const GenomeOut* g) { return I.genome_bgi[(u32)((S.h_key[g->seg] >> 2) & 0x3FFFFFFFFull)]; };
       std::stable_sort(rs.begin(), rs.end(), [&](GenomeOut* a, GenomeOut* b) { return (bgi_of(a) & 131071) < (bgi_of(b) & 131071); });    // :1848-1853
@@ -1019,8 +1094,10 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
         for (size_t i = 0; i < g->sds.size(); i++) { if (used[i]) continue; for (size_t j = i; j < g->sds.size(); j++) if (!used[j] && g->sds[j]->iseq == g->sds[i]->iseq) { used[j] = 1; ord.push_back(g->sds[j]); } }
         int cls = 1, j = 1; for (const HostCluster* sd : ord) { for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[gd].size(); r.chunk_idx = 0; r.n_chunks = 1; r.seq_len = (i32)I.seq_sizes[gd][sd->iseq];
             r.cls = cls; r.hsp = j; r.qb = h.qb; r.qe = h.qe; r.tb = h.tb; r.te = h.te; r.rc = sd->rc; r.alen = h.alen; r.matches = h.matched; r.gaps = h.gaps; r.score = h.score; r.bitscore = h.bitscore; r.evalue = h.evalue; r.qcov_hsp = h.af; r.pident = h.pident; r.qcov_gnm = g->af;
-            r.cigar_off = R.pool.size(); r.cigar_len = (u32)h.cigar.size(); R.pool += h.cigar; R.rows.push_back(r); R.seqids.push_back(I.seq_ids[gd][sd->iseq]); j++; } cls++; } }
+            r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; rows.push_back(r); rg.push_back(gd); j++; } cls++; } }
       x = y; } }
+  { size_t nr = 0; for (auto& v : trows) nr += v.size(); R.rows.reserve(nr); R.row_genome.reserve(nr); for (int ti = 0; ti < NTF; ti++) { u64 po = R.pool.size(); for (lmg_hsp& r : trows[ti]) { r.cigar_off += po; R.rows.push_back(r); } R.pool += tpool[ti]; R.row_genome.insert(R.row_genome.end(), trg[ti].begin(), trg[ti].end()); } R.img = &I; }
+  lap("group+rows");
   T.mark(); finish_times(7);                                                                             // [6] finish (host)
 }
 
@@ -1049,8 +1126,8 @@ void lmg_free(void* p) { free(p); }
 int lmg_last_timing(const lmg_index* ix, double* ms16, uint64_t* c16) { for (int i = 0; i < 16; i++) { if (ms16) ms16[i] = ix->ms[i]; if (c16) c16[i] = ix->counters[i]; } if (c16) c16[15] = g_launches; return 0; }
 
 int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* kmers, uint32_t* nlocs, uint32_t* minloc, uint64_t* suf, uint64_t suf_cap, uint64_t* n_suf) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
-    const int m = ix->img.m, k = ix->img.k; auto hc = cap.to_host(); auto hv = B.qvals.to_host(); auto ho = owner.to_host(); u64 ns = 0; std::vector<std::array<u64, 4>> trip;
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+    const int m = ix->img.m, k = ix->img.k; std::vector<Capture> hc((u64)n * m); { auto a = cap.kmer.to_host(); auto b = cap.lo.to_host(); auto c = cap.n.to_host(); auto d = cap.smask.to_host(); for (size_t i = 0; i < hc.size(); i++) { hc[i].kmer = a[i]; hc[i].lo = b[i]; hc[i].n = c[i]; hc[i].smask = d[i]; } } auto hv = B.qvals.to_host(); auto ho = owner.to_host(); u64 ns = 0; std::vector<std::array<u64, 4>> trip;
     for (int q = 0; q < n; q++) { trip.clear();
       for (int i = 0; i < m; i++) { const Capture& c = hc[(u64)q * m + i]; u64 o = (u64)q * m + i; kmers[o] = c.kmer; nlocs[o] = c.kmer ? c.n : 0; u32 mn = 0xffffffffu; if (c.kmer) for (u32 t = 0; t < c.n; t++) mn = std::min(mn, hv[B.h_koff[q] + c.lo + t] & 0x7fffffffu); minloc[o] = c.kmer ? mn : 0;
         if (c.kmer && ho[B.h_koff[q] + c.lo] == (u32)i) trip.push_back({(u64)q, (u64)c.smask, (u64)i, kmer_reverse62(c.kmer, k)}); }
@@ -1059,7 +1136,7 @@ int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int3
 }
 
 int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_anchor** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
     Anchors A; seed_probe(ix, B, p, cap, owner, A, true); auto hi = A.hi.to_host(A.n), lo = A.lo.to_host(A.n); lmg_anchor* o = (lmg_anchor*)malloc(sizeof(lmg_anchor) * (A.n + 1));
     for (u64 i = 0; i < A.n; i++) { lmg_anchor& a = o[i]; u32 g = (u32)((hi[i] >> 2) & 0x3FFFFFFFFull); a.genome = ix->img.genome_bgi[g]; a.query = (u32)(hi[i] >> 36); a.qbegin = (i32)(lo[i] >> 36); a.len = (u8)(63 - ((lo[i] >> 30) & 63)); a.tbegin = (i32)((lo[i] >> 2) & 0x0FFFFFFF); a.qrc = (lo[i] >> 1) & 1; a.trc = lo[i] & 1; a.pad = 0; }
     *out = o; *n_out = A.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
@@ -1068,7 +1145,7 @@ int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
 
 #define LMG_HAVE_CHAIN 1
 int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_chain** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); DBuf<Capture> cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
     Anchors A; seed_probe(ix, B, p, cap, owner, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
     lmg_chain* o = (lmg_chain*)malloc(sizeof(lmg_chain) * (C.n + 1));
     for (u32 i = 0; i < C.n; i++) { const ChainRec& r = C.h[i]; lmg_chain& c = o[i]; u64 key = S.h_key[r.seg]; c.query = (u32)(key >> 36); c.genome = ix->img.genome_bgi[(u32)((key >> 2) & 0x3FFFFFFFFull)]; c.score = r.score; c.n_seeds = r.nseeds;
@@ -1083,7 +1160,7 @@ int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
-int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) { if (row >= r->seqids.size()) return -1; *seqid = r->seqids[row].c_str(); return 0; }
+int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) { if (row >= r->rows.size() || !r->img) return -1; *seqid = r->img->seq_ids[r->row_genome[row]][r->rows[row].seq_idx].c_str(); return 0; }
 void lmg_results_free(lmg_results* r) { delete r; }
 
 #define LMG_HAVE_WFA 1

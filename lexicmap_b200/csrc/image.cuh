@@ -18,6 +18,8 @@ struct Image {
   u64 E = 0, V = 0; int G = 0; size_t bytes = 0;
   // device arrays
   u64 *d_masks = nullptr, *d_bucket_off = nullptr, *d_keys = nullptr, *d_val_off = nullptr, *d_vals = nullptr; u32* d_anchor_start = nullptr;
+  u32* d_anchor_bits = nullptr;   // m * NA/32 words: bit a of mask i set iff anchor_start[i][a] is present (10 MB, L2-resident filter in front of the 328 MB table)
+  u32* d_mask_pstart = nullptr; int mask_pbits = 14;   // masks bucketed by their mask_prefix leading bases: [pstart[p], pstart[p+1])
   u8* d_g2bit = nullptr; u64* d_g_off = nullptr; u32 *d_g_nbases = nullptr, *d_g_seq_off = nullptr, *d_seq_sizes = nullptr; u32* d_batch_base = nullptr;
   // host metadata
   std::vector<u64> h_masks; std::vector<std::string> genome_names; std::vector<u64> genome_bgi; std::vector<std::vector<std::string>> seq_ids; std::vector<std::vector<u32>> seq_sizes;
@@ -66,7 +68,9 @@ struct Image {
       for (u64 e = 0; e < E; e++) { no[e] = nv.size(); for (u64 t = val_off[e]; t < val_off[e + 1]; t++) { auto it = bgi2dense.find(vals[t] >> 30); if (it != bgi2dense.end() && (int)(it->second % n_shards) == shard) nv.push_back(vals[t]); } }
       no[E] = nv.size(); vals.swap(nv); val_off.swap(no); V = vals.size();
     }
+    { mask_pbits = 2 * mask_prefix; std::vector<u32> ps(((size_t)1 << mask_pbits) + 1, 0); for (u64 mk : h_masks) ps[(mk >> (2 * k - mask_pbits)) + 1]++; for (size_t i = 0; i + 1 < ps.size(); i++) ps[i + 1] += ps[i]; d_mask_pstart = up(ps); }
+    { std::vector<u32> bits((size_t)m * NA / 32 + 1, 0); for (size_t t = 0; t < anchor_start.size(); t++) if (anchor_start[t] != 0xFFFFFFFFu) bits[t >> 5] |= 1u << (t & 31); d_anchor_bits = up(bits); }
     d_masks = up(h_masks); d_bucket_off = up(bucket_off); d_keys = up(keys); d_val_off = up(val_off); d_vals = up(vals); d_anchor_start = up(anchor_start);
   }
-  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_keys, (void*)d_val_off, (void*)d_vals, (void*)d_anchor_start, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base}) if (p) cudaFree(p); }
+  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_keys, (void*)d_val_off, (void*)d_vals, (void*)d_anchor_start, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits}) if (p) cudaFree(p); }
 };
