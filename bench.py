@@ -233,12 +233,12 @@ def main():
            "e2e": {"value": bp_all / (t_e2e * 1e-3), "unit": "bp/s", "h2d_bytes_per_step": int(packed[0].nbytes + packed[1].nbytes), "d2h_bytes_per_step": int(nrows * 136), "ms_per_step": t_e2e},
            "gpu_launches": launches, "rows_per_step": rows_all,
            "stage_ms": {k: float(v) / a.steps for k, v in zip(["h2d", "sketch", "seed_probe", "chain", "pseudo_align", "extend_wfa", "host_finish", "total"], stage_ms)},
-           "roofline": {"bound": "hbm", "kernel": "k_probe_find", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "kernel": "k_probe_filter+k_probe_find2 (seed lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_probe * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},
            "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage],
-                     "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep", 10), ("wfa_fast", 11), ("wfa_general", 12), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
-                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11])},
+                     "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep+general", 10), ("wfa_fwd+bt", 11), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
+                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_filter_us": int(kcnt[12]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14]), "wfa_lmax": int(kcnt[15])},
            "clocks": sampler.summary()}
     print(json.dumps(out))
     idx.free_staged(staged)

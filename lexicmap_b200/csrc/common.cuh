@@ -22,7 +22,7 @@ struct Arena {
   void* alloc(size_t bytes) {
     bytes = al(bytes + 64);
     while (cur < chunks.size() && off + bytes > chunks[cur].size) { cur++; off = 0; }
-    if (cur >= chunks.size()) { size_t tot = 0; for (auto& c : chunks) tot += c.size; size_t sz = std::max(bytes, std::max<size_t>(tot, (size_t)1 << 30)); Chunk c; c.size = sz;
+    if (cur >= chunks.size()) { size_t tot = 0; for (auto& c : chunks) tot += c.size; size_t sz = std::max(bytes, std::max<size_t>(tot / 4, (size_t)1 << 30)); Chunk c; c.size = sz;
       cudaError_t e = cudaMalloc((void**)&c.base, sz); if (e != cudaSuccess) { cudaGetLastError(); c.size = sz = bytes; e = cudaMalloc((void**)&c.base, sz); }
       if (e != cudaSuccess) throw std::runtime_error(std::string("device arena: cudaMalloc failed: ") + cudaGetErrorString(e)); chunks.push_back(c); cur = chunks.size() - 1; off = 0; }
     void* p = chunks[cur].base + off; off += bytes; return p;

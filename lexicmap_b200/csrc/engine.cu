@@ -149,6 +149,39 @@ __global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, CapSoA cap, c
     if (have) hits[base + __popc(bal & ((1u << lane) - 1))] = h; }
 }
 
+// ---- two-phase probe. Phase A (k_probe_filter, one thread per (query, mask)): everything that can be decided from coalesced / L2-resident
+// data — captured k-mer present, first-owner test of the reversed k-mer, anchor presence bit — and compaction of the surviving probes.
+// Phase B (k_probe_find2, one thread per survivor): the dependent random HBM accesses (anchor start, key search, value flags) with all
+// lanes of a warp on the long path instead of ~1 in 3.
+struct Surv { u64 kmer; u32 qi; u32 aslot_dir; };   // aslot_dir = (bucket*NA + anchor) | dir << 31
+__global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nslot, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
+  u64 qi = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool s0 = false, s1 = false; Surv a, b; u32 issued = 0;
+  if (qi < nslot) { u64 kmer = cap.kmer[qi];
+    if (kmer != 0) { u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); const int s2 = (P.k - P.p) << 1; const u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1;
+      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; } }
+      u32 lo = cap.lo[qi]; if (owner[koff[q] + lo] == (u32)i) { u64 rv = kmer_reverse62(kmer, P.k); u32 sm = cap.smask[qi]; u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)sm * P.NA + an; issued++;
+        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; } } } }
+  int lane = threadIdx.x & 31; u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1); u32 tot = __popc(b0) + __popc(b1);
+  if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
+    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = b; } }
+  if (stats) { for (int o = 16; o; o >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, o); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
+}
+__global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, CapSoA cap, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0;
+  if (t < ns) { Surv sv = surv[t]; int dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; int bucket = (int)(aslot / (u32)P.NA); u64 kmer = sv.kmer;
+    int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; u32 as = P.anchor_start[aslot];
+    u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; u64 lo = b0 + as, hi = b1;
+    u64 step = 1, l = lo; while (l + step < hi && P.keys[l + step] < left) { l += step; step <<= 1; steps++; }
+    u64 r = min(hi, l + step); if (P.keys[l] >= left) r = l; else l = l + 1;
+    while (l < r) { u64 mid = (l + r) >> 1; if (P.keys[mid] < left) l = mid + 1; else r = mid; steps++; }
+    u64 e0 = l; u32 na = 0;
+    while (e0 + ne < hi && P.keys[e0 + ne] <= right) { u64 v0 = P.val_off[e0 + ne], v1 = P.val_off[e0 + ne + 1]; if (v1 > v0 && (int)(P.vals[v0] & 1) == dir) na += (u32)(v1 - v0); ne++; }
+    if (na) { u32 cl = cap.lo[sv.qi], cn = cap.n[sv.qi]; have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = cl; h.n = cn; h.kmer = kmer; h.nanch = na * cn; h.pad = 0; } }
+  int lane = threadIdx.x & 31; u32 bal = __ballot_sync(FULLMASK, have);
+  if (bal) { u32 base = 0; if (lane == __ffs(bal) - 1) base = atomicAdd(nhits, __popc(bal)); base = __shfl_sync(FULLMASK, base, __ffs(bal) - 1); if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_hits) hits[w] = h; } }
+  if (stats) { for (int o = 16; o; o >>= 1) { steps += __shfl_xor_sync(FULLMASK, steps, o); ne += __shfl_xor_sync(FULLMASK, ne, o); } if (lane == 0) { atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); } }
+}
+
 __global__ void k_hit_counts(const ProbeHit* __restrict__ h, u32 n, u64* __restrict__ c) { u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t <= n) c[t] = (t < n) ? h[t].nanch : 0; }
 
 // anchor keys: hi = query<<36 | genome(dense)<<2 | (sorted only on bits >= 2) ; lo = QBegin<<36 | (63-Len)<<30 | TBegin<<2 | qrc<<1 | trc
@@ -178,7 +211,7 @@ struct QBatch {  // device-side query batch
 
 struct lmg_index {
   Image img; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[2] = {nullptr, nullptr}; Arena arena;
+  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena;
 };
 
 static thread_local std::string g_err;
@@ -237,16 +270,21 @@ static int bits_for(u64 v) { int b = 1; while ((v >> b) && b < 64) b++; return b
 static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, CapBufs& cap, DBuf<u32>& owner, Anchors& A, bool stats) {
   cudaStream_t st = ix->st; const Image& I = ix->img; if (prm->min_prefix < I.mask_prefix + I.anchor_prefix || prm->min_prefix > I.k) throw std::runtime_error("the minimum prefix length should be in the range of [maskPrefix+anchorPrefix, k]");  // kv-searcher.go:202
   ProbeParams P = probe_params(I, prm->min_prefix); u64 nprobe = (u64)B.nq * I.m * 2;
-  DBuf<u32> nh(1, st); nh.zero(); DBuf<u64> dstats(8, st); dstats.zero();
-  // hit list capacity: every probe may hit
-  u64 capHits = std::min<u64>(nprobe, 1ull << 31); DBuf<ProbeHit> hits;
-  // first pass with a bounded list; typical hit rates are a few % of probes
-  u64 tryCap = std::min<u64>(capHits, std::max<u64>(1u << 20, nprobe / 4));
-  for (;;) { hits.alloc(tryCap, st); nh.zero(); if (stats) dstats.zero();
-    if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); } cudaEventRecord(ix->kev[0], st);
-    k_probe_find<<<cdiv((i64)nprobe, 256), 256, 0, st>>>(P, cap.soa(), owner.p, B.koff.p, nprobe, hits.p, nh.p, stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
-    u32 h = nh.to_host()[0]; { float f = 0; cudaEventElapsedTime(&f, ix->kev[0], ix->kev[1]); ix->ms[8] = f; ix->counters[8] = nprobe; } if (h <= tryCap) { tryCap = h; break; } tryCap = capHits; }
-  u32 nhit = (u32)tryCap; if (stats) { auto s = dstats.to_host(); for (int i = 0; i < 4; i++) ix->counters[i] = s[i]; ix->counters[4] = nhit; }
+  DBuf<u32> nh(1, st), nsv(1, st); DBuf<u64> dstats(8, st); dstats.zero(); u64 nslot = (u64)B.nq * I.m;
+  if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); cudaEventCreate(&ix->kev[2]); }
+  // phase A: filter + compact (capacity: half of all probes first, everything on overflow)
+  DBuf<Surv> surv; u64 capS = std::max<u64>(1u << 20, nprobe / 2); u32 ns = 0;
+  for (int attempt = 0; attempt < 2; attempt++) { surv.alloc(capS, st); nsv.zero(); dstats.zero(); cudaEventRecord(ix->kev[0], st);
+    k_probe_filter<<<cdiv((i64)nslot, 256), 256, 0, st>>>(P, cap.soa(), owner.p, B.koff.p, nslot, surv.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
+    ns = nsv.to_host()[0]; if (ns <= capS) break; capS = nprobe; }
+  // phase B: index lookup on the survivors
+  DBuf<ProbeHit> hits; u64 capH = std::max<u64>(1u << 18, (u64)ns / 2 + 1024); u32 nhit = 0;
+  for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) { u64 z[2] = {0, 0}; CUDA_CHECK(cudaMemcpyAsync(dstats.p + 2, z, 16, cudaMemcpyHostToDevice, st)); }
+    cudaEventRecord(ix->kev[1], st); k_probe_find2<<<cdiv(ns, 256), 256, 0, st>>>(P, cap.soa(), surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
+    nhit = nh.to_host()[0]; if (nhit <= capH) break; capH = (u64)ns + 1024; }
+  if (!hits.p) hits.alloc(16, st);
+  { float fa = 0, fb = 0; cudaEventSynchronize(ix->kev[1]); cudaEventElapsedTime(&fa, ix->kev[0], ix->kev[1]); if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] = fa + fb; ix->counters[8] = nprobe; ix->counters[12] = (u64)(fa * 1000); ix->counters[13] = (u64)(fb * 1000); }
+  { auto sdt = dstats.to_host(); ix->counters[0] = sdt[0]; ix->counters[1] = ns; if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; } ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
   DBuf<u64> hoff(nhit + 1, st);
   { DBuf<u64> cnt(nhit + 1, st); k_hit_counts<<<cdiv(nhit + 1, 256), 256, 0, st>>>(hits.p, nhit, cnt.p); KERNEL_CHECK();
@@ -422,14 +460,22 @@ __device__ bool tree_search_slow(const u64* __restrict__ a, u32 n, u64 key, int 
 }
 // keys sharing >= p leading bases with `key`: [lo,hi) in the sorted table (fast path = range search; the radix-tree quirk only
 // adds results when the range is empty and bases [p-2,p) of the key are AA)
-__device__ __forceinline__ bool tree_search(const u64* __restrict__ a, u32 n, u64 key, int p, u32* rlo, u32* rhi) {
-  const int K = 31; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 x = 0, y = n;
+// The radix-tree quirk can only fire when the query shares d+1 >= 1 bases with some key (d = matched depth), d <= p-2, and its bases
+// [d, p) are all A. With L = longest common prefix with the two neighbours of the insertion point (L < p here), that implies bases
+// [L-1, p) all A: a cheap necessary test that keeps the emulation off the common path.
+__device__ __forceinline__ bool quirk_possible(const u64* __restrict__ a, u32 n, u32 x, u64 key, int p) {
+  const int K = 31; if (p < 2 || ((key >> (2 * (K - p))) & 0xF) != 0) return false; int L = 0; if (x > 0) L = max(L, lcp31(key, a[x - 1])); if (x < n) L = max(L, lcp31(key, a[x])); if (L < 1) return false;
+  int from = min(L - 1, p - 2); u64 span = (key >> (2 * (K - p))) & ((1ull << (2 * (p - from))) - 1); return span == 0;
+}
+__device__ __forceinline__ bool tree_search_in(const u64* __restrict__ a, u32 n, u32 x, u32 y, u64 key, int p, u32* rlo, u32* rhi) {   // [x,y) must contain every key sharing >= p bases with `key`
+  const int K = 31; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low;
   while (x < y) { u32 m = (x + y) >> 1; if (a[m] < left) x = m + 1; else y = m; }
   u32 e = x; while (e < n && a[e] <= right) e++;
   if (e > x) { *rlo = x; *rhi = e; return true; }
-  if (p >= 2 && ((key >> (2 * (K - p))) & 0xF) == 0) return tree_search_slow(a, n, key, p, rlo, rhi);
+  if (quirk_possible(a, n, x, key, p)) return tree_search_slow(a, n, key, p, rlo, rhi);
   return false;
 }
+__device__ __forceinline__ bool tree_search(const u64* __restrict__ a, u32 n, u64 key, int p, u32* rlo, u32* rhi) { return tree_search_in(a, n, 0, n, key, p, rlo, rhi); }
 
 // one CTA per window; threads over target positions. EMIT=false: count anchors; EMIT=true: write them (packed like seed anchors).
 template <bool EMIT>
@@ -478,7 +524,7 @@ __device__ __forceinline__ bool th_lookup(const u64* __restrict__ T, u32 H, u32 
 // keys sharing >= p bases: hash path when p == 11, else binary search; identical result set to tree_search()
 __device__ __forceinline__ bool tree_search_h(const u64* __restrict__ a, u32 n, const u64* __restrict__ T, u32 H, u64 key, int p, u32* rlo, u32* rhi) {
   if (p == 11 && H) { u32 st, c; if (th_lookup(T, H, (u32)(key >> 40), &st, &c)) { if (c) { *rlo = st; *rhi = st + c; return true; } return tree_search(a, n, key, p, rlo, rhi); }
-    if (((key >> 40) & 0xF) == 0) return tree_search_slow(a, n, key, p, rlo, rhi); return false; }
+    if (((key >> 40) & 0xF) == 0) return tree_search(a, n, key, p, rlo, rhi); return false; }
   return tree_search(a, n, key, p, rlo, rhi);
 }
 // one CTA per window. The oriented window is packed into shared memory (16 bases per word) once; every thread extracts its 31-mer
@@ -517,9 +563,15 @@ __global__ void __launch_bounds__(128) k_pa_anchors2(const WinItem* __restrict__
 // Windows are packed into shared memory one at a time. Queries whose table does not fit use k_pa_anchors2 (table in L2).
 __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
                                                      const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn) {
-  __shared__ u32 s_base; extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
+  __shared__ u32 s_base; __shared__ u32 bloom[1024]; __shared__ u32 pdir[257];   // bloom: 32768 bits over hashed 11-base prefixes; pdir: first table row of every 4-base prefix
+  extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
   const u32 q = qlist[blockIdx.x]; const u32 t0q = toff[q], tn = toff[q + 1] - t0q; const int K = 31;
+  for (u32 i = threadIdx.x; i < 1024; i += 256) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += 256) pdir[i] = tn;
   for (u32 i = threadIdx.x; i < tn; i += 256) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < tn; i += 256) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> 17; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
+  __syncthreads();
+  if (threadIdx.x == 0) { u32 nxt = tn; for (int b = 255; b >= 0; b--) { if (pdir[b] == tn) pdir[b] = nxt; else nxt = pdir[b]; } pdir[256] = tn; }   // empty buckets -> start of the next one
   const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull;
   for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
@@ -531,7 +583,9 @@ __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__
     for (i32 idx = threadIdx.x; idx < np; idx += 256) {
       u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2, kr = kmer_reverse62(~km & ttt, K);
       if (km == 0 || km == ccc || km == ggg || km == ttt || !tn) continue;
-      u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0, c = 0; bool f1 = tree_search(sk, tn, km, w.mp, &l1, &h1), f2 = tree_search(sk, tn, kr, w.mp, &l2, &h2);
+      u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0, c = 0; bool f1, f2;
+      { u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; bool maybe = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0); u32 b = (u32)(km >> 54); f1 = maybe && tree_search_in(sk, tn, pdir[b], pdir[b + 1], km, w.mp, &l1, &h1);
+        hb = ((u32)(kr >> 40) * 2654435761u) >> 17; maybe = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); b = (u32)(kr >> 54); f2 = maybe && tree_search_in(sk, tn, pdir[b], pdir[b + 1], kr, w.mp, &l2, &h2); }
       if (f1) for (u32 u = l1; u < h1; u++) { u32 vv = sv[u]; int lp = lcp31(km, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
       if (f2) for (u32 u = l2; u < h2; u++) { u32 vv = sv[u]; int lp = lcp31(kr, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
       if (!c) continue; u32 wpos = atomicAdd(&s_base, c); if ((u64)wpos + c > (u64)cap) continue; u64* out = a_lo + base0 + wpos;
@@ -547,10 +601,19 @@ struct Chain2Params { int max_gap, min_score, min_align_len, band_count, band_ba
 
 // one warp per window: nested-anchor removal, trimming, banded chaining DP, region splitting. Scalar control flow is executed
 // redundantly by all lanes (uniform); the DP inner loop and arg-max scans are lane-parallel.
-__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_in, const u64* __restrict__ abeg, const u64* __restrict__ aend, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
+#define PA_SORT_MAX 0   // in-kernel warp bitonic sort measured slower than CUB's segmented sort at 64 KB smem / CTA (occupancy); 0 = always CUB
+// lo_sorted: output of the CUB segmented sort (only used by windows with more than PA_SORT_MAX anchors); smaller windows sort their
+// anchors right here with a warp-level bitonic network in shared memory, reading the unsorted anchors from c_lo (which is then reused
+// as the compacted output, as before).
+__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_sorted, const u64* __restrict__ abeg, const u64* __restrict__ aend, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
                                                   C2Rec* __restrict__ out, u32* __restrict__ nout, u32 cap) {
+  extern __shared__ u64 ssort[];
   u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31; if (it >= nitems) return;
-  u64 b = abeg[it]; u32 n = (u32)(aend[it] - b); if (n == 0) return; const u64* A = lo_in + b; u64* C = c_lo + b; const int k = P.k;
+  u64 b = abeg[it]; u32 n = (u32)(aend[it] - b); if (n == 0) return; u64* C = c_lo + b; const u64* A = lo_sorted + b; const int k = P.k;
+  if (PA_SORT_MAX > 0 && n <= PA_SORT_MAX) { u64* sm = ssort + (threadIdx.x >> 5) * PA_SORT_MAX; u32 Pn = 32; while (Pn < n) Pn <<= 1;
+    for (u32 i = lane; i < Pn; i += 32) sm[i] = (i < n) ? C[i] : ~0ull; __syncwarp();
+    for (u32 kk = 2; kk <= Pn; kk <<= 1) for (u32 j = kk >> 1; j > 0; j >>= 1) { for (u32 t = lane; t < (Pn >> 1); t += 32) { u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j; bool up = (i & kk) == 0; u64 x = sm[i], y = sm[l]; if ((x > y) == up) { sm[i] = y; sm[l] = x; } } __syncwarp(); }
+    A = sm; }
   // ---- ClearSubstrPairs
   if (n > 1) { u32 kept = 0;
     for (u32 base = 0; base < n; base += 32) { u32 i = base + lane; bool keep = false;
@@ -798,26 +861,26 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
 struct WfaSeg { u64 qw, tw; };   // word offsets of the job's packed query / target (query: 2 streams: bases at qw, ambiguity at qw + nqw)
 
 __global__ void k_wfa_prep(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, u32 njobs, const u64* __restrict__ woff /*2 per job +1*/, const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff,
-                           const u8* __restrict__ g2bit, const u64* __restrict__ g_off, u64* __restrict__ words) {
-  u32 jb = blockIdx.x; if (jb >= njobs) return; HspJob J = jobs[jb]; ExtOut e = ext[jb]; const u8* q2 = qpacked + qboff[J.q]; const u8* qm = qamask + qboff[J.q]; const u8* g2 = g2bit + g_off[J.g];
+                           const u8* __restrict__ g2bit, const u64* __restrict__ g_off, u64* __restrict__ words, u32* __restrict__ has_amb) {
+  u32 jb = blockIdx.x; if (jb >= njobs) return; if (threadIdx.x == 0) has_amb[jb] = 0; __syncthreads(); HspJob J = jobs[jb]; ExtOut e = ext[jb]; const u8* q2 = qpacked + qboff[J.q]; const u8* qm = qamask + qboff[J.q]; const u8* g2 = g2bit + g_off[J.g];
   i32 plen = e.qe - e.qs, tlen = e.te - e.ts; u32 nq = (u32)((plen + 31) / 32 + 2), nt = (u32)((tlen + 31) / 32 + 2); u64* Q = words + woff[2 * jb]; u64* A = Q + nq; u64* T = words + woff[2 * jb + 1];
-  for (u32 w = threadIdx.x; w < nq; w += blockDim.x) { u64 b = 0, a = 0; for (int j = 0; j < 32; j++) { i32 i = (i32)w * 32 + j; u64 c = 0, am = 0; if (i < plen) { i32 p = e.qs + i; c = get_base(q2, (u64)p); am = ((qm[p >> 3] >> (p & 7)) & 1) ? 3 : 0; } b = (b << 2) | c; a = (a << 2) | am; } Q[w] = b; A[w] = a; }
+  for (u32 w = threadIdx.x; w < nq; w += blockDim.x) { u64 b = 0, a = 0; for (int j = 0; j < 32; j++) { i32 i = (i32)w * 32 + j; u64 c = 0, am = 0; if (i < plen) { i32 p = e.qs + i; c = get_base(q2, (u64)p); am = ((qm[p >> 3] >> (p & 7)) & 1) ? 3 : 0; } b = (b << 2) | c; a = (a << 2) | am; } Q[w] = b; A[w] = a; if (a) has_amb[jb] = 1; }
   for (u32 w = threadIdx.x; w < nt; w += blockDim.x) { u64 b = 0; for (int j = 0; j < 32; j++) { i32 i = (i32)w * 32 + j; u64 c = (i < tlen) ? win_base(g2, J.tBegin, J.tEnd, J.rc, e.ts + i) : 0; b = (b << 2) | c; } T[w] = b; }
 }
 __device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos) { u32 i = (u32)pos >> 5, sh = ((u32)pos & 31) * 2; u64 a = W[i]; if (sh == 0) return a; return (a << sh) | (W[i + 1] >> (64 - sh)); }
 
-__global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, u32 njobs, u32* __restrict__ next_job,
-                                                          u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int adaptive) {
+__global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, u32 job0, u32 njobs, u32* __restrict__ next_job,
+                                                          u16* __restrict__ slabs, WfaOut* __restrict__ outs, int adaptive, int lmax) {
   __shared__ u16 ring[WF_WARPS][9][WFS];   // 0-4: M levels (L%5), 5-6: I (L%2), 7-8: D (L%2)
   const int X2 = 2, OE2 = 4, E2 = 1;        // penalties 4 / 8 / 2 in units of levels (score = 2*level)
-  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u32 warp = blockIdx.x * WF_WARPS + wib; u16* slab = slabs + (u64)warp * WF_LMAX * 3 * WFS; u16 (*R)[WFS] = ring[wib]; u64* ops = ops_scratch + (u64)warp * WF_OPSMAX;
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u16 (*R)[WFS] = ring[wib];
   for (;;) {
-    u32 jb = 0; if (lane == 0) jb = atomicAdd(next_job, 1u); jb = __shfl_sync(FULLMASK, jb, 0); if (jb >= njobs) return;
+    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job0 + jr; u16* slab = slabs + (u64)jr * lmax * 3 * WFS;   // one slab per alignment of the round
     ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
-    const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1];
+    const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
     if (plen >= 65000 || tlen >= 65000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
-    auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = (fetch64(Q, v) ^ fetch64(T, h)) | fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
+    auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
     // level 0. History of levels L-1..L-4: effective lo/hi (after reduction), null bits (1 M, 2 I, 4 D). Every level writes the diagonals
     // [min(lo, rlo) - PAD, max(hi, rhi) + PAD] where [rlo,rhi] spans the effective ranges of the last 4 non-null levels, so later levels and
     // the backtrace can read k-1 / k+1 of any source level without bounds checks.
@@ -827,7 +890,7 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
       hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; __syncwarp(); }
     i32 L = 0; bool done = (kend == 0 && R[0][WFK0] != 0xFFFF && (i32)R[0][WFK0] >= tlen), overflow = false;
     while (!done) {
-      L++; if (L >= WF_LMAX) { overflow = true; break; }
+      L++; if (L >= lmax) { overflow = true; break; }
       bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; bool allnull = nx && no && ni && nd;
       if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
@@ -842,9 +905,8 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
           i32 a = (L >= OE2) ? (i32)M4[x - 1] : 0xFFFF, b = (i32)I1[x - 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 ins = max(a, b); ins = (ins < 0) ? -1 : ins + 1;
           a = (L >= OE2) ? (i32)M4[x + 1] : 0xFFFF; b = (i32)D1[x + 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 del = max(a, b);
           i32 mis = (L >= X2) ? (i32)M2[x] : 0xFFFF; mis = (mis == 0xFFFF) ? -1 : mis + 1;
-          if (!(ins >= 0 && ins - k >= 0 && ins <= tlen && ins - k <= plen)) ins = -1;
-          if (!(del >= 0 && del - k >= 0 && del <= tlen && del - k <= plen)) del = -1;
-          if (!(mis >= 0 && mis - k >= 0 && mis <= tlen && mis - k <= plen)) mis = -1;
+          const i32 hmax = min(tlen, plen + k);   // h <= tlen and v = h - k <= plen; h >= 0 and v >= 0 hold by construction
+          if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
           i32 mm = max(mis, max(ins, del)); if (mm >= 0) { mm = extend(k, mm); anyM = true; om = (u16)mm; } if (ins >= 0) { anyI = true; oi = (u16)ins; } if (del >= 0) { anyD = true; od = (u16)del; }
         }
         Mo[x] = om; Io[x] = oi; Do[x] = od; G[x] = om; G[WFS + x] = oi; G[2 * WFS + x] = od;
@@ -868,35 +930,39 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
       __syncwarp();
       if (!allnull && kend >= lo && kend <= hi) { u16 v = Mo[kend + WFK0]; done = (v != 0xFFFF && (i32)v >= tlen); }
     }
-    if (overflow) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
-    if (lane == 0) {   // backtrace, identical decision rule to k_wfa
-      WfaOut& Rr = Rz; Rr.wscore = 2 * L; i32 k = kend, off = tlen, lv = L; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
-      auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
-      auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
-        if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
-        else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
-      auto ld = [&](i32 lvl, int comp, i32 kk) -> i32 { if (lvl < 0) return -1; u16 v = slab[(u64)lvl * 3 * WFS + comp * WFS + kk + WFK0]; return v == 0xFFFF ? -1 : (i32)v; };
-      auto pig = [](i32 o, int type) -> i64 { return o < 0 ? INT64_MIN : (((i64)o << 4) | type); };
-      while (vv > 0 && h > 0 && lv > 0) {
-        i32 l_mis = lv - X2, l_open = lv - OE2, l_ext = lv - E2; i64 c_mis = INT64_MIN, c_io = INT64_MIN, c_ie = INT64_MIN, c_do = INT64_MIN, c_de = INT64_MIN;
-        i32 v_mis = -1, v_io = -1, v_ie = -1, v_do = -1, v_de = -1;
-        if (mat == 0) v_mis = ld(l_mis, 0, k); if (mat == 0 || mat == 1) { v_io = ld(l_open, 0, k - 1); v_ie = ld(l_ext, 1, k - 1); } if (mat == 0 || mat == 2) { v_do = ld(l_open, 0, k + 1); v_de = ld(l_ext, 2, k + 1); }
-        if (mat == 0) c_mis = pig(v_mis < 0 ? -1 : v_mis + 1, 9); if (mat == 0 || mat == 1) { c_io = pig(v_io < 0 ? -1 : v_io + 1, 1); c_ie = pig(v_ie < 0 ? -1 : v_ie + 1, 2); } if (mat == 0 || mat == 2) { c_do = pig(v_do, 5); c_de = pig(v_de, 6); }
-        i64 best = max(c_mis, max(max(c_io, c_ie), max(c_do, c_de))); if (best == INT64_MIN) { Rr.status = 2; break; }
-        if (mat == 0) { i32 mo = (i32)(best >> 4); i32 nm = off - mo; put('M', nm, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
-        int type = (int)(best & 15);
-        switch (type) { case 9: lv = l_mis; mat = 0; put('X', 1, off - k, off); off--; break;
-          case 1: lv = l_open; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: lv = l_ext; mat = 1; put('I', 1, off - k, off); k--; off--; break;
-          case 5: lv = l_open; mat = 0; put('D', 1, off - k, off); k++; break; case 6: lv = l_ext; mat = 2; put('D', 1, off - k, off); k++; break; }
-        vv = off - k; h = off;
-      }
-      if (Rr.status == 0) { if (lv == 0) put('M', off, off - k, off); else { if (vv > 0) put('D', vv, vv, h); if (h > 0) put('I', h, 0, h); } }
-      flush();
-      if (want_ops && Rr.status == 0) { if (ops_over) Rr.status = 1; else { u64 o = atomicAdd((unsigned long long*)ops_cursor, (unsigned long long)nops); if (o + nops <= ops_cap) { for (u32 i = 0; i < nops; i++) ops_pool[o + i] = ops[i]; Rr.ops_off = o; Rr.ops_n = nops; } else Rr.status = 3; } }
-      outs[jb] = Rr;
-    }
+    if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = 2 * L; outs[jb] = Rz; }   // the backtrace runs in k_wfa_bt, one thread per alignment
     __syncwarp();
   }
+}
+// Backtrace of the fast path, ONE THREAD per alignment: the walk is a chain of dependent HBM reads (~1 us each), so 32 of them per warp
+// (instead of lane 0 only) hide the latency. Same decision rule as k_wfa: mismatch(9) > D ext(6) > D open(5) > I ext(2) > I open(1).
+__global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, u32 job0, u32 njobs, const u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int lmax) {
+  const int X2 = 2, OE2 = 4, E2 = 1; u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
+  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u16* slab = slabs + (u64)t * lmax * 3 * WFS; u64* ops = ops_scratch + (u64)t * WF_OPSMAX;
+  i32 L = Rr.wscore / 2; i32 k = kend, off = tlen, lv = L; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0; (void)plen;
+  auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
+  auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
+    if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
+    else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
+  auto ld = [&](i32 lvl, int comp, i32 kk) -> i32 { if (lvl < 0) return -1; u16 v = slab[(u64)lvl * 3 * WFS + comp * WFS + kk + WFK0]; return v == 0xFFFF ? -1 : (i32)v; };
+  auto pig = [](i32 o, int type) -> i64 { return o < 0 ? INT64_MIN : (((i64)o << 4) | type); };
+  while (vv > 0 && h > 0 && lv > 0) {
+    i32 l_mis = lv - X2, l_open = lv - OE2, l_ext = lv - E2; i64 c_mis = INT64_MIN, c_io = INT64_MIN, c_ie = INT64_MIN, c_do = INT64_MIN, c_de = INT64_MIN;
+    i32 v_mis = -1, v_io = -1, v_ie = -1, v_do = -1, v_de = -1;
+    if (mat == 0) v_mis = ld(l_mis, 0, k); if (mat == 0 || mat == 1) { v_io = ld(l_open, 0, k - 1); v_ie = ld(l_ext, 1, k - 1); } if (mat == 0 || mat == 2) { v_do = ld(l_open, 0, k + 1); v_de = ld(l_ext, 2, k + 1); }
+    if (mat == 0) c_mis = pig(v_mis < 0 ? -1 : v_mis + 1, 9); if (mat == 0 || mat == 1) { c_io = pig(v_io < 0 ? -1 : v_io + 1, 1); c_ie = pig(v_ie < 0 ? -1 : v_ie + 1, 2); } if (mat == 0 || mat == 2) { c_do = pig(v_do, 5); c_de = pig(v_de, 6); }
+    i64 best = max(c_mis, max(max(c_io, c_ie), max(c_do, c_de))); if (best == INT64_MIN) { Rr.status = 2; break; }
+    if (mat == 0) { i32 mo = (i32)(best >> 4); i32 nm = off - mo; put('M', nm, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
+    int type = (int)(best & 15);
+    switch (type) { case 9: lv = l_mis; mat = 0; put('X', 1, off - k, off); off--; break;
+      case 1: lv = l_open; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: lv = l_ext; mat = 1; put('I', 1, off - k, off); k--; off--; break;
+      case 5: lv = l_open; mat = 0; put('D', 1, off - k, off); k++; break; case 6: lv = l_ext; mat = 2; put('D', 1, off - k, off); k++; break; }
+    vv = off - k; h = off;
+  }
+  if (Rr.status == 0) { if (lv == 0) put('M', off, off - k, off); else { if (vv > 0) put('D', vv, vv, h); if (h > 0) put('I', h, 0, h); } }
+  flush();
+  if (want_ops && Rr.status == 0) { if (ops_over) Rr.status = 1; else { u64 o = atomicAdd((unsigned long long*)ops_cursor, (unsigned long long)nops); if (o + nops <= ops_cap) { for (u32 i = 0; i < nops; i++) ops_pool[o + i] = ops[i]; Rr.ops_off = o; Rr.ops_n = nops; } else Rr.status = 3; } }
+  outs[jb] = Rr;
 }
 
 static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
@@ -905,11 +971,20 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
-      DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st);
-      { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p); KERNEL_CHECK(); }
-      u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (nj + WF_WARPS - 1) / WF_WARPS); u64 nwarps = (u64)blocks * WF_WARPS;
-      DBuf<u16> fslabs(nwarps * WF_LMAX * 3 * WFS, st); DBuf<u64> oscr(want_ops ? nwarps * WF_OPSMAX : 8, st); DBuf<u32> next(1, st); next.zero();
-      { KTimer kt(st, &ms[11]); k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, nj, next.p, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); }
+      DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st); DBuf<u32> hasamb(nj + 1, st);
+      { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p, hasamb.p); KERNEL_CHECK(); }
+      // rounds: a fixed HBM budget of per-alignment slabs; forward pass by persistent warps, backtrace by one thread per alignment.
+      // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
+      i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
+      const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64)); const u64 slab_bytes = (u64)lmax * 3 * WFS * 2;
+      size_t fb = 0, tb_ = 0; CUDA_CHECK(cudaMemGetInfo(&fb, &tb_)); const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30); const u32 nwarps = (u32)sm_count * 4 * WF_WARPS;
+      u32 per_round = (u32)std::min<u64>(nj, std::max<u64>(nwarps, budgetF / slab_bytes)); if (per_round > nwarps) per_round = per_round / nwarps * nwarps; if (g_arena == nullptr) per_round = std::min<u32>(per_round, 2048);
+      DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
+      { KTimer kt(st, &ms[11]);
+        for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (n + WF_WARPS - 1) / WF_WARPS);
+          k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
+          k_wfa_bt<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
+      counters[14] = per_round; counters[15] = (u64)lmax;
       std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
       counters[9] = nj; counters[10] = ids.size(); }
     size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
@@ -918,7 +993,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
       if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
       DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
-      { KTimer kt(st, &ms[12]); k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); } counters[11] += n;
+      { KTimer kt(st, &ms[10]); k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); } counters[11] += n;
       std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
       ids.swap(again); slab_words *= 8;
     }
@@ -948,25 +1023,27 @@ struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u3
 
 static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
+  auto hw0 = std::chrono::steady_clock::now(); static const bool dbgt = getenv("LMG_DEBUG_TIMING") != nullptr; auto lap = [&](const char* what) { if (dbgt) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host] %-18s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - hw0).count()); hw0 = n; } };
   QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
-  sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); T.mark();   // [1] sketch
-  Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); T.mark();              // [2] probe
-  Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); T.mark();                // [3] chain
+  lap("upload"); sketch_tables(ix, B); if (dbgt) cudaStreamSynchronize(st); lap("sketch tables"); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); if (dbgt) cudaStreamSynchronize(st); lap("capture"); T.mark();   // [1] sketch
+  Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); if (dbgt) cudaStreamSynchronize(st); lap("probe+anchor sort"); T.mark();              // [2] probe
+  Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); lap("chain stage"); T.mark();                // [3] chain
   for (int i = 0; i < 16; i++) if (i != 8 && i != 9) ix->ms[i] = 0; ix->counters[11] = 0;
   auto finish_times = [&](int upto) { const int map_[6] = {0, 1, 2, 3, 4, 5}; (void)map_; CUDA_CHECK(cudaStreamSynchronize(st)); for (int i = 0; i < upto; i++) ix->ms[i] = T.ms(i, i + 1); ix->ms[7] = T.ms(0, upto); ix->counters[6] = B.total_bases; ix->counters[7] = (u64)B.nq; };
   if (Cn.n == 0) { T.mark(); finish_times(4); return; }
   // ---- windows (lib-index-search.go:1987-2051)
   const int K = I.k, extLen = prm->ext_len; std::vector<WinItem> items(Cn.n);
-  for (u32 c = 0; c < Cn.n; c++) { const ChainRec& r = Cn.h[c]; u64 key = S.h_key[r.seg]; WinItem w; w.q = (u32)(key >> 36); w.g = (u32)((key >> 2) & 0x3FFFFFFFFull); w.chain = c;
+#pragma omp parallel for schedule(static) num_threads(std::max(1, std::min(16, omp_get_max_threads())))
+  for (i64 c = 0; c < (i64)Cn.n; c++) { const ChainRec& r = Cn.h[c]; u64 key = S.h_key[r.seg]; WinItem w; w.q = (u32)(key >> 36); w.g = (u32)((key >> 2) & 0x3FFFFFFFFull); w.chain = (u32)c;
     i32 qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); i32 qb = r.q0, tb = r.t0, qe = r.q1 + r.len1 - 1, te = r.t1 + r.len1 - 1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1;
     bool rc = (r.nseeds == 1) ? (qrc != trc) : (tb > r.t1); i32 tBegin, tEnd;
     if (rc) { tBegin = r.t1 - extLen; if (tBegin < 0) tBegin = 0; tEnd = tb + r.len1 - 1 + extLen; } else { tBegin = tb - extLen; if (tBegin < 0) tBegin = 0; tEnd = te + extLen; }
     w.qBegin = qb - std::min(qb, extLen); w.qEnd = qe + std::min(qlen - qe - 1, extLen);
-    i32 nBases = (i32)I.seq_sizes[w.g].size() ? 0 : 0; (void)nBases; i32 nb = 0; { const auto& ss = I.seq_sizes[w.g]; i64 t = 0; for (size_t x = 0; x < ss.size(); x++) t += ss[x]; t += (i64)(ss.size() - 1) * I.contig_interval; nb = (i32)t; }
+    i32 nb = (i32)I.h_nbases[w.g];
     i32 start = std::max(tBegin, 0), end = tEnd; if (end >= nb - 1) end = nb - 1; if (end < start) end = start; i32 sl = end - start + 1; if (sl < tEnd - tBegin + 1) tEnd -= tEnd - tBegin + 1 - sl;   // SubSeq3 clamp + :2045-2047
     w.tBegin = tBegin; w.tEnd = tEnd; w.W = sl; w.rc = rc; w.mp = 11 + (sl >= 1000000 ? 8 : sl >= 250000 ? 6 : sl >= 50000 ? 4 : sl >= 10000 ? 2 : 0); items[c] = w; }
   u32 nit = Cn.n; DBuf<WinItem> d_items(nit, st); d_items.from_host(items.data(), nit);
-  DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff);
+  lap("windows host"); DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff); lap("tree tables");
   // ---- K4 anchors: per-query prefix hash, one pass into capacity-bounded regions (exact rerun for the rare overflow), per-window sort
   std::vector<u32> htoff = toff.to_host(B.nq + 1); std::vector<u64> hhoff(B.nq + 1, 0); for (int q = 0; q < B.nq; q++) { u32 n = htoff[q + 1] - htoff[q]; u64 H = 0; if (n) { H = 16; while (H < 2ull * n) H <<= 1; } hhoff[q + 1] = hhoff[q] + H; }
   // queries -> item ranges (items are ordered by (query, genome)); per-query kernel when table + window fit in shared memory
@@ -984,6 +1061,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
   DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
   if (!qlist.empty()) CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  lap("k4 host prep");
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than 2*W+256: capacities become the exact counts
     for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
     if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
@@ -993,25 +1071,28 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
       if (!rest.empty()) { k_pa_anchors2<<<(u32)rest.size(), 128, smemW, st>>>(d_items.p, d_rest.p, (u32)rest.size(), I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); } }
     hcnt = cnt.to_host(nit); bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
     if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
+  lap("pa_anchors");
   std::vector<C2Rec> c2;
   if (NA > 0) {
-    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); DBuf<u64> lo1(habeg[nit] + 2, st);
-    { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, aend.p, st); CUB_CHECK(); }
+    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); bool anyLarge = false; std::vector<u64> hbigend(nit); for (u32 i = 0; i < nit; i++) { bool big = hcnt[i] > PA_SORT_MAX; anyLarge |= big; hbigend[i] = big ? haend[i] : habeg[i]; }
+    DBuf<u64> lo1(anyLarge ? habeg[nit] + 2 : 2, st);
+    if (anyLarge) { DBuf<u64> bigend(nit, st); bigend.from_host(hbigend.data(), nit); size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, bigend.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, bigend.p, st); CUB_CHECK(); }
+    if (dbgt) cudaStreamSynchronize(st); lap("k4 seg sort");
     Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
     DBuf<i32> sc(habeg[nit], st); DBuf<u32> pred(habeg[nit], st); DBuf<u64> stack(habeg[nit], st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
-    { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
+    if (PA_SORT_MAX > 0) CUDA_CHECK(cudaFuncSetAttribute(k_pa_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PA_SORT_MAX * 8));
+    { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 4 * PA_SORT_MAX * 8, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
     u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
-    bucket_sort(c2, nit, [](const C2Rec& a) { return a.item; }, [](const C2Rec& a, const C2Rec& b) { if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
+    lap("pa_chain+d2h"); bucket_sort(c2, nit, [](const C2Rec& a) { return a.item; }, [](const C2Rec& a, const C2Rec& b) { if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
-  tkeys.free(); tvals.free(); T.mark();                                                                  // [4] pseudo-align
+  lap("c2 bucket sort"); tkeys.free(); tvals.free(); T.mark();                                                                  // [4] pseudo-align
   if (c2.empty()) { T.mark(); finish_times(5); return; }
-  auto hw0 = std::chrono::steady_clock::now(); static const bool dbgt = getenv("LMG_DEBUG_TIMING") != nullptr; auto lap = [&](const char* what) { if (dbgt) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host] %-18s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - hw0).count()); hw0 = n; } };
   // ---- contig mapping, clusters, jobs (lib-index-search.go:2083-2469) — host, sequential per (query, genome)
   std::vector<HostCluster> clusters; std::vector<HspJob> jobs; const int contigInterval = I.contig_interval;
   { // segments (query, genome) are independent: process them in parallel, concatenate in order
     std::vector<std::pair<u32, u32>> segs; { u32 c = 0; while (c < nit) { u32 seg = Cn.h[c].seg, e = c; while (e < nit && Cn.h[e].seg == seg) e++; segs.push_back({c, e}); c = e; } }
     std::vector<size_t> c2beg(nit + 1, c2.size()); { size_t x = c2.size(); for (i64 it = (i64)nit - 1; it >= 0; it--) { while (x > 0 && c2[x - 1].item >= (u32)it) x--; c2beg[it] = x; } }
-    const int NT = std::max(1, std::min(16, omp_get_max_threads())); std::vector<std::vector<HostCluster>> segCl(NT); std::vector<std::vector<HspJob>> segJobs(NT);
+    const int NT = std::max(1, std::min(32, omp_get_max_threads())); std::vector<std::vector<HostCluster>> segCl(NT); std::vector<std::vector<HspJob>> segJobs(NT);
 #pragma omp parallel for schedule(static, 1) num_threads(NT)
     for (int ti = 0; ti < NT; ti++) { std::vector<HostCluster>& clusters_l = segCl[ti]; std::vector<HspJob>& jobs_l = segJobs[ti]; size_t s0 = segs.size() * ti / NT, s1 = segs.size() * (ti + 1) / NT; std::vector<std::array<int, 6>> keys;
      for (size_t si = s0; si < s1; si++) { u32 c = segs[si].first, cEnd = segs[si].second, seg = Cn.h[c].seg;
@@ -1073,7 +1154,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   lap("score clusters");
   // group clusters per segment -> genomes -> queries; whole queries are independent, so static chunks of queries run in parallel
   struct GenomeOut { u32 seg; std::vector<const HostCluster*> sds; double af; };
-  const int NTF = std::max(1, std::min(16, omp_get_max_threads())); std::vector<size_t> cut(NTF + 1, clusters.size()); cut[0] = 0;
+  const int NTF = std::max(1, std::min(32, omp_get_max_threads())); std::vector<size_t> cut(NTF + 1, clusters.size()); cut[0] = 0;
   for (int t = 1; t < NTF; t++) { size_t x = clusters.size() * t / NTF; while (x > 0 && x < clusters.size() && (u32)(S.h_key[clusters[x].seg] >> 36) == (u32)(S.h_key[clusters[x - 1].seg] >> 36)) x++; cut[t] = std::max(x, cut[t - 1]); }
   std::vector<std::vector<lmg_hsp>> trows(NTF); std::vector<std::string> tpool(NTF); std::vector<std::vector<u32>> trg(NTF);
 #pragma omp parallel for schedule(static, 1) num_threads(NTF)

@@ -109,3 +109,27 @@ def test_search_exact_wfa_matches_oracle(gpu_small, oracle_small, small_queries)
     gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1, wfa_adaptive=0))
     orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1, wfa_adaptive=0))
     _rows_equal(gr, orr, gs, os_, gc, oc)
+
+
+@pytest.fixture(scope="module")
+def long_case(workdir):
+    """longer queries: 3-kb and 12-kb reads (12 kb: k-mer table > 200 KB -> L2 pseudo-alignment kernel, windows >= 10 kb -> min prefix 13)
+    against a 2 x 3 x 150-kb index; divergent enough that some alignments leave the fast WFA kernel."""
+    from conftest import make_index, make_queries
+    from oracle_binding import Oracle, read_fasta
+    import lexicmap_b200
+    idx = make_index(workdir, "longcase", "2,3,150000,11,2")
+    _, s3 = read_fasta(make_queries(workdir, idx, "long_q3k", 6, 3000, seed=5))
+    _, s12 = read_fasta(make_queries(workdir, idx, "long_q12k", 3, 12000, seed=6, max_sub=0.06, max_indel=0.02))
+    _, s20 = read_fasta(make_queries(workdir, idx, "long_q20k", 1, 20000, seed=7, max_sub=0.02, max_indel=0.005))
+    return lexicmap_b200.Index(idx, device=0), Oracle(idx), s3 + s12 + s20
+
+
+def test_long_queries_match_oracle(long_case):
+    g, o, seqs = long_case
+    gr, gs, gc = g.search(seqs, g.default_params(output_seq=1))
+    orr, os_, oc = o.search(seqs, o.default_params(output_seq=1), threads=8)
+    assert len(orr) > 10
+    _rows_equal(gr, orr, gs, os_, gc, oc)
+    ga, oa = g.anchors(seqs), o.anchors(seqs)
+    assert ga.tobytes() == oa.tobytes()
