@@ -18,6 +18,13 @@ data-path collective; one NCCL all-reduce of the per-rank hit/row counters at th
 import argparse
 import json
 import os
+
+# torchrun exports OMP_NUM_THREADS=1; the host side of the library (and the index builder) use OpenMP for list handling, so give every
+# rank its share of the cores before any OpenMP runtime is loaded
+_world = int(os.environ.get("WORLD_SIZE", 1))
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, _world)))
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 import subprocess
 import sys
 import threading
@@ -145,6 +152,8 @@ def main():
     import lexicmap_b200
     from lexicmap_b200.api import pack_queries
     dist = None
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)   # libraries (NCCL banner) must not pollute the one JSON line on stdout
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -211,6 +220,7 @@ def main():
     rows_all, bp_all, t_val, t_e2e = (float(x) for x in hits.tolist())
     if rank != 0:
         idx.free_staged(staged)
+        dist.destroy_process_group()
         return
     # ---- roofline of the seed-lookup kernel: statistics pass (untimed) on the same batch
     idx.anchors(seqs[:2000])
@@ -240,8 +250,12 @@ def main():
                      "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep+general", 10), ("wfa_fwd+bt", 11), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
                      "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_filter_us": int(kcnt[12]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14]), "wfa_lmax": int(kcnt[15])},
            "clocks": sampler.summary()}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
     idx.free_staged(staged)
+    if dist:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -363,17 +363,22 @@ __global__ void __launch_bounds__(128) k_clear_chain(const u64* __restrict__ lo_
 struct ChainRec { u32 seg, ord; i32 q0, t0, len0, q1, t1, len1; u32 flags1; i32 nseeds; float score; u32 pad; };  // flags1: bit1 qrc, bit0 trc of the LAST anchor
 
 // one thread per segment: backtrack (lib-chaining.go:490-629). s2i_sorted ascending within the segment.
-__global__ void k_backtrack(const u64* __restrict__ seg_off, const u32* __restrict__ c_n, u32 nseg, const u64* __restrict__ c_lo, const u32* __restrict__ pred, const signed char* __restrict__ dirs,
+#define BT_SMALL 96   // segments up to this many anchors walk their (score,index) keys by repeated selection; larger ones use the CUB-sorted copy
+__global__ void k_seg_end(const u64* __restrict__ seg_off, const u32* __restrict__ c_n, u32 nseg, u64* __restrict__ seg_end) { u32 s = blockIdx.x * blockDim.x + threadIdx.x; if (s < nseg) seg_end[s] = seg_off[s] + (c_n[s] > BT_SMALL ? c_n[s] : 0); }
+__global__ void k_widen(const u32* __restrict__ a, u32 n, u64* __restrict__ o) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i <= n) o[i] = (i < n) ? a[i] : 0; }
+__global__ void k_backtrack(const u64* __restrict__ seg_off, const u32* __restrict__ c_n, u32 nseg, const u64* __restrict__ c_lo, const u32* __restrict__ pred, const signed char* __restrict__ dirs, const u64* __restrict__ s2i_unsorted,
                             const u64* __restrict__ s2i_sorted, u8* __restrict__ visited, ChainParams P, ChainRec* __restrict__ out, u32* __restrict__ nout, u32 cap, float* __restrict__ seg_score) {
-  u32 seg = blockIdx.x * blockDim.x + threadIdx.x; if (seg >= nseg) return; u64 b = seg_off[seg]; i32 n = (i32)c_n[seg]; const u64* C = c_lo + b; const u32* Pd = pred + b; const signed char* D = dirs + b; const u64* K2 = s2i_sorted + b; u8* V = visited + b;
+  u32 seg = blockIdx.x * blockDim.x + threadIdx.x; if (seg >= nseg) return; u64 b = seg_off[seg]; i32 n = (i32)c_n[seg]; const u64* C = c_lo + b; const u32* Pd = pred + b; const signed char* D = dirs + b; const u64* K2 = s2i_sorted + b; const u64* KU = s2i_unsorted + b; u8* V = visited + b; const bool small = n <= BT_SMALL;
   u32 ord = 0;
   auto emit = [&](i32 first, i32 last, i32 cnt, float sc) { u32 w = atomicAdd(nout, 1u); if (w < cap) { ChainRec r; r.seg = seg; r.ord = ord; u64 f = C[first], l = C[last]; r.q0 = a_q(f); r.t0 = a_t(f); r.len0 = a_len(f); r.q1 = a_q(l); r.t1 = a_t(l); r.len1 = a_len(l); r.flags1 = (u32)(l & 3); r.nseeds = cnt; r.score = sc; r.pad = 0; out[w] = r; } ord++; };
-  if (n == 1) { float w = __uint_as_float((u32)(K2[0] >> 32)); seg_score[seg] = w; if (w >= P.min_score) emit(0, 0, 1, w); return; }
-  i32 iMax = n - 1; float maxScore = 0; bool first = true; int nChecked = 0;
+  if (n == 1) { float w = __uint_as_float((u32)(KU[0] >> 32)); seg_score[seg] = w; if (w >= P.min_score) emit(0, 0, 1, w); return; }
+  i32 iMax = n - 1; float maxScore = 0; bool first = true; int nChecked = 0; u64 last = ~0ull; bool exhausted = false;
   for (;;) {
     nChecked++; if (P.top_chains > 0 && nChecked > P.top_chains) break;
     float M = 0; u32 Mi = 0;
-    while (iMax >= 0) { u64 e = K2[iMax]; M = __uint_as_float((u32)(e >> 32)); Mi = (u32)e; if (!V[Mi]) { iMax--; break; } iMax--; }
+    if (!small) { while (iMax >= 0) { u64 e = K2[iMax]; M = __uint_as_float((u32)(e >> 32)); Mi = (u32)e; if (!V[Mi]) { iMax--; break; } iMax--; } }
+    else { while (!exhausted) { u64 best = 0; bool f = false; for (i32 x = 0; x < n; x++) { u64 e = KU[x]; if (e < last && (!f || e > best)) { best = e; f = true; } } if (!f) { exhausted = true; break; }
+        last = best; M = __uint_as_float((u32)(best >> 32)); Mi = (u32)best; if (!V[Mi]) break; } }   // keys are distinct (index in the low word): descending walk == the sorted order
     if (M < P.min_score) break;
     i32 i = (i32)Mi; if (first) { maxScore = M; first = false; }
     i32 cnt = 0, lastA = -1, firstA = -1;
@@ -401,8 +406,7 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   DBuf<u64> ukey(N, st); DBuf<u32> cnt(N + 1, st); DBuf<u32> nruns(1, st);
   { size_t tb = 0; cub::DeviceRunLengthEncode::Encode(nullptr, tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); cub::DeviceRunLengthEncode::Encode(ix->tmp.get(tb), tb, A.hi.p, ukey.p, cnt.p, nruns.p, (int)N, st); CUB_CHECK(); }
   u32 nseg = nruns.to_host()[0]; S.nseg = nseg; S.off.alloc(nseg + 1, st);
-  { DBuf<u64> c64(nseg + 1, st); struct Dummy {}; // widen counts
-    std::vector<u32> hc = cnt.to_host(nseg); S.h_off.assign(nseg + 1, 0); for (u32 i = 0; i < nseg; i++) S.h_off[i + 1] = S.h_off[i] + hc[i]; S.off.from_host(S.h_off.data(), nseg + 1); }
+  { DBuf<u64> c64(nseg + 1, st); k_widen<<<cdiv(nseg + 1, 256), 256, 0, st>>>(cnt.p, nseg, c64.p); KERNEL_CHECK(); size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, c64.p, S.off.p, (int)(nseg + 1), st); cub::DeviceScan::ExclusiveSum(ix->tmp.get(tb), tb, c64.p, S.off.p, (int)(nseg + 1), st); CUB_CHECK(); }
   S.h_key = ukey.to_host(nseg); S.key = std::move(ukey);
   // gap-score table on the host (gapScore lib-chaining.go:662: 0.1*g + 0.5*float32(log2(float64(g))), g integer <= max_gap)
   int gt = std::max(2, (int)std::floor(prm->max_gap) + 2); std::vector<float> gtab(gt, 0.0f);
@@ -412,11 +416,10 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   S.c_lo.alloc(N, st); S.cn.alloc(nseg, st); S.score.alloc(nseg, st); DBuf<float> sc(N, st); DBuf<u32> pred(N, st); DBuf<signed char> dirs(N, st); DBuf<u64> s2i(N, st), s2i_s(N, st); DBuf<u8> visited(N, st); visited.zero();
   k_clear_chain<<<cdiv((i64)nseg * 32, 128), 128, 0, st>>>(A.lo.p, S.off.p, nseg, P, S.c_lo.p, S.cn.p, sc.p, pred.p, dirs.p, s2i.p); KERNEL_CHECK();
   // per-segment ascending sort of (score bits << 32 | index) over the compacted prefix of each segment
-  DBuf<u64> seg_end(nseg, st);
-  { std::vector<u32> hcn = S.cn.to_host(nseg); std::vector<u64> he(nseg); for (u32 i = 0; i < nseg; i++) he[i] = S.h_off[i] + hcn[i]; seg_end.from_host(he.data(), nseg); CUDA_CHECK(cudaStreamSynchronize(st)); }
+  DBuf<u64> seg_end(nseg, st); k_seg_end<<<cdiv(nseg, 256), 256, 0, st>>>(S.off.p, S.cn.p, nseg, seg_end.p); KERNEL_CHECK();
   { size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, s2i.p, s2i_s.p, (int)N, (int)nseg, S.off.p, seg_end.p, st); CUB_CHECK(); }
   u32 cap = (u32)std::min<u64>(N + nseg, 0x7fffffffu); Cn.rec.alloc(cap, st); DBuf<u32> nout(1, st); nout.zero();
-  k_backtrack<<<cdiv(nseg, 128), 128, 0, st>>>(S.off.p, S.cn.p, nseg, S.c_lo.p, pred.p, dirs.p, s2i_s.p, visited.p, P, Cn.rec.p, nout.p, cap, S.score.p); KERNEL_CHECK();
+  k_backtrack<<<cdiv(nseg, 128), 128, 0, st>>>(S.off.p, S.cn.p, nseg, S.c_lo.p, pred.p, dirs.p, s2i.p, s2i_s.p, visited.p, P, Cn.rec.p, nout.p, cap, S.score.p); KERNEL_CHECK();
   u32 nc = nout.to_host()[0]; if (nc > cap) throw std::runtime_error("chain list overflow"); Cn.n = nc; Cn.seg_score = S.score.to_host(nseg);
   Cn.h = Cn.rec.to_host(nc);
   // drop genomes below min score (:1724), optional top-N genomes per query (:1780-1805), order chains by (segment, first TBegin, emission order) (:1967-1974)
