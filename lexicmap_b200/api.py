@@ -14,7 +14,7 @@ class Params(C.Structure):  # lmg_params
                 ("max_gap", C.c_float), ("max_distance", C.c_float), ("ext_len", C.c_int32), ("ext_len2", C.c_int32),
                 ("min_qcov_genome", C.c_double), ("max_evalue", C.c_double),
                 ("align_max_gap", C.c_int32), ("align_min_len", C.c_int32), ("align_band", C.c_int32), ("output_seq", C.c_int32),
-                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double), ("wfa_adaptive", C.c_int32), ("reserved", C.c_int32)]
+                ("min_pident", C.c_double), ("min_qcov_hsp", C.c_double), ("wfa_adaptive", C.c_int32), ("lanes", C.c_int32)]
 
 
 class Info(C.Structure):  # lmg_info

@@ -8,7 +8,7 @@
 #include <vector>
 #include <algorithm>
 
-typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int64_t i64;
+typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int16_t i16; typedef int32_t i32; typedef int64_t i64;
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(e_) + " at " __FILE__ ":" + std::to_string(__LINE__)); } while (0)
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())

@@ -18,6 +18,8 @@
 #include <numeric>
 #include <chrono>
 #include <mutex>
+#include <atomic>
+#include <thread>
 #include <set>
 #include <array>
 
@@ -25,7 +27,7 @@
 // small device utilities
 // =====================================================================================================
 #define FULLMASK 0xffffffffu
-static unsigned long long g_launches = 0;   // kernels of THIS library launched (CUB's internal kernels are not counted)
+static std::atomic<unsigned long long> g_launches{0};   // kernels of THIS library launched (CUB's internal kernels are not counted)
 #undef KERNEL_CHECK
 #define KERNEL_CHECK() do { g_launches++; CUDA_CHECK(cudaGetLastError()); } while (0)
 #define CUB_CHECK() CUDA_CHECK(cudaGetLastError())
@@ -209,12 +211,20 @@ struct QBatch {  // device-side query batch
   DBuf<u64> qkeys; DBuf<u32> qvals;    // per-query sorted (k-mer, loc) tables
 };
 
+// One search context: the shared HBM image plus this context's stream, arena, scratch and timers. The handle returned by lmg_index_open
+// is lane 0 and owns the image; further lanes (same image, own stream/arena) are created on demand so that big batches can be split into
+// sub-batches whose host phases (window geometry, contig mapping, scoring) overlap the other sub-batch's kernels.
 struct lmg_index {
-  Image img; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena;
+  Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
+  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0;
+  lmg_index(Image* p, bool own) : imgp(p), img(*p), owner(own) {}
 };
 
 static thread_local std::string g_err;
+// host-side lap timer (LMG_DEBUG_TIMING=1): prints the wall time since the previous lap of the calling thread
+struct LapTimer { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); bool on = getenv("LMG_DEBUG_TIMING") != nullptr; int lane = 0;
+  void operator()(const char* what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host L%d] %-18s %.2f ms\n", lane, what, std::chrono::duration<double, std::milli>(n - t0).count()); t0 = n; } };
+static thread_local LapTimer* g_lap = nullptr;
 struct KTimer { cudaEvent_t a, b; cudaStream_t st; double* dst; KTimer(cudaStream_t s, double* d) : st(s), dst(d) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); } ~KTimer() { cudaEventRecord(b, st); cudaEventSynchronize(b); float f = 0; cudaEventElapsedTime(&f, a, b); *dst += f; cudaEventDestroy(a); cudaEventDestroy(b); } };
 // activates the index's arena for the calling thread and rewinds it when the batch is done (all DBufs of the batch are dead by then)
 struct ArenaReset { lmg_index* ix; ArenaScope sc; ArenaReset(lmg_index* i) : ix(i), sc(&i->arena) {} ~ArenaReset() { cudaStreamSynchronize(ix->st); ix->arena.reset(); } };
@@ -249,7 +259,6 @@ static void sketch_capture(lmg_index* ix, QBatch& B, CapBufs& cap, DBuf<u32>& ow
   u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
   u32 smem_cap = (u32)std::min<u64>((ix->smem_optin - 1024) / 8, 24576);  // entries
   u32 need = (u32)std::min<u64>(maxn, smem_cap); size_t smem = ((size_t)need * 8 + 15) & ~15ull;
-  CUDA_CHECK(cudaFuncSetAttribute(k_capture, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 16)));
   // slices: enough CTAs to fill 148 SMs a few times over, but keep >= 1024 masks per CTA so the staged table is reused
   int slices = std::max(1, std::min(I.m / 1024, cdiv(ix->sm_count * 8, std::max(1, B.nq))));
   k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap.soa(), owner.p, need, ix->use_tma, I.d_mask_pstart, I.mask_pbits); KERNEL_CHECK();
@@ -602,21 +611,30 @@ __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__
 struct C2Rec { u32 item, ord; i32 qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors; };
 struct Chain2Params { int max_gap, min_score, min_align_len, band_count, band_base, k; };
 
-// one warp per window: nested-anchor removal, trimming, banded chaining DP, region splitting. Scalar control flow is executed
-// redundantly by all lanes (uniform); the DP inner loop and arg-max scans are lane-parallel.
-#define PA_SORT_MAX 0   // in-kernel warp bitonic sort measured slower than CUB's segmented sort at 64 KB smem / CTA (occupancy); 0 = always CUB
-// lo_sorted: output of the CUB segmented sort (only used by windows with more than PA_SORT_MAX anchors); smaller windows sort their
-// anchors right here with a warp-level bitonic network in shared memory, reading the unsorted anchors from c_lo (which is then reused
-// as the compacted output, as before).
-__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_sorted, const u64* __restrict__ abeg, const u64* __restrict__ aend, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
-                                                  C2Rec* __restrict__ out, u32* __restrict__ nout, u32 cap) {
+// Per-window anchor sort (the order ClearSubstrPairs / Chainer2 need: ascending packed key). Windows are binned by anchor count on the host;
+// each bin runs a shared-memory bitonic network sized to the bin (TPW threads per window), only the rare huge window goes through CUB.
+template <int CAP, int TPW>
+__global__ void __launch_bounds__(TPW < 128 ? 128 : TPW) k_pa_sort(const u32* __restrict__ list, u32 nlist, const u64* __restrict__ abeg, const u64* __restrict__ cbeg, const u32* __restrict__ counts, const u64* __restrict__ in, u64* __restrict__ out) {
   extern __shared__ u64 ssort[];
+  const u32 wpc = blockDim.x / TPW, sub = threadIdx.x / TPW, t0 = threadIdx.x % TPW; u32 li = blockIdx.x * wpc + sub; bool live = li < nlist;
+  u64* sm = ssort + (size_t)sub * CAP; u32 it = live ? list[li] : 0; u32 n = live ? counts[it] : 0; u64 b = live ? abeg[it] : 0, cb = live ? cbeg[it] : 0; u32 Pn = 2; while (Pn < n) Pn <<= 1;
+  auto sync = [&]() { if (TPW == 32) __syncwarp(); else __syncthreads(); };
+  for (u32 i = t0; i < Pn; i += TPW) sm[i] = (i < n) ? in[b + i] : ~0ull; sync();
+  for (u32 kk = 2; kk <= Pn; kk <<= 1) for (u32 j = kk >> 1; j > 0; j >>= 1) { for (u32 t = t0; t < (Pn >> 1); t += TPW) { u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j; bool up = (i & kk) == 0; u64 x = sm[i], y = sm[l]; if ((x > y) == up) { sm[i] = y; sm[l] = x; } } sync(); }
+  for (u32 i = t0; i < n; i += TPW) out[cb + i] = sm[i];
+}
+// windows too large for the shared-memory sort: copy their anchors to the compact layout, CUB sorts them there
+__global__ void k_pa_gather(const u32* __restrict__ list, u32 nlist, const u64* __restrict__ abeg, const u64* __restrict__ cbeg, const u32* __restrict__ counts, const u64* __restrict__ in, u64* __restrict__ out) {
+  if (blockIdx.x >= nlist) return; u32 it = list[blockIdx.x]; u32 n = counts[it]; u64 b = abeg[it], cb = cbeg[it]; for (u32 i = threadIdx.x; i < n; i += blockDim.x) out[cb + i] = in[b + i];
+}
+
+// one warp per window: nested-anchor removal, trimming, banded chaining DP, region splitting. Scalar control flow is executed
+// redundantly by all lanes (uniform); the DP inner loop and arg-max scans are lane-parallel. lo_sorted holds each window's anchors sorted;
+// c_lo (the unsorted copy) is reused as the compacted output.
+__global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_sorted, const u64* __restrict__ abeg, const u64* __restrict__ aend, const u64* __restrict__ cbeg, u32 nitems, Chain2Params P, u64* __restrict__ c_lo, i32* __restrict__ score, u32* __restrict__ pred, u64* __restrict__ stack,
+                                                  C2Rec* __restrict__ out, u32* __restrict__ nout, u32 cap) {
   u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31; if (it >= nitems) return;
-  u64 b = abeg[it]; u32 n = (u32)(aend[it] - b); if (n == 0) return; u64* C = c_lo + b; const u64* A = lo_sorted + b; const int k = P.k;
-  if (PA_SORT_MAX > 0 && n <= PA_SORT_MAX) { u64* sm = ssort + (threadIdx.x >> 5) * PA_SORT_MAX; u32 Pn = 32; while (Pn < n) Pn <<= 1;
-    for (u32 i = lane; i < Pn; i += 32) sm[i] = (i < n) ? C[i] : ~0ull; __syncwarp();
-    for (u32 kk = 2; kk <= Pn; kk <<= 1) for (u32 j = kk >> 1; j > 0; j >>= 1) { for (u32 t = lane; t < (Pn >> 1); t += 32) { u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j; bool up = (i & kk) == 0; u64 x = sm[i], y = sm[l]; if ((x > y) == up) { sm[i] = y; sm[l] = x; } } __syncwarp(); }
-    A = sm; }
+  u64 b = abeg[it]; u32 n = (u32)(aend[it] - b); if (n == 0) return; u64* C = c_lo + b; b = cbeg[it]; const u64* A = lo_sorted + b; const int k = P.k;   // from here on b indexes the compact arrays
   // ---- ClearSubstrPairs
   if (n > 1) { u32 kept = 0;
     for (u32 base = 0; base < n; base += 32) { u32 i = base + lane; bool keep = false;
@@ -709,19 +727,26 @@ __device__ u32 ext_count(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n
   p = tbase(v, ta); for (i32 i = 1; i < n2; i++) { u32 c = tbase(v, ta + dt * i); u32 m = (p << 2) | c; if (m < 8) b0 += 1ull << (8 * m); else b1 += 1ull << (8 * (m - 8)); p = c; }
   u32 t = 0; for (int i = 0; i < 8; i++) { t += (u32)((a0 >> (8 * i)) & 255) * (u32)((b0 >> (8 * i)) & 255) + (u32)((a1 >> (8 * i)) & 255) * (u32)((b1 >> (8 * i)) & 255); } return t;
 }
-// _extendRight: anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10, BandCount 20), best chain end + 1
-__device__ void ext_run(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i32* __restrict__ sc, u16* __restrict__ pj, i32* e1, i32* e2) {
+// _extendRight: anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10, BandCount 20), best chain end + 1.
+// The per-thread scratch arrays are interleaved across the warp (element i of lane l at [i*32 + l]): lanes walk their lists in lockstep, so
+// the warp's loads/stores of element i (and of element j in the inner loop) fall into the same few sectors instead of 32 separate ones.
+#define EXI(a, i) (a)[(size_t)(i) << 5]
+__device__ void ext_run(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, i32* e1, i32* e2) {
   *e1 = *e2 = 0; if (n1 < 2 || n2 < 2) return; u32 n = 0;
-  for (i32 i1 = 0; i1 + 1 < n1; i1++) { u32 c = (qbase(v, qa + dq * i1) << 2) | qbase(v, qa + dq * (i1 + 1)); for (i32 i2 = 0; i2 + 1 < n2; i2++) if (((tbase(v, ta + dt * i2) << 2) | tbase(v, ta + dt * (i2 + 1))) == c) anc[n++] = (u16)((i1 << 8) | i2); }
+  { // positions of every target 2-mer as bit sets (flanks are at most 192 bases: checked on the host), then one pass over the query 2-mers
+    u64 Mk[16][3]; for (int c = 0; c < 16; c++) Mk[c][0] = Mk[c][1] = Mk[c][2] = 0;
+    u32 tp = tbase(v, ta); for (i32 i2 = 0; i2 + 1 < n2; i2++) { u32 tn = tbase(v, ta + dt * (i2 + 1)); Mk[(tp << 2) | tn][i2 >> 6] |= 1ull << (i2 & 63); tp = tn; }
+    u32 qp = qbase(v, qa); for (i32 i1 = 0; i1 + 1 < n1; i1++) { u32 qn = qbase(v, qa + dq * (i1 + 1)); u32 c = (qp << 2) | qn; qp = qn;
+      for (int w = 0; w < 3; w++) { u64 mk = Mk[c][w]; while (mk) { int b = __ffsll((long long)mk) - 1; mk &= mk - 1; EXI(anc, n) = (u16)((i1 << 8) | (w * 64 + b)); n++; } } } }
   if (n == 0) return;
   i32 M = 0; u32 Mi = 0;
-  for (u32 i = 0; i < n; i++) { i32 aq = anc[i] >> 8, at = anc[i] & 255; i32 m = 2 - max(aq, at) - abs(aq - at); u32 mj = i; i32 cnt = 0;   // Len - distance2(origin) - gap2(origin)
-    for (i32 j = (i32)i - 1; j >= 0; j--) { i32 bq = anc[j] >> 8, bt = anc[j] & 255; if (bq == aq || bt > at) continue; cnt++; if (!((aq - bq - 2) <= 10 || cnt <= 20)) break;
-      i32 d = max(abs(aq - bq), abs(at - bt)); if (d > 10) continue; i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > 5) continue; i32 s = sc[j] + 2 - d - g; if (s >= m) { m = s; mj = (u32)j; } }
-    sc[i] = m; pj[i] = (u16)mj; if (i >= 1 && m > M) { M = m; Mi = i; } }
+  for (u32 i = 0; i < n; i++) { u32 ai = EXI(anc, i); i32 aq = ai >> 8, at = ai & 255; i32 m = 2 - max(aq, at) - abs(aq - at); u32 mj = i; i32 cnt = 0;   // Len - distance2(origin) - gap2(origin)
+    for (i32 j = (i32)i - 1; j >= 0; j--) { u32 aj = EXI(anc, j); i32 bq = aj >> 8, bt = aj & 255; if (bq == aq || bt > at) continue; cnt++; if (!((aq - bq - 2) <= 10 || cnt <= 20)) break;
+      i32 d = max(abs(aq - bq), abs(at - bt)); if (d > 10) continue; i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > 5) continue; i32 s = (i32)EXI(sc, j) + 2 - d - g; if (s >= m) { m = s; mj = (u32)j; } }
+    EXI(sc, i) = (i16)m; EXI(pj, i) = (u16)mj; if (i >= 1 && m > M) { M = m; Mi = i; } }
   if (M < 1) return;
   i32 i = (i32)Mi, nMatched = 0, beginOfNext = 0, qb = 0, qe = 0, tb = 0, te = 0; bool firstA = true;
-  for (;;) { i32 j = pj[i]; i32 sq = anc[i] >> 8, stt = anc[i] & 255;
+  for (;;) { i32 j = EXI(pj, i); u32 ai = EXI(anc, i); i32 sq = ai >> 8, stt = ai & 255;
     if (firstA) { firstA = false; qe = sq + 1; te = stt + 1; qb = sq; tb = stt; nMatched += 2; } else { qb = sq; tb = stt; if (sq + 1 >= beginOfNext) nMatched += beginOfNext - sq; else nMatched += 2; }
     beginOfNext = sq;
     if (i == j) { i32 nAQ = qe - qb + 1; if (nAQ < 2) return; i32 nAT = te - tb + 1; double pid = (double)nMatched / (double)max(nAQ, nAT) * 100; if (pid < 15.0) return; *e1 = qe + 1; *e2 = te + 1; return; }
@@ -735,14 +760,14 @@ __device__ __forceinline__ void ext_sides(const HspJob& J, i32* rext, i32* lext)
 // one thread per (job, side). COUNT: scratch sizes; else run.
 template <bool COUNT>
 __global__ void k_extend(const HspJob* __restrict__ jobs, u32 njobs, const u8* __restrict__ qpacked, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
-                         u32* __restrict__ counts, const u64* __restrict__ soff, u16* __restrict__ anc, i32* __restrict__ sc, u16* __restrict__ pj, i32* __restrict__ res /*2 per (job,side)*/) {
+                         u32* __restrict__ counts, const u64* __restrict__ soff /*per warp*/, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, i32* __restrict__ res /*2 per (job,side)*/) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs * 2) return; u32 jb = t >> 1; int side = t & 1; HspJob J = jobs[jb];
   SeqView v; v.q2 = qpacked + qboff[J.q]; v.qm = nullptr; v.g2 = g2bit + g_off[J.g]; v.tBegin = J.tBegin; v.tEnd = J.tEnd; v.rc = J.rc;
   i32 rext, lext; ext_sides(J, &rext, &lext); i32 qa, n1, ta, n2; int d;
   if (side == 0) { if (!rext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } qa = J.end1; n1 = min(J.end1 + rext, J.qlen) - J.end1; ta = J.end2; n2 = min(J.end2 + rext, J.tlen) - J.end2; d = 1; }
   else { if (!lext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } i32 s1 = max(J.start1 - lext, 0), s2 = max(J.start2 - lext, 0); qa = J.start1 - 1; n1 = J.start1 - s1; ta = J.start2 - 1; n2 = J.start2 - s2; d = -1; }
   if (COUNT) { counts[t] = ext_count(v, qa, n1, d, ta, n2, d); }
-  else { u64 o = soff[t]; i32 e1, e2; ext_run(v, qa, n1, d, ta, n2, d, anc + o, sc + o, pj + o, &e1, &e2); res[2 * t] = e1; res[2 * t + 1] = e2; }
+  else { u64 o = soff[t >> 5] + (t & 31); i32 e1, e2; ext_run(v, qa, n1, d, ta, n2, d, anc + o, sc + o, pj + o, &e1, &e2); res[2 * t] = e1; res[2 * t + 1] = e2; }
 }
 __global__ void k_extend_final(const HspJob* __restrict__ jobs, u32 njobs, const i32* __restrict__ res, ExtOut* __restrict__ out) {
   u32 jb = blockIdx.x * blockDim.x + threadIdx.x; if (jb >= njobs) return; HspJob J = jobs[jb]; ExtOut o; o.e1 = res[4 * jb]; o.e2 = res[4 * jb + 1]; o.s1 = res[4 * jb + 2]; o.s2 = res[4 * jb + 3];
@@ -969,28 +994,28 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
 }
 
 static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
-                        int want_ops, int adaptive, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters, double* ms) {
+                        int want_ops, int adaptive, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters, double* ms, size_t total_mem, int active_lanes = 1) {
     // WFA: fast kernel (packed words + smem ring) for every job, then the general kernel for whatever did not fit
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
       DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st); DBuf<u32> hasamb(nj + 1, st);
-      { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p, hasamb.p); KERNEL_CHECK(); }
+      if (g_lap) (*g_lap)("wfa host prep"); { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p, hasamb.p); KERNEL_CHECK(); }
       // rounds: a fixed HBM budget of per-alignment slabs; forward pass by persistent warps, backtrace by one thread per alignment.
       // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
       i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
       const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64)); const u64 slab_bytes = (u64)lmax * 3 * WFS * 2;
-      size_t fb = 0, tb_ = 0; CUDA_CHECK(cudaMemGetInfo(&fb, &tb_)); const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30); const u32 nwarps = (u32)sm_count * 4 * WF_WARPS;
+      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30) / (u64)std::max(1, active_lanes); const u32 nwarps = (u32)sm_count * 4 * WF_WARPS;
       u32 per_round = (u32)std::min<u64>(nj, std::max<u64>(nwarps, budgetF / slab_bytes)); if (per_round > nwarps) per_round = per_round / nwarps * nwarps; if (g_arena == nullptr) per_round = std::min<u32>(per_round, 2048);
-      DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
+      if (g_lap) (*g_lap)("wfa prep kernel"); DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
       { KTimer kt(st, &ms[11]);
         for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (n + WF_WARPS - 1) / WF_WARPS);
           k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
           k_wfa_bt<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
-      counters[14] = per_round; counters[15] = (u64)lmax;
+      counters[14] = per_round; counters[15] = (u64)lmax; if (g_lap) (*g_lap)("wfa rounds");
       std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
-      counters[9] = nj; counters[10] = ids.size(); }
-    size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); u64 budget = (u64)(freeb * 0.6);
+      counters[9] = nj; counters[10] = ids.size(); if (g_lap) (*g_lap)("wfa d2h"); }
+    u64 budget = 0; if (!ids.empty()) { size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); budget = (u64)(freeb * 0.6); }
     u64 slab_words = 1ull << 20;  // 4 MB per warp to start
     for (int round = 0; round < 6 && !ids.empty(); round++) {
       u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
@@ -1026,9 +1051,10 @@ struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u3
 
 static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
-  auto hw0 = std::chrono::steady_clock::now(); static const bool dbgt = getenv("LMG_DEBUG_TIMING") != nullptr; auto lap = [&](const char* what) { if (dbgt) { auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host] %-18s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - hw0).count()); hw0 = n; } };
+  LapTimer lap; lap.lane = ix->lane_id; const bool dbgt = lap.on; struct LapScope { LapTimer* prev; LapScope(LapTimer* l) : prev(g_lap) { g_lap = l; } ~LapScope() { g_lap = prev; } } lapscope(&lap);
   QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
   lap("upload"); sketch_tables(ix, B); if (dbgt) cudaStreamSynchronize(st); lap("sketch tables"); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); if (dbgt) cudaStreamSynchronize(st); lap("capture"); T.mark();   // [1] sketch
+  if (prm->ext_len2 < 0 || prm->ext_len2 + 80 > 190) throw std::runtime_error("align-ext-len2 must be in [0, 110] for the GPU path (flank windows are held as 192-bit sets)");
   Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); if (dbgt) cudaStreamSynchronize(st); lap("probe+anchor sort"); T.mark();              // [2] probe
   Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); lap("chain stage"); T.mark();                // [3] chain
   for (int i = 0; i < 16; i++) if (i != 8 && i != 9) ix->ms[i] = 0; ix->counters[11] = 0;
@@ -1057,15 +1083,13 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   if (rest.empty()) std::fill(hhoff.begin(), hhoff.end(), 0);   // the L2-resident hash index is only needed by the fallback kernel
   DBuf<u64> hoff(B.nq + 1, st); hoff.from_host(hhoff.data(), B.nq + 1); DBuf<u64> htab(hhoff[B.nq] + 2, st); htab.fill_ff();
   if (!rest.empty()) { u32 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, htoff[q + 1] - htoff[q]); if (maxn) { dim3 g((unsigned)std::max(1, std::min(32, cdiv(maxn, 256))), B.nq); k_tree_hash_build<<<g, 256, 0, st>>>(tkeys.p, toff.p, hoff.p, B.nq, htab.p); KERNEL_CHECK(); } }
-  std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>(2ll * std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
+  std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>((i64)std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
   size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
-  CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smemW, 1024)));
   DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
   max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
   DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
-  if (!qlist.empty()) CUDA_CHECK(cudaFuncSetAttribute(k_pa_anchors3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
   lap("k4 host prep");
-  for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than 2*W+256: capacities become the exact counts
+  for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than W+226: capacities become the exact counts
     for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
     if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
@@ -1077,14 +1101,23 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   lap("pa_anchors");
   std::vector<C2Rec> c2;
   if (NA > 0) {
-    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); bool anyLarge = false; std::vector<u64> hbigend(nit); for (u32 i = 0; i < nit; i++) { bool big = hcnt[i] > PA_SORT_MAX; anyLarge |= big; hbigend[i] = big ? haend[i] : habeg[i]; }
-    DBuf<u64> lo1(anyLarge ? habeg[nit] + 2 : 2, st);
-    if (anyLarge) { DBuf<u64> bigend(nit, st); bigend.from_host(hbigend.data(), nit); size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, bigend.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, lo0.p, lo1.p, (int)habeg[nit], (int)nit, abeg.p, bigend.p, st); CUB_CHECK(); }
+    // compact layout for everything but the raw anchors: cbeg = exclusive prefix sum of the per-window counts
+    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); std::vector<u64> hcbeg(nit + 1, 0); std::vector<u32> bins[4];
+    for (u32 i = 0; i < nit; i++) { u32 c = hcnt[i]; hcbeg[i + 1] = hcbeg[i] + c; if (c) bins[c <= 64 ? 0 : c <= 512 ? 1 : c <= 4096 ? 2 : 3].push_back(i); }
+    DBuf<u64> cbeg(nit + 1, st); cbeg.from_host(hcbeg.data(), nit + 1); DBuf<u64> lo1(NA + 2, st);
+    { std::vector<u32> all; u32 boff[5] = {0, 0, 0, 0, 0}; for (int k3 = 0; k3 < 4; k3++) { all.insert(all.end(), bins[k3].begin(), bins[k3].end()); boff[k3 + 1] = (u32)all.size(); } DBuf<u32> dl(all.size() + 1, st); dl.from_host(all.data(), all.size());
+      if (boff[1] > boff[0]) { k_pa_sort<64, 32><<<cdiv(boff[1] - boff[0], 4), 128, 4 * 64 * 8, st>>>(dl.p + boff[0], boff[1] - boff[0], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[2] > boff[1]) { k_pa_sort<512, 128><<<boff[2] - boff[1], 128, 512 * 8, st>>>(dl.p + boff[1], boff[2] - boff[1], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[3] > boff[2]) { k_pa_sort<4096, 256><<<boff[3] - boff[2], 256, 4096 * 8, st>>>(dl.p + boff[2], boff[3] - boff[2], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[4] > boff[3]) {   // rare: > 4096 anchors in one window
+        std::vector<u64> hb(nit), he(nit); for (u32 i = 0; i < nit; i++) { hb[i] = hcbeg[i]; he[i] = hcnt[i] > 4096 ? hcbeg[i + 1] : hcbeg[i]; } DBuf<u64> sb(nit, st), se(nit, st), tmpc(NA + 2, st); sb.from_host(hb.data(), nit); se.from_host(he.data(), nit);
+        k_pa_gather<<<boff[4] - boff[3], 256, 0, st>>>(dl.p + boff[3], boff[4] - boff[3], abeg.p, cbeg.p, cnt.p, lo0.p, tmpc.p); KERNEL_CHECK();
+        size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, tmpc.p, lo1.p, (int)NA, (int)nit, sb.p, se.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, tmpc.p, lo1.p, (int)NA, (int)nit, sb.p, se.p, st); CUB_CHECK(); CUDA_CHECK(cudaStreamSynchronize(st)); }
+      if (dbgt) fprintf(stderr, "[lmg host] pa anchors %llu in %u windows (%.1f GB of slots): bins %zu / %zu / %zu / %zu\n", (unsigned long long)NA, nit, habeg[nit] * 8e-9, bins[0].size(), bins[1].size(), bins[2].size(), bins[3].size()); }
     if (dbgt) cudaStreamSynchronize(st); lap("k4 seg sort");
     Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
-    DBuf<i32> sc(habeg[nit], st); DBuf<u32> pred(habeg[nit], st); DBuf<u64> stack(habeg[nit], st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
-    if (PA_SORT_MAX > 0) CUDA_CHECK(cudaFuncSetAttribute(k_pa_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PA_SORT_MAX * 8));
-    { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 4 * PA_SORT_MAX * 8, st>>>(lo1.p, abeg.p, aend.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
+    DBuf<i32> sc(NA + 2, st); DBuf<u32> pred(NA + 2, st); DBuf<u64> stack(NA + 2, st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
+    { KTimer kt(st, &ix->ms[15]); k_pa_chain<<<cdiv((i64)nit * 32, 128), 128, 0, st>>>(lo1.p, abeg.p, aend.p, cbeg.p, nit, P2, lo0.p, sc.p, pred.p, stack.p, d_c2.p, nout.p, capc); KERNEL_CHECK(); }
     u32 nc2 = nout.to_host()[0]; if (nc2 > capc) throw std::runtime_error("chain2 list overflow"); c2 = d_c2.to_host(nc2);
     lap("pa_chain+d2h"); bucket_sort(c2, nit, [](const C2Rec& a) { return a.item; }, [](const C2Rec& a, const C2Rec& b) { if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
@@ -1130,11 +1163,12 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   if (nj) {
     DBuf<HspJob> d_jobs(nj, st); d_jobs.from_host(jobs.data(), nj); DBuf<u32> ecnt(2 * (u64)nj + 1, st); DBuf<i32> eres(4 * (u64)nj, st);
     { KTimer kt(st, &ix->ms[13]); k_extend<true><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p, nullptr, nullptr, nullptr, nullptr, nullptr); KERNEL_CHECK(); }
-    std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); std::vector<u64> hso(2 * (u64)nj + 1, 0); for (u64 i = 0; i < 2 * (u64)nj; i++) hso[i + 1] = hso[i] + hec[i]; u64 ES = hso.back();
-    DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i32> esc(ES + 2, st);
+    std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); const u64 nwp = (2 * (u64)nj + 31) / 32; std::vector<u64> hso(nwp + 1, 0);   // per warp: 32 x the longest anchor list of its 32 (job, side) threads
+    for (u64 w = 0; w < nwp; w++) { u32 mx = 0; for (u64 i = w * 32; i < std::min<u64>(2 * (u64)nj, w * 32 + 32); i++) mx = std::max(mx, hec[i]); hso[w + 1] = hso[w] + 32ull * mx; } u64 ES = hso.back();
+    DBuf<u64> soff(nwp + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i16> esc(ES + 2, st);
     { KTimer kt(st, &ix->ms[13]); k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK(); }
     lap("extend kernels"); DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
-    wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, prm->wfa_adaptive, hw, hops, ix->counters, ix->ms);
+    wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, prm->wfa_adaptive, hw, hops, ix->counters, ix->ms, ix->total_mem, ix->active_lanes);
   }
   lap("K5 total");
   T.mark();                                                                                              // [5] extend + wfa
@@ -1191,21 +1225,36 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
 extern "C" {
 
 void lmg_default_params(lmg_params* p) { p->min_prefix = 15; p->min_single_prefix = 17; p->top_n_genomes = 0; p->top_n_chains = 0; p->max_gap = 50; p->max_distance = 1000; p->ext_len = 1000; p->ext_len2 = 50;
-  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; p->wfa_adaptive = 1; p->reserved = 0; }
+  p->min_qcov_genome = 0; p->max_evalue = 10; p->align_max_gap = 20; p->align_min_len = 50; p->align_band = 100; p->output_seq = 0; p->min_pident = 70; p->min_qcov_hsp = 0; p->wfa_adaptive = 1; p->lanes = 0; }
 const char* lmg_last_error(void) { return g_err.c_str(); }
+
+static lmg_index* make_ctx(Image* im, bool owner, int device) {
+  lmg_index* ix = new lmg_index(im, owner); CUDA_CHECK(cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking)); ix->tmp.st = ix->st;
+  cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); ix->sm_count = pr.multiProcessorCount; ix->smem_optin = (u32)pr.sharedMemPerBlockOptin; if (pr.major < 9) ix->use_tma = 0;
+  if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
+  // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
+  auto raise = [&](const void* f) { cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, f)); CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin - fa.sharedSizeBytes))); };
+  if (owner) { raise((const void*)k_capture); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 256>); }
+  return ix;
+}
+static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }
+static lmg_index* lane_ctx(lmg_index* ix, int l) { if (l == 0) return ix; while ((int)ix->lanes.size() < l) { ix->lanes.push_back(make_ctx(ix->imgp, false, ix->img.device)); ix->lanes.back()->lane_id = (int)ix->lanes.size(); } return ix->lanes[l - 1]; }
+// number of concurrent sub-batches: explicit (params.lanes / LMG_LANES) or up to 3 for batches big enough to amortise the split
+// (measured on the 10,000 x 1-kb bench: 1 lane 175 ms, 2 lanes 134 ms, 3 lanes 127 ms, 4 lanes 140 ms per batch; exclusive GPU phases were slower)
+static int pick_lanes(const lmg_params* p, int nq, u64 bases) { int L = (p && p->lanes > 0) ? p->lanes : 0; if (!L) { const char* e = getenv("LMG_LANES"); if (e) L = atoi(e); } bool forced = L > 0; if (!L) L = 3; L = std::max(1, std::min(L, 8));
+  if (!forced) while (L > 1 && (nq < 1000 * L || bases < (u64)1000000 * L)) L--; return std::max(1, std::min(L, std::max(nq, 1))); }
+static std::vector<int> lane_cuts(const u64* off, int nq, int L) { std::vector<int> cut(L + 1, nq); cut[0] = 0; u64 tot = off[nq] - off[0]; int q = 0; for (int l = 1; l < L; l++) { u64 want = off[0] + tot * l / L; while (q < nq && off[q] < want) q++; cut[l] = std::max(q, cut[l - 1]); } return cut; }
 
 int lmg_index_open(const char* dir, int device, int shard, int n_shards, lmg_index** out) {
   try { int ndev = 0; CUDA_CHECK(cudaGetDeviceCount(&ndev)); if (ndev == 0) throw std::runtime_error("no CUDA device: the LexicMap GPU path has no CPU fallback");
-    lmg_index* ix = new lmg_index; ix->img.load(dir, device, shard, std::max(1, n_shards)); CUDA_CHECK(cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking)); ix->tmp.st = ix->st;
-    cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); ix->sm_count = pr.multiProcessorCount; ix->smem_optin = (u32)pr.sharedMemPerBlockOptin; if (pr.major < 9) ix->use_tma = 0;
-    if (getenv("LMG_NO_TMA")) ix->use_tma = 0;
+    Image* im = new Image; lmg_index* ix = nullptr; try { im->load(dir, device, shard, std::max(1, n_shards)); ix = make_ctx(im, true, device); } catch (...) { if (!ix) { im->release(); delete im; } throw; }
     cudaMemPool_t pool; CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device)); u64 thr = ~0ull; CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = ix; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int lmg_index_info(const lmg_index* ix, lmg_info* o) { const Image& I = ix->img; o->k = I.k; o->masks = I.m; o->chunks = I.info.chunks; o->partitions = I.info.partitions; o->genomes = I.G; o->genome_batches = I.info.genome_batches;
   o->contig_interval = I.contig_interval; o->mask_prefix = I.mask_prefix; o->anchor_prefix = I.anchor_prefix; o->input_bases = I.total_bases; o->seed_keys = I.E; o->seed_values = I.V; o->image_bytes = I.bytes; return 0; }
 int lmg_genome_name(const lmg_index* ix, uint64_t genome, const char** name) { auto it = ix->img.bgi2dense.find(genome); if (it == ix->img.bgi2dense.end()) { *name = ""; return -1; } *name = ix->img.genome_names[it->second].c_str(); return 0; }
-void lmg_index_close(lmg_index* ix) { if (!ix) return; cudaSetDevice(ix->img.device); cudaStreamSynchronize(ix->st); ix->img.release(); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } cudaStreamDestroy(ix->st); delete ix; }
+void lmg_index_close(lmg_index* ix) { if (!ix) return; cudaSetDevice(ix->img.device); for (lmg_index* l : ix->lanes) { free_ctx(l); delete l; } free_ctx(ix); ix->img.release(); Image* im = ix->imgp; delete ix; delete im; }
 void lmg_free(void* p) { free(p); }
 int lmg_last_timing(const lmg_index* ix, double* ms16, uint64_t* c16) { for (int i = 0; i < 16; i++) { if (ms16) ms16[i] = ix->ms[i]; if (c16) c16[i] = ix->counters[i]; } if (c16) c16[15] = g_launches; return 0; }
 
@@ -1238,9 +1287,30 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
 }
 
 #define LMG_HAVE_SEARCH 1
+struct lmg_queries { std::vector<QBatch> parts; std::vector<int> cut; };
+// Runs the pipeline over L sub-batches concurrently (one host thread, stream and arena per lane) and concatenates the rows in query order.
+// Queries are independent all the way through the reference path (search.go:437-533 handles one query at a time), so the split is exact.
+static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, const u64* off, int nq, lmg_results& R, lmg_queries* staged) {
+  auto w0 = std::chrono::steady_clock::now(); const int dev = ix->img.device; CUDA_CHECK(cudaSetDevice(dev));
+  std::vector<int> cut = staged ? staged->cut : lane_cuts(off, nq, pick_lanes(p, nq, off[nq] - off[0])); const int L = (int)cut.size() - 1;
+  if (L == 1) { ix->active_lanes = 1; ArenaReset ar_(ix); search_pipeline(ix, p, seqs, off, nq, R, staged ? &staged->parts[0] : nullptr); }
+  else {
+    std::vector<lmg_results> Rl(L); std::vector<std::string> err(L); std::vector<lmg_index*> lx(L); for (int l = 0; l < L; l++) { lx[l] = lane_ctx(ix, l); lx[l]->active_lanes = L; }
+    auto work = [&](int l) { try { CUDA_CHECK(cudaSetDevice(dev)); ArenaReset ar_(lx[l]); int n = cut[l + 1] - cut[l]; if (n > 0) search_pipeline(lx[l], p, seqs, staged ? nullptr : off + cut[l], n, Rl[l], staged ? &staged->parts[l] : nullptr); else { for (double& m : lx[l]->ms) m = 0; for (u64& c : lx[l]->counters) c = 0; } }
+      catch (std::exception& e) { err[l] = e.what(); if (err[l].empty()) err[l] = "error"; cudaGetLastError(); } };
+    std::vector<std::thread> th; for (int l = 1; l < L; l++) th.emplace_back(work, l); work(0); for (auto& t : th) t.join();
+    for (int l = 0; l < L; l++) if (!err[l].empty()) throw std::runtime_error(err[l]);
+    size_t nr = 0, np = 0; for (auto& r : Rl) { nr += r.rows.size(); np += r.pool.size(); } R.rows.reserve(nr); R.row_genome.reserve(nr); R.pool.reserve(np); R.img = &ix->img;
+    for (int l = 0; l < L; l++) { u64 po = R.pool.size(); for (lmg_hsp& r : Rl[l].rows) { r.query += (u32)cut[l]; r.cigar_off += po; R.rows.push_back(r); } R.pool += Rl[l].pool; R.row_genome.insert(R.row_genome.end(), Rl[l].row_genome.begin(), Rl[l].row_genome.end()); }
+    // timers and counters: summed over the lanes (the lanes overlap, so stage sums exceed the wall time in ms[7])
+    double msum[16] = {0}; u64 csum[16] = {0}; for (int l = 0; l < L; l++) for (int i = 0; i < 16; i++) { msum[i] += lx[l]->ms[i]; csum[i] += lx[l]->counters[i]; }
+    csum[14] = lx[0]->counters[14]; for (int i = 0; i < 16; i++) { ix->ms[i] = msum[i]; ix->counters[i] = csum[i]; }
+    ix->ms[7] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  }
+  ix->ms[12] = (double)L; ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+}
 int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R;
-    ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; try { search_lanes(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
@@ -1258,18 +1328,17 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
     DBuf<u8> dq(qp.size(), st), dt(tp.size(), st), dqm(qmk.size(), st); dqm.from_host(qmk.data(), qmk.size()); dq.from_host(qp.data(), qp.size()); dt.from_host(tp.data(), tp.size()); DBuf<u64> dqo(n + 1, st), dto(n + 1, st); dqo.from_host(qo.data(), n + 1); dto.from_host(to.data(), n + 1);
     DBuf<HspJob> dj(n, st); dj.from_host(jobs.data(), n); DBuf<ExtOut> de(n, st); de.from_host(ex.data(), n); (void)opsCap;
     cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); std::vector<WfaOut> hw; std::vector<u64> ops; u64 counters[16] = {0}; double dms[16] = {0};
-    wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, adaptive, hw, ops, counters, dms); std::string out;
+    wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, adaptive, hw, ops, counters, dms, pr.totalGlobalMem); std::string out;
     for (int i = 0; i < n; i++) { for (i64 x = (i64)hw[i].ops_n - 1; x >= 0; x--) { u64 op = ops[hw[i].ops_off + x]; out += std::to_string((u32)(op & 0xffffffffu)); out.push_back((char)(op >> 32)); } out.push_back('\n'); }
     char* c = (char*)malloc(out.size() + 1); memcpy(c, out.data(), out.size() + 1); *cigars = c; *cigars_len = out.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 
-struct lmg_queries { QBatch B; };
 int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_queries** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; upload_queries(ix, seqs, off, n, Q->B); CUDA_CHECK(cudaStreamSynchronize(ix->st)); *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; Q->cut = lane_cuts(off, n, pick_lanes(nullptr, n, off[n] - off[0])); const int L = (int)Q->cut.size() - 1; Q->parts.resize(L);
+    for (int l = 0; l < L; l++) { lmg_index* lx = lane_ctx(ix, l); upload_queries(lx, seqs, off + Q->cut[l], Q->cut[l + 1] - Q->cut[l], Q->parts[l]); CUDA_CHECK(cudaStreamSynchronize(lx->st)); } *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int lmg_search_staged(lmg_index* ix, const lmg_params* p, lmg_queries* q, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); auto w0 = std::chrono::steady_clock::now(); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); lmg_results* R = new lmg_results; try { search_pipeline(ix, p, nullptr, nullptr, q->B.nq, *R, &q->B); } catch (...) { delete R; throw; } *out = R;
-    ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; try { search_lanes(ix, p, nullptr, nullptr, q->cut.back(), *R, q); } catch (...) { delete R; throw; } *out = R; return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 void lmg_queries_free(lmg_index* ix, lmg_queries* q) { if (!q) return; cudaSetDevice(ix->img.device); delete q; }

@@ -1,4 +1,6 @@
 """GPU parity, stage by stage: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs. Bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -69,6 +71,25 @@ def test_search_rows_match_oracle(gpu_small, oracle_small, small_queries):
     gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1))
     orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
     assert len(orr) > 50
+    _rows_equal(gr, orr, gs, os_, gc, oc)
+
+
+@pytest.mark.parametrize("lanes", [2, 3, 5])
+def test_search_lanes_match_oracle(gpu_small, oracle_small, small_queries, lanes):
+    """the batch split into concurrent sub-batches (own stream, arena and host thread each) gives the same rows in the same order;
+    both the host-buffer and the staged entry point"""
+    ids, seqs = small_queries
+    orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
+    gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1, lanes=lanes))
+    _rows_equal(gr, orr, gs, os_, gc, oc)
+    assert int(gpu_small.timing()[0][12]) == min(lanes, len(seqs))
+    os.environ["LMG_LANES"] = str(lanes)
+    try:
+        q = gpu_small.stage(seqs)
+    finally:
+        del os.environ["LMG_LANES"]
+    gr, gs, gc = gpu_small.search_staged(q, gpu_small.default_params(output_seq=1))
+    gpu_small.free_staged(q)
     _rows_equal(gr, orr, gs, os_, gc, oc)
 
 
