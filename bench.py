@@ -107,14 +107,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm or None, "reasons": sorted(self.reasons)}
 
 
-def probe_algorithmic_bytes(cnt, masks, nq):
-    """SURVEY.md §8(d) / DESIGN.md §4, sector-granular because the access is random. Per issued probe: 12 B (query k-mer + mask id)
-    + 32 B (anchor-table sector); per probe whose anchor exists: 32 B per search step actually taken (gallop + binary search) + 16 B per
-    entry scanned in the range (key + first value); 48 B per hit record written; 16 B per anchor written. Unissued slots (no captured
-    k-mer / not the first owner of a reversed k-mer) cost their 8-byte k-mer read."""
-    issued, with_anchor, steps, entries, hits, anchors = (int(cnt[i]) for i in range(6))
-    slots = 2 * nq * masks
-    return (slots - issued) * 8 + issued * 44 + steps * 32 + entries * 16 + hits * 48 + anchors * 16
+def probe_algorithmic_bytes(cnt):
+    """SURVEY.md §8(d) / DESIGN.md §4 for k_probe_find2, sector-granular because the access is random. Per surviving probe: its 24-byte
+    record + the 32-byte sector of its anchor-table entry; 32 B per search step actually taken (gallop + binary search over the bucket's
+    keys); 16 B per entry scanned in the matching range (key + first value); 48 B per hit record written."""
+    surv, steps, entries, hits = int(cnt[1]), int(cnt[2]), int(cnt[3]), int(cnt[4])
+    return surv * (24 + 32) + steps * 32 + entries * 16 + hits * 48
 
 
 def cpu_port_throughput(idx_dir, seqs, threads, target_s=12.0):
@@ -244,7 +242,7 @@ def main():
     idx.anchors(seqs[:2000])
     _, cnt = idx.timing()
     scale = len(seqs) / 2000.0
-    alg_bytes = probe_algorithmic_bytes(cnt, idx.info.masks, 2000) * scale
+    alg_bytes = probe_algorithmic_bytes(cnt) * scale
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -253,22 +251,31 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_probe = float(np.mean(probe_ms)) * 1e-3
     achieved = alg_bytes / t_probe / 1e9 if t_probe > 0 else 0.0
+    # the same kernel alone on the GPU (one lane, so no other lane's kernels share the SMs / HBM during its launches)
+    p1 = idx.default_params(lanes=1)
+    iso = []
+    for _ in range(3):
+        idx.search_count(packed, p1)
+        iso.append(idx.timing()[0][8])
+    t_iso = float(np.mean(iso[1:])) * 1e-3
     # ---- CPU baseline on this box (bounded sample)
     threads = os.cpu_count() or 1
     cpu_s = float(os.environ.get("LMG_BENCH_CPU_S", 12.0))   # 0 skips the CPU leg (parameter sweeps only; the default run always reports it)
     cpu_bps, cpu_n, cpu_dt, _ = cpu_port_throughput(idx_dir, seqs, threads, target_s=cpu_s) if cpu_s > 0 else (0.0, 0, 0.0, None)
-    config["lanes"] = int(kern_ms[12] / max(a.steps, 1) + 0.5)   # concurrent sub-batches inside one call; stage_ms / kernel_ms are summed over the lanes (they overlap)
+    config_lanes = int(kern_ms[12] / max(a.steps, 1) + 0.5)
+    config["lanes"] = config_lanes   # concurrent sub-batches inside one call; stage_ms / kernel_ms are summed over the lanes (they overlap)
     out = {"metric": "aligned query bp/s", "value": bp_all / (t_val * 1e-3), "unit": "bp/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t_val,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
            "e2e": {"value": bp_all / (t_e2e * 1e-3), "unit": "bp/s", "h2d_bytes_per_step": int(packed[0].nbytes + packed[1].nbytes), "d2h_bytes_per_step": int(nrows * 136), "ms_per_step": t_e2e},
            "gpu_launches": launches, "rows_per_step": rows_all,
            "stage_ms": {k: float(v) / a.steps for k, v in zip(["h2d", "sketch", "seed_probe", "chain", "pseudo_align", "extend_wfa", "host_finish", "total"], stage_ms)},
-           "roofline": {"bound": "hbm", "kernel": "k_probe_filter+k_probe_find2 (seed lookup)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": t_probe * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+           "roofline": {"bound": "hbm", "kernel": "k_probe_find2 (seed index lookup of the surviving probes)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": t_probe * 1e3, "launches_per_step": config_lanes,
+                        "alone": {"kernel_ms": t_iso * 1e3, "achieved": alg_bytes / t_iso / 1e9 if t_iso > 0 else 0.0, "frac": (alg_bytes / t_iso / 1e9 / peak) if t_iso > 0 else 0.0, "note": "same batch through one lane: no concurrent kernels"}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},
            "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage],
                      "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep+general", 10), ("wfa_fwd+bt", 11), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
-                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_filter_us": int(kcnt[12]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14]), "wfa_lmax": int(kcnt[15])},
+                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14]), "wfa_lmax": int(kcnt[15])},
            "clocks": sampler.summary()}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)

@@ -155,20 +155,61 @@ __global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, CapSoA cap, c
 // data — captured k-mer present, first-owner test of the reversed k-mer, anchor presence bit — and compaction of the surviving probes.
 // Phase B (k_probe_find2, one thread per survivor): the dependent random HBM accesses (anchor start, key search, value flags) with all
 // lanes of a warp on the long path instead of ~1 in 3.
-struct Surv { u64 kmer; u32 qi; u32 aslot_dir; };   // aslot_dir = (bucket*NA + anchor) | dir << 31
+struct Surv { u64 kmer; u32 qi; u32 aslot_dir; u32 lo, n; };   // aslot_dir = (bucket*NA + anchor) | dir << 31; [lo, lo+n) = rows of the query table holding the captured k-mer
 __global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nslot, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
   u64 qi = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool s0 = false, s1 = false; Surv a, b; u32 issued = 0;
   if (qi < nslot) { u64 kmer = cap.kmer[qi];
     if (kmer != 0) { u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); const int s2 = (P.k - P.p) << 1; const u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1;
-      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; } }
+      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; a.lo = cap.lo[qi]; a.n = cap.n[qi]; } }
       u32 lo = cap.lo[qi]; if (owner[koff[q] + lo] == (u32)i) { u64 rv = kmer_reverse62(kmer, P.k); u32 sm = cap.smask[qi]; u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)sm * P.NA + an; issued++;
-        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; } } } }
+        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = lo; b.n = cap.n[qi]; } } } }
   int lane = threadIdx.x & 31; u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1); u32 tot = __popc(b0) + __popc(b1);
   if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
     if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = b; } }
   if (stats) { for (int o = 16; o; o >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, o); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
 }
-__global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, CapSoA cap, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
+// K1b + K2 phase A fused (queries whose sorted k-mer table fits in shared memory): one CTA per query captures every mask (pass 1, as
+// k_capture), tests the anchor-presence bit of the prefix probe at once, and records the first mask that captured each table row in shared
+// memory; pass 2 walks the table ROWS: only a row's first owner searches for the suffix mask of the base-reversed k-mer (about one mask
+// in ten), tests its anchor bit and emits the suffix probe. Nothing per (query, mask) slot goes to HBM — only the surviving probes do.
+// DUMP additionally writes the per-slot capture arrays for lmg_mask_batch.
+template <bool DUMP>
+__global__ void __launch_bounds__(256) k_capture2(const u64* __restrict__ qkeys, const u64* __restrict__ koff, const u64* __restrict__ masks, ProbeParams P, CapSoA cap, u32* __restrict__ owner_g, u32 max_n, int use_tma,
+                                                  const u32* __restrict__ mask_pstart, int mask_pbits, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
+  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; u32* own = (u32*)(stab + max_n); __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024];
+  const int q = blockIdx.x, m = P.m, k = P.k, lane = threadIdx.x & 31; const u64 o = koff[q]; const u32 n = (u32)(koff[q + 1] - o);
+  if (n == 0) { if (DUMP) for (int i = threadIdx.x; i < m; i += blockDim.x) { u64 w = (u64)q * m + i; cap.kmer[w] = 0; cap.lo[w] = 0; cap.n[w] = 0; cap.smask[w] = 0; } return; }
+  if (use_tma) { if (threadIdx.x == 0) mbar_init(&mbar, 1); __syncthreads(); if (threadIdx.x == 0) { u32 bytes = ((n * 8u) + 15u) & ~15u; tma_load_1d(stab, qkeys + o, bytes, &mbar); } for (u32 t = threadIdx.x; t < n; t += blockDim.x) own[t] = 0xFFFFFFFFu; mbar_wait(&mbar, 0); }
+  else { for (u32 t = threadIdx.x; t < n; t += blockDim.x) { stab[t] = qkeys[o + t]; own[t] = 0xFFFFFFFFu; } }
+  const u64* tab = stab;
+  int pb = 31 - __clz(max(n, 16u)) - 3; pb = max(4, min(pb, 10)); const int psh = 2 * k - pb; const u32 NP = 1u << pb;
+  for (u32 t = threadIdx.x; t < NP; t += blockDim.x) { pst[t] = 0xFFFFFFFFu; pen[t] = 0; } __syncthreads();
+  for (u32 t = threadIdx.x; t < n; t += blockDim.x) { u32 p = (u32)(tab[t] >> psh); if (t == 0 || (u32)(tab[t - 1] >> psh) != p) pst[p] = t; if (t + 1 == n || (u32)(tab[t + 1] >> psh) != p) pen[p] = t + 1; } __syncthreads();
+  const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1; const int msh = 2 * k - mask_pbits; u32 issued = 0;
+  auto emit = [&](bool have, const Surv& r) { u32 bal = __ballot_sync(FULLMASK, have); if (!bal) return; u32 base = 0; int ldr = __ffs(bal) - 1; if (lane == ldr) base = atomicAdd(nsurv, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr);
+    if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; } };
+  // pass 1: masks
+  for (int ib = 0; ib < m; ib += blockDim.x) { int i = ib + threadIdx.x; bool s0 = false; Surv r;
+    if (i < m) { u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
+      u64 km = tab[lo]; bool lc = kmer_low_complexity(km, k);   // km==0 is DUST-low-complexity too, as in the reference
+      if (!lc) { atomicMin(&own[lo], (u32)i); u64 left = km & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++;
+        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot; r.lo = lo; r.n = hi - lo; } }
+      if (DUMP) { u64 w = (u64)q * m + i; cap.kmer[w] = lc ? 0 : km; cap.lo[w] = lo; cap.n[w] = hi - lo; cap.smask[w] = 0; } }
+    emit(s0, r); }
+  __syncthreads();
+  // pass 2: table rows; own[r] is set only at the first row of a run of equal k-mers that some mask captured
+  for (u32 rb = 0; rb < n; rb += blockDim.x) { u32 rr = rb + threadIdx.x; bool s1 = false; Surv r;
+    if (rr < n) { u32 i = own[rr];
+      if (i != 0xFFFFFFFFu) { u64 km = tab[rr]; u32 c = 1; while (rr + c < n && tab[rr + c] == km) c++;
+        u64 rv = kmer_reverse62(km, k); u32 mp = (u32)(rv >> msh); u32 a = mask_pstart[mp], b = mask_pstart[mp + 1]; if (a == b) { a = 0; b = (u32)m; } xor_argmin_range(masks, a, b, rv);
+        u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)a * P.NA + an; issued++;
+        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; r.kmer = rv; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot | 0x80000000u; r.lo = rr; r.n = c; }
+        if (DUMP) { cap.smask[(u64)q * m + i] = a; owner_g[o + rr] = i; } } }
+    emit(s1, r); }
+  if (stats) { for (int of = 16; of; of >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, of); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
+}
+
+__global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0;
   if (t < ns) { Surv sv = surv[t]; int dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; int bucket = (int)(aslot / (u32)P.NA); u64 kmer = sv.kmer;
     int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; u32 as = P.anchor_start[aslot];
@@ -178,7 +219,7 @@ __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, CapSoA cap, 
     while (l < r) { u64 mid = (l + r) >> 1; if (P.keys[mid] < left) l = mid + 1; else r = mid; steps++; }
     u64 e0 = l; u32 na = 0;
     while (e0 + ne < hi && P.keys[e0 + ne] <= right) { u64 v0 = P.val_off[e0 + ne], v1 = P.val_off[e0 + ne + 1]; if (v1 > v0 && (int)(P.vals[v0] & 1) == dir) na += (u32)(v1 - v0); ne++; }
-    if (na) { u32 cl = cap.lo[sv.qi], cn = cap.n[sv.qi]; have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = cl; h.n = cn; h.kmer = kmer; h.nanch = na * cn; h.pad = 0; } }
+    if (na) { u32 cl = sv.lo, cn = sv.n; have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = cl; h.n = cn; h.kmer = kmer; h.nanch = na * cn; h.pad = 0; } }
   int lane = threadIdx.x & 31; u32 bal = __ballot_sync(FULLMASK, have);
   if (bal) { u32 base = 0; if (lane == __ffs(bal) - 1) base = atomicAdd(nhits, __popc(bal)); base = __shfl_sync(FULLMASK, base, __ffs(bal) - 1); if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_hits) hits[w] = h; } }
   if (stats) { for (int o = 16; o; o >>= 1) { steps += __shfl_xor_sync(FULLMASK, steps, o); ne += __shfl_xor_sync(FULLMASK, ne, o); } if (lane == 0) { atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); } }
@@ -254,16 +295,6 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 
 // K1b: capture
 struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
-static void sketch_capture(lmg_index* ix, QBatch& B, CapBufs& cap, DBuf<u32>& owner) {
-  cudaStream_t st = ix->st; const Image& I = ix->img; u64 nslot = (u64)B.nq * I.m; cap.kmer.alloc(nslot, st); cap.lo.alloc(nslot, st); cap.n.alloc(nslot, st); cap.smask.alloc(nslot, st); owner.alloc(B.total_k + 2, st); owner.fill_ff();
-  u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
-  u32 smem_cap = (u32)std::min<u64>((ix->smem_optin - 1024) / 8, 24576);  // entries
-  u32 need = (u32)std::min<u64>(maxn, smem_cap); size_t smem = ((size_t)need * 8 + 15) & ~15ull;
-  // slices: enough CTAs to fill 148 SMs a few times over, but keep >= 1024 masks per CTA so the staged table is reused
-  int slices = std::max(1, std::min(I.m / 1024, cdiv(ix->sm_count * 8, std::max(1, B.nq))));
-  k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap.soa(), owner.p, need, ix->use_tma, I.d_mask_pstart, I.mask_pbits); KERNEL_CHECK();
-}
-
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
 static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.keys = I.d_keys; P.val_off = I.d_val_off; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
@@ -275,25 +306,45 @@ template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>&
 
 static int bits_for(u64 v) { int b = 1; while ((v >> b) && b < 64) b++; return b; }
 
-// K2: probes -> anchors sorted by (query, genome, QBegin, QEnd desc, TBegin, qrc, trc)
-static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, CapBufs& cap, DBuf<u32>& owner, Anchors& A, bool stats) {
+// K1b + K2 phase A: surviving probes of the batch. Fused kernel when every query table fits in shared memory next to its owner array,
+// otherwise (long queries) capture into HBM arrays with several CTAs per query, then the separate filter kernel.
+struct Survivors { DBuf<Surv> d; u32 n = 0; };
+static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivors& SV, CapBufs* dump_cap, DBuf<u32>* dump_owner) {
   cudaStream_t st = ix->st; const Image& I = ix->img; if (prm->min_prefix < I.mask_prefix + I.anchor_prefix || prm->min_prefix > I.k) throw std::runtime_error("the minimum prefix length should be in the range of [maskPrefix+anchorPrefix, k]");  // kv-searcher.go:202
-  ProbeParams P = probe_params(I, prm->min_prefix); u64 nprobe = (u64)B.nq * I.m * 2;
-  DBuf<u32> nh(1, st), nsv(1, st); DBuf<u64> dstats(8, st); dstats.zero(); u64 nslot = (u64)B.nq * I.m;
+  ProbeParams P = probe_params(I, prm->min_prefix); const u64 nslot = (u64)B.nq * I.m, nprobe = nslot * 2; DBuf<u32> nsv(1, st); DBuf<u64> dstats(8, st);
   if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); cudaEventCreate(&ix->kev[2]); }
-  // phase A: filter + compact (capacity: half of all probes first, everything on overflow)
-  DBuf<Surv> surv; u64 capS = std::max<u64>(1u << 20, nprobe / 2); u32 ns = 0;
-  for (int attempt = 0; attempt < 2; attempt++) { surv.alloc(capS, st); nsv.zero(); dstats.zero(); cudaEventRecord(ix->kev[0], st);
-    k_probe_filter<<<cdiv((i64)nslot, 256), 256, 0, st>>>(P, cap.soa(), owner.p, B.koff.p, nslot, surv.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st);
-    ns = nsv.to_host()[0]; if (ns <= capS) break; capS = nprobe; }
+  u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
+  const bool fused = maxn <= 8192 && maxn * 12 + 16384 <= ix->smem_optin && !getenv("LMG_NO_FUSED_CAPTURE"); ix->ms[8] = 0;
+  if (dump_cap) { dump_cap->kmer.alloc(nslot, st); dump_cap->lo.alloc(nslot, st); dump_cap->n.alloc(nslot, st); dump_cap->smask.alloc(nslot, st); dump_owner->alloc(B.total_k + 2, st); dump_owner->fill_ff(); }
+  CapBufs capl; DBuf<u32> ownl; CapBufs* cap = dump_cap ? dump_cap : &capl; DBuf<u32>* owner = dump_owner ? dump_owner : &ownl;
+  if (!fused) { if (!dump_cap) { capl.kmer.alloc(nslot, st); capl.lo.alloc(nslot, st); capl.n.alloc(nslot, st); capl.smask.alloc(nslot, st); ownl.alloc(B.total_k + 2, st); ownl.fill_ff(); }
+    u32 smem_cap = (u32)std::min<u64>((ix->smem_optin - 1024) / 8, 24576); u32 need = (u32)std::min<u64>(maxn, smem_cap); size_t smem = ((size_t)need * 8 + 15) & ~15ull;
+    // slices: enough CTAs to fill 148 SMs a few times over, but keep >= 1024 masks per CTA so the staged table is reused
+    int slices = std::max(1, std::min(I.m / 1024, cdiv(ix->sm_count * 8, std::max(1, B.nq))));
+    k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap->soa(), owner->p, need, ix->use_tma, I.d_mask_pstart, I.mask_pbits); KERNEL_CHECK(); }
+  // capacity: a quarter of all probes first (about 10 % survive on the bench workload), everything on overflow
+  u64 capS = std::max<u64>(1u << 20, nprobe / 4);
+  for (int attempt = 0; attempt < 2; attempt++) { SV.d.alloc(capS, st); nsv.zero(); dstats.zero();
+    if (fused) { u32 mx = (u32)((maxn + 1) & ~1ull); size_t smem = (size_t)mx * 12 + 16;
+      if (dump_cap) { k_capture2<true><<<B.nq, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), owner->p, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); }
+      else { k_capture2<false><<<B.nq, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), nullptr, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); } }
+    else { cudaEventRecord(ix->kev[0], st); k_probe_filter<<<cdiv((i64)nslot, 256), 256, 0, st>>>(P, cap->soa(), owner->p, B.koff.p, nslot, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st); }
+    SV.n = nsv.to_host()[0]; if (SV.n <= capS) break; capS = nprobe; }
+  if (!fused) { float fa = 0; cudaEventSynchronize(ix->kev[1]); cudaEventElapsedTime(&fa, ix->kev[0], ix->kev[1]); ix->ms[8] = fa; ix->counters[12] = (u64)(fa * 1000); } else ix->counters[12] = 0;
+  ix->counters[0] = dstats.to_host()[0]; ix->counters[1] = SV.n; ix->counters[8] = nprobe;
+}
+
+// K2 phase B: index lookup on the surviving probes -> anchors sorted by (query, genome, QBegin, QEnd desc, TBegin, qrc, trc)
+static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivors& SV, Anchors& A, bool stats) {
+  cudaStream_t st = ix->st; const Image& I = ix->img; ProbeParams P = probe_params(I, prm->min_prefix); DBuf<u32> nh(1, st); DBuf<u64> dstats(8, st); dstats.zero(); const u32 ns = SV.n; DBuf<Surv>& surv = SV.d;
   // phase B: index lookup on the survivors
   DBuf<ProbeHit> hits; u64 capH = std::max<u64>(1u << 18, (u64)ns / 2 + 1024); u32 nhit = 0;
   for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) { u64 z[2] = {0, 0}; CUDA_CHECK(cudaMemcpyAsync(dstats.p + 2, z, 16, cudaMemcpyHostToDevice, st)); }
-    cudaEventRecord(ix->kev[1], st); k_probe_find2<<<cdiv(ns, 256), 256, 0, st>>>(P, cap.soa(), surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
+    cudaEventRecord(ix->kev[1], st); k_probe_find2<<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
     nhit = nh.to_host()[0]; if (nhit <= capH) break; capH = (u64)ns + 1024; }
   if (!hits.p) hits.alloc(16, st);
-  { float fa = 0, fb = 0; cudaEventSynchronize(ix->kev[1]); cudaEventElapsedTime(&fa, ix->kev[0], ix->kev[1]); if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] = fa + fb; ix->counters[8] = nprobe; ix->counters[12] = (u64)(fa * 1000); ix->counters[13] = (u64)(fb * 1000); }
-  { auto sdt = dstats.to_host(); ix->counters[0] = sdt[0]; ix->counters[1] = ns; if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; } ix->counters[4] = nhit; }
+  { float fb = 0; if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] += fb; ix->counters[13] = (u64)(fb * 1000); }
+  { auto sdt = dstats.to_host(); if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; } ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
   DBuf<u64> hoff(nhit + 1, st);
   { DBuf<u64> cnt(nhit + 1, st); k_hit_counts<<<cdiv(nhit + 1, 256), 256, 0, st>>>(hits.p, nhit, cnt.p); KERNEL_CHECK();
@@ -1053,9 +1104,9 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
   LapTimer lap; lap.lane = ix->lane_id; const bool dbgt = lap.on; struct LapScope { LapTimer* prev; LapScope(LapTimer* l) : prev(g_lap) { g_lap = l; } ~LapScope() { g_lap = prev; } } lapscope(&lap);
   QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
-  lap("upload"); sketch_tables(ix, B); if (dbgt) cudaStreamSynchronize(st); lap("sketch tables"); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner); if (dbgt) cudaStreamSynchronize(st); lap("capture"); T.mark();   // [1] sketch
+  lap("upload"); sketch_tables(ix, B); if (dbgt) cudaStreamSynchronize(st); lap("sketch tables"); Survivors SV; probe_survivors(ix, B, prm, SV, nullptr, nullptr); lap("capture+filter"); T.mark();   // [1] sketch (tables, capture, anchor-bit filter)
   if (prm->ext_len2 < 0 || prm->ext_len2 + 80 > 190) throw std::runtime_error("align-ext-len2 must be in [0, 110] for the GPU path (flank windows are held as 192-bit sets)");
-  Anchors A; seed_probe(ix, B, prm, cap, owner, A, false); cap.free(); owner.free(); if (dbgt) cudaStreamSynchronize(st); lap("probe+anchor sort"); T.mark();              // [2] probe
+  Anchors A; seed_probe(ix, B, prm, SV, A, false); SV.d.free(); if (dbgt) cudaStreamSynchronize(st); lap("probe+anchor sort"); T.mark();              // [2] probe
   Segments S; Chains Cn; chain_stage(ix, prm, A, S, Cn); A.hi.free(); A.lo.free(); lap("chain stage"); T.mark();                // [3] chain
   for (int i = 0; i < 16; i++) if (i != 8 && i != 9) ix->ms[i] = 0; ix->counters[11] = 0;
   auto finish_times = [&](int upto) { const int map_[6] = {0, 1, 2, 3, 4, 5}; (void)map_; CUDA_CHECK(cudaStreamSynchronize(st)); for (int i = 0; i < upto; i++) ix->ms[i] = T.ms(i, i + 1); ix->ms[7] = T.ms(0, upto); ix->counters[6] = B.total_bases; ix->counters[7] = (u64)B.nq; };
@@ -1234,7 +1285,7 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
   if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
   // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
   auto raise = [&](const void* f) { cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, f)); CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin - fa.sharedSizeBytes))); };
-  if (owner) { raise((const void*)k_capture); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 256>); }
+  if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 256>); }
   return ix;
 }
 static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }
@@ -1259,7 +1310,7 @@ void lmg_free(void* p) { free(p); }
 int lmg_last_timing(const lmg_index* ix, double* ms16, uint64_t* c16) { for (int i = 0; i < 16; i++) { if (ms16) ms16[i] = ix->ms[i]; if (c16) c16[i] = ix->counters[i]; } if (c16) c16[15] = g_launches; return 0; }
 
 int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* kmers, uint32_t* nlocs, uint32_t* minloc, uint64_t* suf, uint64_t suf_cap, uint64_t* n_suf) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; { lmg_params dp; lmg_default_params(&dp); Survivors SV; probe_survivors(ix, B, &dp, SV, &cap, &owner); }
     const int m = ix->img.m, k = ix->img.k; std::vector<Capture> hc((u64)n * m); { auto a = cap.kmer.to_host(); auto b = cap.lo.to_host(); auto c = cap.n.to_host(); auto d = cap.smask.to_host(); for (size_t i = 0; i < hc.size(); i++) { hc[i].kmer = a[i]; hc[i].lo = b[i]; hc[i].n = c[i]; hc[i].smask = d[i]; } } auto hv = B.qvals.to_host(); auto ho = owner.to_host(); u64 ns = 0; std::vector<std::array<u64, 4>> trip;
     for (int q = 0; q < n; q++) { trip.clear();
       for (int i = 0; i < m; i++) { const Capture& c = hc[(u64)q * m + i]; u64 o = (u64)q * m + i; kmers[o] = c.kmer; nlocs[o] = c.kmer ? c.n : 0; u32 mn = 0xffffffffu; if (c.kmer) for (u32 t = 0; t < c.n; t++) mn = std::min(mn, hv[B.h_koff[q] + c.lo + t] & 0x7fffffffu); minloc[o] = c.kmer ? mn : 0;
@@ -1269,8 +1320,8 @@ int lmg_mask_batch(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int3
 }
 
 int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_anchor** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
-    Anchors A; seed_probe(ix, B, p, cap, owner, A, true); auto hi = A.hi.to_host(A.n), lo = A.lo.to_host(A.n); lmg_anchor* o = (lmg_anchor*)malloc(sizeof(lmg_anchor) * (A.n + 1));
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); Survivors SV; probe_survivors(ix, B, p, SV, nullptr, nullptr);
+    Anchors A; seed_probe(ix, B, p, SV, A, true); auto hi = A.hi.to_host(A.n), lo = A.lo.to_host(A.n); lmg_anchor* o = (lmg_anchor*)malloc(sizeof(lmg_anchor) * (A.n + 1));
     for (u64 i = 0; i < A.n; i++) { lmg_anchor& a = o[i]; u32 g = (u32)((hi[i] >> 2) & 0x3FFFFFFFFull); a.genome = ix->img.genome_bgi[g]; a.query = (u32)(hi[i] >> 36); a.qbegin = (i32)(lo[i] >> 36); a.len = (u8)(63 - ((lo[i] >> 30) & 63)); a.tbegin = (i32)((lo[i] >> 2) & 0x0FFFFFFF); a.qrc = (lo[i] >> 1) & 1; a.trc = lo[i] & 1; a.pad = 0; }
     *out = o; *n_out = A.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
@@ -1278,8 +1329,8 @@ int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
 
 #define LMG_HAVE_CHAIN 1
 int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_chain** out, uint64_t* n_out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); CapBufs cap; DBuf<u32> owner; sketch_capture(ix, B, cap, owner);
-    Anchors A; seed_probe(ix, B, p, cap, owner, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); Survivors SV; probe_survivors(ix, B, p, SV, nullptr, nullptr);
+    Anchors A; seed_probe(ix, B, p, SV, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
     lmg_chain* o = (lmg_chain*)malloc(sizeof(lmg_chain) * (C.n + 1));
     for (u32 i = 0; i < C.n; i++) { const ChainRec& r = C.h[i]; lmg_chain& c = o[i]; u64 key = S.h_key[r.seg]; c.query = (u32)(key >> 36); c.genome = ix->img.genome_bgi[(u32)((key >> 2) & 0x3FFFFFFFFull)]; c.score = r.score; c.n_seeds = r.nseeds;
       c.q0 = r.q0; c.t0 = r.t0; c.len0 = r.len0; c.q1 = r.q1; c.t1 = r.t1; c.len1 = r.len1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1; c.rc = (r.nseeds == 1) ? (qrc != trc) : (r.t0 > r.t1); }
