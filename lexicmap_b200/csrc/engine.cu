@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap,
 template <bool DUMP>
 __global__ void __launch_bounds__(256) k_capture2(const u64* __restrict__ qkeys, const u64* __restrict__ koff, const u64* __restrict__ masks, ProbeParams P, CapSoA cap, u32* __restrict__ owner_g, u32 max_n, int use_tma,
                                                   const u32* __restrict__ mask_pstart, int mask_pbits, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
-  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; u32* own = (u32*)(stab + max_n); __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024];
+  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; u32* own = (u32*)(stab + max_n); __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024]; __shared__ u32 lcb[256];   // lcb: low-complexity flag per table row (rows <= 8192)
   const int q = blockIdx.x, m = P.m, k = P.k, lane = threadIdx.x & 31; const u64 o = koff[q]; const u32 n = (u32)(koff[q + 1] - o);
   if (n == 0) { if (DUMP) for (int i = threadIdx.x; i < m; i += blockDim.x) { u64 w = (u64)q * m + i; cap.kmer[w] = 0; cap.lo[w] = 0; cap.n[w] = 0; cap.smask[w] = 0; } return; }
   if (use_tma) { if (threadIdx.x == 0) mbar_init(&mbar, 1); __syncthreads(); if (threadIdx.x == 0) { u32 bytes = ((n * 8u) + 15u) & ~15u; tma_load_1d(stab, qkeys + o, bytes, &mbar); } for (u32 t = threadIdx.x; t < n; t += blockDim.x) own[t] = 0xFFFFFFFFu; mbar_wait(&mbar, 0); }
@@ -184,14 +184,17 @@ __global__ void __launch_bounds__(256) k_capture2(const u64* __restrict__ qkeys,
   const u64* tab = stab;
   int pb = 31 - __clz(max(n, 16u)) - 3; pb = max(4, min(pb, 10)); const int psh = 2 * k - pb; const u32 NP = 1u << pb;
   for (u32 t = threadIdx.x; t < NP; t += blockDim.x) { pst[t] = 0xFFFFFFFFu; pen[t] = 0; } __syncthreads();
-  for (u32 t = threadIdx.x; t < n; t += blockDim.x) { u32 p = (u32)(tab[t] >> psh); if (t == 0 || (u32)(tab[t - 1] >> psh) != p) pst[p] = t; if (t + 1 == n || (u32)(tab[t + 1] >> psh) != p) pen[p] = t + 1; } __syncthreads();
+  for (u32 t = threadIdx.x; t < n; t += blockDim.x) { u32 p = (u32)(tab[t] >> psh); if (t == 0 || (u32)(tab[t - 1] >> psh) != p) pst[p] = t; if (t + 1 == n || (u32)(tab[t + 1] >> psh) != p) pen[p] = t + 1; }
+  // the DUST score is a property of the k-mer, not of the mask: once per table row (about 2,000) instead of once per mask (20,000); it was 65 % of this kernel's instructions
+  for (u32 tb = 0; tb < n; tb += blockDim.x) { u32 t = tb + threadIdx.x; bool lc = (t < n) && kmer_low_complexity(tab[t], k); u32 bal = __ballot_sync(FULLMASK, lc); if (lane == 0 && (tb + threadIdx.x) < ((n + 31) & ~31u)) lcb[(tb + threadIdx.x) >> 5] = bal; }
+  __syncthreads();
   const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1; const int msh = 2 * k - mask_pbits; u32 issued = 0;
   auto emit = [&](bool have, const Surv& r) { u32 bal = __ballot_sync(FULLMASK, have); if (!bal) return; u32 base = 0; int ldr = __ffs(bal) - 1; if (lane == ldr) base = atomicAdd(nsurv, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr);
     if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; } };
   // pass 1: masks
   for (int ib = 0; ib < m; ib += blockDim.x) { int i = ib + threadIdx.x; bool s0 = false; Surv r;
     if (i < m) { u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
-      u64 km = tab[lo]; bool lc = kmer_low_complexity(km, k);   // km==0 is DUST-low-complexity too, as in the reference
+      u64 km = tab[lo]; bool lc = (lcb[lo >> 5] >> (lo & 31)) & 1;   // km==0 is DUST-low-complexity too, as in the reference
       if (!lc) { atomicMin(&own[lo], (u32)i); u64 left = km & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++;
         if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot; r.lo = lo; r.n = hi - lo; } }
       if (DUMP) { u64 w = (u64)q * m + i; cap.kmer[w] = lc ? 0 : km; cap.lo[w] = lo; cap.n[w] = hi - lo; cap.smask[w] = 0; } }
@@ -635,26 +638,42 @@ __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__
   for (u32 i = threadIdx.x; i < tn; i += 256) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> 17; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
   __syncthreads();
   if (threadIdx.x == 0) { u32 nxt = tn; for (int b = 255; b >= 0; b--) { if (pdir[b] == tn) pdir[b] = nxt; else nxt = pdir[b]; } pdir[256] = tn; }   // empty buckets -> start of the next one
-  const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull;
+  const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const int lane = threadIdx.x & 31;
+  // Work compaction: most window positions fail the Bloom / prefix pre-check, and of those that search the table only a few take the
+  // radix-tree emulation. Doing everything in one pass ran at ~10 active lanes per instruction; instead positions that pass the pre-check
+  // are queued (position << 1 | strand) and searched 256 at a time, and the rare slow-path searches are queued again.
+  __shared__ u32 qfast[1024], qslow[768]; __shared__ u32 nfast, nslow;
   for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
     __syncthreads();   // previous window fully consumed (and, first time, table loaded)
     i32 nw = (w.W + 15) / 16 + 2;
     for (i32 x = threadIdx.x; x < nw; x += 256) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
-    if (threadIdx.x == 0) s_base = 0; __syncthreads();
-    i32 np = w.W - K + 1;
-    for (i32 idx = threadIdx.x; idx < np; idx += 256) {
-      u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2, kr = kmer_reverse62(~km & ttt, K);
-      if (km == 0 || km == ccc || km == ggg || km == ttt || !tn) continue;
-      u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0, c = 0; bool f1, f2;
-      { u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; bool maybe = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0); u32 b = (u32)(km >> 54); f1 = maybe && tree_search_in(sk, tn, pdir[b], pdir[b + 1], km, w.mp, &l1, &h1);
-        hb = ((u32)(kr >> 40) * 2654435761u) >> 17; maybe = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); b = (u32)(kr >> 54); f2 = maybe && tree_search_in(sk, tn, pdir[b], pdir[b + 1], kr, w.mp, &l2, &h2); }
-      if (f1) for (u32 u = l1; u < h1; u++) { u32 vv = sv[u]; int lp = lcp31(km, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
-      if (f2) for (u32 u = l2; u < h2; u++) { u32 vv = sv[u]; int lp = lcp31(kr, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
-      if (!c) continue; u32 wpos = atomicAdd(&s_base, c); if ((u64)wpos + c > (u64)cap) continue; u64* out = a_lo + base0 + wpos;
-      if (f1) for (u32 u = l1; u < h1; u++) { u32 vv = sv[u]; int lp = lcp31(km, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx, 0, 0); }
-      if (f2) for (u32 u = l2; u < h2; u++) { u32 vv = sv[u]; int lp = lcp31(kr, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; *out++ = pack_lo((i32)p, (u32)lp, idx + K - lp, 1, 1); }
-    }
+    if (threadIdx.x == 0) { s_base = 0; nfast = 0; nslow = 0; } __syncthreads();
+    const i32 np = w.W - K + 1;
+    auto key_at = [&](u32 e) -> u64 { u32 idx = e >> 1; u32 wi = idx >> 4, sh = (idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2; return (e & 1) ? kmer_reverse62(~km & ttt, K) : km; };
+    auto emit = [&](u32 e, u64 key, u32 l, u32 h) { const u32 idx = e >> 1; u32 c = 0;
+      if (!(e & 1)) { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; } }
+      else { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; } }
+      if (!c) return; u32 wpos = atomicAdd(&s_base, c); if ((u64)wpos + c > (u64)cap) return; u64* out = a_lo + base0 + wpos;
+      if (!(e & 1)) { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; *out++ = pack_lo((i32)p, (u32)lp, (i32)idx, 0, 0); } }
+      else { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; *out++ = pack_lo((i32)p, (u32)lp, (i32)idx + K - lp, 1, 1); } } };
+    auto push = [&](u32* qu, u32* cnt, bool have, u32 e) { u32 bal = __ballot_sync(FULLMASK, have); if (!bal) return; u32 base = 0; int ldr = __ffs(bal) - 1; if (lane == ldr) base = atomicAdd(cnt, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr); if (have) qu[base + __popc(bal & ((1u << lane) - 1))] = e; };
+    auto drain = [&](bool all) {   // uniform across the CTA
+      __syncthreads(); u32 nf = nfast;
+      while (nf >= 256 || (all && nf > 0)) { u32 take = min(nf, 256u), start = nf - take; bool slow = false; u32 e = 0;
+        if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = key_at(e); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
+          while (x < y) { u32 m = (x + y) >> 1; if (sk[m] < left) x = m + 1; else y = m; } u32 en = x; while (en < tn && sk[en] <= right) en++;
+          if (en > x) emit(e, key, x, en); else slow = quirk_possible(sk, tn, x, key, p); }
+        __syncthreads(); if (threadIdx.x == 0) nfast = start; push(qslow, &nslow, slow, e); __syncthreads(); nf = start;
+        u32 ns = nslow; if (ns >= 256 || (all && nf == 0 && ns > 0)) { while (ns > 0) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = key_at(e2); u32 l, h; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) emit(e2, key, l, h); } ns = st2; } __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } }
+      if (all) { u32 ns = nslow; if (ns > 0) { while (ns > 0) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = key_at(e2); u32 l, h; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) emit(e2, key, l, h); } ns = st2; } __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } } };
+    for (i32 base = 0; base < np && tn; base += 256) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
+      if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
+        if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
+          u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
+          hb = ((u32)(kr >> 40) * 2654435761u) >> 17; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
+      push(qfast, &nfast, c1, (u32)idx << 1); push(qfast, &nfast, c2, ((u32)idx << 1) | 1u); drain(false); }
+    drain(true);
     __syncthreads(); if (threadIdx.x == 0) counts[it] = s_base;
   }
 }
@@ -724,7 +743,7 @@ __global__ void __launch_bounds__(128) k_pa_chain(const u64* __restrict__ lo_sor
       i32 s = -1; bool valid = nonskip && lane < firstBrk;
       if (valid) { i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > P.max_gap) valid = false; else s = S[j] + bl - g; }
       i32 rs = valid ? s : INT32_MIN, rj = valid ? j : INT32_MAX;
-      for (int o = 16; o; o >>= 1) { i32 os = __shfl_xor_sync(FULLMASK, rs, o), oj = __shfl_xor_sync(FULLMASK, rj, o); if (os > rs || (os == rs && oj < rj)) { rs = os; rj = oj; } }
+      { i32 mx = __reduce_max_sync(FULLMASK, rs); rj = __reduce_min_sync(FULLMASK, rs == mx ? rj : INT32_MAX); rs = mx; }   // best score of the chunk, smallest j among equals (hardware warp reductions)
       if (rj != INT32_MAX && rs >= bs) { bs = rs; bj = rj; }     // s >= m: later (smaller j) wins ties
       cnt += __popc(bal);
     }
@@ -778,26 +797,39 @@ __device__ u32 ext_count(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n
   p = tbase(v, ta); for (i32 i = 1; i < n2; i++) { u32 c = tbase(v, ta + dt * i); u32 m = (p << 2) | c; if (m < 8) b0 += 1ull << (8 * m); else b1 += 1ull << (8 * (m - 8)); p = c; }
   u32 t = 0; for (int i = 0; i < 8; i++) { t += (u32)((a0 >> (8 * i)) & 255) * (u32)((b0 >> (8 * i)) & 255) + (u32)((a1 >> (8 * i)) & 255) * (u32)((b1 >> (8 * i)) & 255); } return t;
 }
-// _extendRight: anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10, BandCount 20), best chain end + 1.
-// The per-thread scratch arrays are interleaved across the warp (element i of lane l at [i*32 + l]): lanes walk their lists in lockstep, so
-// the warp's loads/stores of element i (and of element j in the inner loop) fall into the same few sectors instead of 32 separate ones.
-#define EXI(a, i) (a)[(size_t)(i) << 5]
-__device__ void ext_run(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, i32* e1, i32* e2) {
-  *e1 = *e2 = 0; if (n1 < 2 || n2 < 2) return; u32 n = 0;
-  { // positions of every target 2-mer as bit sets (flanks are at most 192 bases: checked on the host), then one pass over the query 2-mers
-    u64 Mk[16][3]; for (int c = 0; c < 16; c++) Mk[c][0] = Mk[c][1] = Mk[c][2] = 0;
-    u32 tp = tbase(v, ta); for (i32 i2 = 0; i2 + 1 < n2; i2++) { u32 tn = tbase(v, ta + dt * (i2 + 1)); Mk[(tp << 2) | tn][i2 >> 6] |= 1ull << (i2 & 63); tp = tn; }
-    u32 qp = qbase(v, qa); for (i32 i1 = 0; i1 + 1 < n1; i1++) { u32 qn = qbase(v, qa + dq * (i1 + 1)); u32 c = (qp << 2) | qn; qp = qn;
-      for (int w = 0; w < 3; w++) { u64 mk = Mk[c][w]; while (mk) { int b = __ffsll((long long)mk) - 1; mk &= mk - 1; EXI(anc, n) = (u16)((i1 << 8) | (w * 64 + b)); n++; } } } }
-  if (n == 0) return;
+// _extendRight, one WARP per (job, side): anchors (i1,i2) with equal 2-mers in (i1,i2) order, Chainer3 DP (MaxGap 5, MaxDistance 10, BandBase 10,
+// BandCount 20), best chain end + 1. Anchor generation: the positions of each of the 16 target 2-mers as 192-bit sets in shared memory (flanks are
+// at most 192 bases: checked on the host), rows (query 2-mers) expanded in parallel after a warp scan of their match counts. DP: anchors in order,
+// the band of predecessors scanned 32 at a time (same ballot scheme as k_pa_chain). The thread-per-task version took 9 ms per batch: its critical
+// path was a serial chain of dependent loads, and a single repetitive flank (thousands of anchors) held a whole wave.
+__device__ void ext_run_warp(const SeqView& v, i32 qa, i32 n1, int dq, i32 ta, i32 n2, int dt, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, unsigned long long* __restrict__ Mk /*[48] shared, per warp*/, i32* e1, i32* e2) {
+  const int lane = threadIdx.x & 31; *e1 = *e2 = 0; if (n1 < 2 || n2 < 2) return;
+  for (int t = lane; t < 48; t += 32) Mk[t] = 0; __syncwarp();
+  for (i32 i2 = lane; i2 + 1 < n2; i2 += 32) { u32 c = (tbase(v, ta + dt * i2) << 2) | tbase(v, ta + dt * (i2 + 1)); atomicOr(&Mk[c * 3 + (i2 >> 6)], 1ull << (i2 & 63)); } __syncwarp();
+  u32 n = 0;
+  for (i32 r0 = 0; r0 + 1 < n1; r0 += 32) { i32 i1 = r0 + lane; u32 c = 0, cnt = 0; bool act = i1 + 1 < n1;
+    if (act) { c = (qbase(v, qa + dq * i1) << 2) | qbase(v, qa + dq * (i1 + 1)); cnt = __popcll(Mk[c * 3]) + __popcll(Mk[c * 3 + 1]) + __popcll(Mk[c * 3 + 2]); }
+    u32 inc = cnt; for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULLMASK, inc, o); if (lane >= o) inc += t; }
+    u32 w = n + inc - cnt; if (act) for (int wd = 0; wd < 3; wd++) { unsigned long long mk = Mk[c * 3 + wd]; while (mk) { int b = __ffsll((long long)mk) - 1; mk &= mk - 1; anc[w++] = (u16)((i1 << 8) | (wd * 64 + b)); } }
+    n += __shfl_sync(FULLMASK, inc, 31); }
+  __syncwarp(); if (n == 0) return;
   i32 M = 0; u32 Mi = 0;
-  for (u32 i = 0; i < n; i++) { u32 ai = EXI(anc, i); i32 aq = ai >> 8, at = ai & 255; i32 m = 2 - max(aq, at) - abs(aq - at); u32 mj = i; i32 cnt = 0;   // Len - distance2(origin) - gap2(origin)
-    for (i32 j = (i32)i - 1; j >= 0; j--) { u32 aj = EXI(anc, j); i32 bq = aj >> 8, bt = aj & 255; if (bq == aq || bt > at) continue; cnt++; if (!((aq - bq - 2) <= 10 || cnt <= 20)) break;
-      i32 d = max(abs(aq - bq), abs(at - bt)); if (d > 10) continue; i32 g = abs(abs(aq - bq) - abs(at - bt)); if (g > 5) continue; i32 s = (i32)EXI(sc, j) + 2 - d - g; if (s >= m) { m = s; mj = (u32)j; } }
-    EXI(sc, i) = (i16)m; EXI(pj, i) = (u16)mj; if (i >= 1 && m > M) { M = m; Mi = i; } }
+  for (u32 i = 0; i < n; i++) { u32 ai = anc[i]; i32 aq = ai >> 8, at = ai & 255; i32 m0 = 2 - max(aq, at) - abs(aq - at); i32 bs = INT32_MIN, bj = -1, cnt = 0; bool stop = false;   // m0 = Len - distance2(origin) - gap2(origin)
+    for (i32 top = (i32)i - 1; top >= 0 && !stop; top -= 32) { i32 j = top - lane; bool nonskip = false; i32 bq = 0, bt = 0;
+      if (j >= 0) { u32 aj = anc[j]; bq = aj >> 8; bt = aj & 255; nonskip = !(bq == aq || bt > at); }
+      u32 bal = __ballot_sync(FULLMASK, nonskip); i32 mycnt = cnt + __popc(bal & ((2u << lane) - 1));
+      bool brk = nonskip && !((aq - bq - 2) <= 10 || mycnt <= 20); u32 bb = __ballot_sync(FULLMASK, brk); int firstBrk = bb ? (__ffs(bb) - 1) : 32; if (bb) stop = true;
+      i32 s = INT32_MIN; if (nonskip && lane < firstBrk) { i32 d = max(abs(aq - bq), abs(at - bt)); i32 g = abs(abs(aq - bq) - abs(at - bt)); if (d <= 10 && g <= 5) s = (i32)sc[j] + 2 - d - g; }
+      i32 rs = s, rj = (s == INT32_MIN) ? INT32_MAX : j;
+      { i32 mx = __reduce_max_sync(FULLMASK, rs); rj = __reduce_min_sync(FULLMASK, rs == mx ? rj : INT32_MAX); rs = mx; }
+      if (rj != INT32_MAX && rs >= bs) { bs = rs; bj = rj; }   // s >= m: the later (smaller j) wins ties
+      cnt += __popc(bal); }
+    i32 m = m0; u32 mj = i; if (bj >= 0 && bs >= m0) { m = bs; mj = (u32)bj; }
+    if (lane == 0) { sc[i] = (i16)m; pj[i] = (u16)mj; } if (i >= 1 && m > M) { M = m; Mi = i; }
+    __syncwarp(); }
   if (M < 1) return;
   i32 i = (i32)Mi, nMatched = 0, beginOfNext = 0, qb = 0, qe = 0, tb = 0, te = 0; bool firstA = true;
-  for (;;) { i32 j = EXI(pj, i); u32 ai = EXI(anc, i); i32 sq = ai >> 8, stt = ai & 255;
+  for (;;) { i32 j = pj[i]; u32 ai = anc[i]; i32 sq = ai >> 8, stt = ai & 255;
     if (firstA) { firstA = false; qe = sq + 1; te = stt + 1; qb = sq; tb = stt; nMatched += 2; } else { qb = sq; tb = stt; if (sq + 1 >= beginOfNext) nMatched += beginOfNext - sq; else nMatched += 2; }
     beginOfNext = sq;
     if (i == j) { i32 nAQ = qe - qb + 1; if (nAQ < 2) return; i32 nAT = te - tb + 1; double pid = (double)nMatched / (double)max(nAQ, nAT) * 100; if (pid < 15.0) return; *e1 = qe + 1; *e2 = te + 1; return; }
@@ -808,17 +840,27 @@ __device__ __forceinline__ void ext_sides(const HspJob& J, i32* rext, i32* lext)
   if (J.end1 + 2 < J.qlen && J.end2 + 2 < J.tlen) { i32 e = J.rc ? min(J.ext, J.tb_arg) : min(J.ext, J.max_ext); if (e > 2) *rext = e; }
   if (J.start1 > 2 && J.start2 > 2) { i32 e = J.rc ? min(J.ext, J.max_ext) : min(J.ext, J.tb_arg); if (e > 2) *lext = e; }
 }
-// one thread per (job, side). COUNT: scratch sizes; else run.
-template <bool COUNT>
-__global__ void k_extend(const HspJob* __restrict__ jobs, u32 njobs, const u8* __restrict__ qpacked, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
-                         u32* __restrict__ counts, const u64* __restrict__ soff /*per warp*/, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, i32* __restrict__ res /*2 per (job,side)*/) {
+__device__ __forceinline__ bool ext_task(const HspJob& J, int side, i32& qa, i32& n1, i32& ta, i32& n2, int& d) {   // flank geometry of one side; false = no extension attempt
+  i32 rext, lext; ext_sides(J, &rext, &lext);
+  if (side == 0) { if (!rext) return false; qa = J.end1; n1 = min(J.end1 + rext, J.qlen) - J.end1; ta = J.end2; n2 = min(J.end2 + rext, J.tlen) - J.end2; d = 1; }
+  else { if (!lext) return false; i32 s1 = max(J.start1 - lext, 0), s2 = max(J.start2 - lext, 0); qa = J.start1 - 1; n1 = J.start1 - s1; ta = J.start2 - 1; n2 = J.start2 - s2; d = -1; }
+  return true;
+}
+// scratch sizes: one thread per (job, side)
+__global__ void k_extend_count(const HspJob* __restrict__ jobs, u32 njobs, const u8* __restrict__ qpacked, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off, u32* __restrict__ counts) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs * 2) return; u32 jb = t >> 1; int side = t & 1; HspJob J = jobs[jb];
   SeqView v; v.q2 = qpacked + qboff[J.q]; v.qm = nullptr; v.g2 = g2bit + g_off[J.g]; v.tBegin = J.tBegin; v.tEnd = J.tEnd; v.rc = J.rc;
-  i32 rext, lext; ext_sides(J, &rext, &lext); i32 qa, n1, ta, n2; int d;
-  if (side == 0) { if (!rext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } qa = J.end1; n1 = min(J.end1 + rext, J.qlen) - J.end1; ta = J.end2; n2 = min(J.end2 + rext, J.tlen) - J.end2; d = 1; }
-  else { if (!lext) { if (COUNT) counts[t] = 0; else { res[2 * t] = res[2 * t + 1] = 0; } return; } i32 s1 = max(J.start1 - lext, 0), s2 = max(J.start2 - lext, 0); qa = J.start1 - 1; n1 = J.start1 - s1; ta = J.start2 - 1; n2 = J.start2 - s2; d = -1; }
-  if (COUNT) { counts[t] = ext_count(v, qa, n1, d, ta, n2, d); }
-  else { u64 o = soff[t >> 5] + (t & 31); i32 e1, e2; ext_run(v, qa, n1, d, ta, n2, d, anc + o, sc + o, pj + o, &e1, &e2); res[2 * t] = e1; res[2 * t + 1] = e2; }
+  i32 qa, n1, ta, n2; int d; counts[t] = ext_task(J, side, qa, n1, ta, n2, d) ? ext_count(v, qa, n1, d, ta, n2, d) : 0;
+}
+// extension: one warp per (job, side)
+__global__ void __launch_bounds__(128) k_extend_run(const HspJob* __restrict__ jobs, u32 njobs, const u8* __restrict__ qpacked, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
+                                                    const u64* __restrict__ soff, u16* __restrict__ anc, i16* __restrict__ sc, u16* __restrict__ pj, i32* __restrict__ res /*2 per (job,side)*/) {
+  __shared__ unsigned long long Mk[4][48];
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (t >= njobs * 2) return; u32 jb = t >> 1; int side = t & 1, lane = threadIdx.x & 31; HspJob J = jobs[jb];
+  SeqView v; v.q2 = qpacked + qboff[J.q]; v.qm = nullptr; v.g2 = g2bit + g_off[J.g]; v.tBegin = J.tBegin; v.tEnd = J.tEnd; v.rc = J.rc;
+  i32 qa, n1, ta, n2; int d; i32 e1 = 0, e2 = 0;
+  if (ext_task(J, side, qa, n1, ta, n2, d)) { u64 o = soff[t]; ext_run_warp(v, qa, n1, d, ta, n2, d, anc + o, sc + o, pj + o, Mk[threadIdx.x >> 5], &e1, &e2); }
+  if (lane == 0) { res[2 * t] = e1; res[2 * t + 1] = e2; }
 }
 __global__ void k_extend_final(const HspJob* __restrict__ jobs, u32 njobs, const i32* __restrict__ res, ExtOut* __restrict__ out) {
   u32 jb = blockIdx.x * blockDim.x + threadIdx.x; if (jb >= njobs) return; HspJob J = jobs[jb]; ExtOut o; o.e1 = res[4 * jb]; o.e2 = res[4 * jb + 1]; o.s1 = res[4 * jb + 2]; o.s2 = res[4 * jb + 3];
@@ -937,6 +979,8 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
 #define WF_LMAX 2048
 #define WF_OPSMAX 4096
 #define WF_WARPS 8
+#define WF_SEQW 144
+#define WF_SMEM_BYTES ((size_t)WF_WARPS * (WF_SEQW * 8 + 9 * WFS * 2 + WFS * 2))
 struct WfaSeg { u64 qw, tw; };   // word offsets of the job's packed query / target (query: 2 streams: bases at qw, ambiguity at qw + nqw)
 
 __global__ void k_wfa_prep(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, u32 njobs, const u64* __restrict__ woff /*2 per job +1*/, const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff,
@@ -950,13 +994,17 @@ __device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos) { u32
 
 __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, u32 job0, u32 njobs, u32* __restrict__ next_job,
                                                           u16* __restrict__ slabs, WfaOut* __restrict__ outs, int adaptive, int lmax) {
-  __shared__ u16 ring[WF_WARPS][9][WFS];   // 0-4: M levels (L%5), 5-6: I (L%2), 7-8: D (L%2)
+  extern __shared__ __align__(16) u8 wf_smem[];   // per warp: packed sequences | ring of 9 wavefronts (0-4: M levels L%5, 5-6: I L%2, 7-8: D L%2) | distances of the current M wavefront
   const int X2 = 2, OE2 = 4, E2 = 1;        // penalties 4 / 8 / 2 in units of levels (score = 2*level)
-  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u16 (*R)[WFS] = ring[wib];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wf_smem + (size_t)wib * WF_SEQW; u16 (*R)[WFS] = (u16 (*)[WFS])(wf_smem + (size_t)WF_WARPS * WF_SEQW * 8) + (size_t)wib * 9;
+  u16* Dst = (u16*)(wf_smem + (size_t)WF_WARPS * WF_SEQW * 8 + (size_t)WF_WARPS * 9 * WFS * 2) + (size_t)wib * WFS;
   for (;;) {
     u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job0 + jr; u16* slab = slabs + (u64)jr * lmax * 3 * WFS;   // one slab per alignment of the round
     ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
     const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
+    { // stage the packed sequences in shared memory when they fit (alignments of up to ~3 kb each side): the extension loop is a chain of dependent word fetches
+      const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
+      if (nqw + nA + ntw <= WF_SEQW) { u64* sq = seqb; for (u32 i = lane; i < nqw + nA; i += 32) sq[i] = Q[i]; for (u32 i = lane; i < ntw; i += 32) sq[nqw + nA + i] = T[i]; __syncwarp(); Q = sq; A = sq + nqw; T = sq + nqw + nA; } }
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
     if (plen >= 65000 || tlen >= 65000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
     auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
@@ -978,31 +1026,32 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
       if (wl <= -(WF_WMAX / 2) || wh >= WF_WMAX / 2) { overflow = true; break; }
       const u16* M2 = R[(L + 5 - X2) % 5]; const u16* M4 = R[(L + 5 - OE2) % 5]; const u16* I1 = R[5 + ((L + 1) & 1)]; const u16* D1 = R[7 + ((L + 1) & 1)];
       u16* Mo = R[L % 5]; u16* Io = R[5 + (L & 1)]; u16* Do = R[7 + (L & 1)]; u16* G = slab + (u64)L * 3 * WFS; bool anyM = false, anyI = false, anyD = false;
-      for (i32 k = wl - WF_PAD + lane; k <= wh + WF_PAD; k += 32) {
-        u16 om = 0xFFFF, oi = 0xFFFF, od = 0xFFFF; int x = k + WFK0;
+      u32 bitM = 0, bitI = 0, bitD = 0, itb = 1; i32 mind = INT32_MAX; const i32 k0 = wl - WF_PAD + lane;   // bit `it` of bitX: this lane's cell of iteration `it` (k = k0 + 32*it) is non-null
+      for (i32 k = k0; k <= wh + WF_PAD; k += 32, itb <<= 1) {
+        u16 om = 0xFFFF, oi = 0xFFFF, od = 0xFFFF, dd = 0xFFFF; int x = k + WFK0;
         if (!allnull && k >= lo && k <= hi) {
           i32 a = (L >= OE2) ? (i32)M4[x - 1] : 0xFFFF, b = (i32)I1[x - 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 ins = max(a, b); ins = (ins < 0) ? -1 : ins + 1;
           a = (L >= OE2) ? (i32)M4[x + 1] : 0xFFFF; b = (i32)D1[x + 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 del = max(a, b);
           i32 mis = (L >= X2) ? (i32)M2[x] : 0xFFFF; mis = (mis == 0xFFFF) ? -1 : mis + 1;
           const i32 hmax = min(tlen, plen + k);   // h <= tlen and v = h - k <= plen; h >= 0 and v >= 0 hold by construction
           if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
-          i32 mm = max(mis, max(ins, del)); if (mm >= 0) { mm = extend(k, mm); anyM = true; om = (u16)mm; } if (ins >= 0) { anyI = true; oi = (u16)ins; } if (del >= 0) { anyD = true; od = (u16)del; }
+          i32 mm = max(mis, max(ins, del)); if (mm >= 0) { mm = extend(k, mm); bitM |= itb; om = (u16)mm; i32 dv = max(plen - (mm - k), tlen - mm); dd = (u16)dv; mind = min(mind, dv); } if (ins >= 0) { bitI |= itb; oi = (u16)ins; } if (del >= 0) { bitD |= itb; od = (u16)del; }
         }
-        Mo[x] = om; Io[x] = oi; Do[x] = od; G[x] = om; G[WFS + x] = oi; G[2 * WFS + x] = od;
+        Mo[x] = om; Io[x] = oi; Do[x] = od; Dst[x] = dd; G[x] = om; G[WFS + x] = oi; G[2 * WFS + x] = od;
       }
-      anyM = __any_sync(FULLMASK, anyM); anyI = __any_sync(FULLMASK, anyI); anyD = __any_sync(FULLMASK, anyD); __syncwarp();
+      anyM = __any_sync(FULLMASK, bitM != 0); anyI = __any_sync(FULLMASK, bitI != 0); anyD = __any_sync(FULLMASK, bitD != 0); __syncwarp();
       if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa and the oracle
-        i32 mind = INT32_MAX; for (i32 k = lo + lane; k <= hi; k += 32) { u16 o = Mo[k + WFK0]; if (o != 0xFFFF) mind = min(mind, max(plen - ((i32)o - k), tlen - (i32)o)); }
-        for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o));
-        i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
-        for (i32 b0 = lo; b0 < top_limit && !found; b0 += 32) { i32 k = b0 + lane; bool okk = false; if (k < top_limit) { u16 o = Mo[k + WFK0]; okk = (o != 0xFFFF) && (max(plen - ((i32)o - k), tlen - (i32)o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nlo = b0 + __ffs(bal) - 1; found = true; } }
+        for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o));   // distances (max of the remaining query / target lengths) were taken in the cell loop; Dst holds them, 0xFFFF = null
+        const i32 thr = mind + 50; i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
+        for (i32 b0 = lo; b0 < top_limit && !found; b0 += 32) { i32 k = b0 + lane; bool okk = (k < top_limit) && ((i32)Dst[k + WFK0] <= thr); u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nlo = b0 + __ffs(bal) - 1; found = true; } }
         if (!found && top_limit > lo) nlo = top_limit;
         i32 bottom_limit = max(kend, nlo); i32 nhi = hi; found = false;
-        for (i32 b0 = hi; b0 > bottom_limit && !found; b0 -= 32) { i32 k = b0 - lane; bool okk = false; if (k > bottom_limit) { u16 o = Mo[k + WFK0]; okk = (o != 0xFFFF) && (max(plen - ((i32)o - k), tlen - (i32)o) - mind <= 50); } u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nhi = b0 - (__ffs(bal) - 1); found = true; } }
+        for (i32 b0 = hi; b0 > bottom_limit && !found; b0 -= 32) { i32 k = b0 - lane; bool okk = (k > bottom_limit) && ((i32)Dst[k + WFK0] <= thr); u32 bal = __ballot_sync(FULLMASK, okk); if (bal) { nhi = b0 - (__ffs(bal) - 1); found = true; } }
         if (!found && hi > bottom_limit) nhi = bottom_limit;
         if (nlo != lo || nhi != hi) { for (i32 k = lo + lane; k <= hi; k += 32) if (k < nlo || k > nhi) { int x = k + WFK0; Mo[x] = 0xFFFF; Io[x] = 0xFFFF; Do[x] = 0xFFFF; G[x] = 0xFFFF; G[WFS + x] = 0xFFFF; G[2 * WFS + x] = 0xFFFF; }
-          __syncwarp(); bool aM = false, aI = false, aD = false; for (i32 k = nlo + lane; k <= nhi; k += 32) { int x = k + WFK0; aM |= Mo[x] != 0xFFFF; aI |= Io[x] != 0xFFFF; aD |= Do[x] != 0xFFFF; }
-          anyM = __any_sync(FULLMASK, aM); anyI = __any_sync(FULLMASK, aI); anyD = __any_sync(FULLMASK, aD); lo = nlo; hi = nhi; }
+          // which of this lane's cells (k = k0 + 32*it) survive: it in [ceil((nlo-k0)/32), floor((nhi-k0)/32)]
+          i32 a0 = nlo - k0, a1 = nhi - k0; i32 itlo = a0 <= 0 ? 0 : (a0 + 31) >> 5, ithi = a1 < 0 ? -1 : (a1 >> 5); u32 keep = (ithi < itlo) ? 0u : ((ithi >= 31 ? 0xFFFFFFFFu : ((2u << ithi) - 1)) & ~((1u << itlo) - 1));
+          anyM = __any_sync(FULLMASK, (bitM & keep) != 0); anyI = __any_sync(FULLMASK, (bitI & keep) != 0); anyD = __any_sync(FULLMASK, (bitD & keep) != 0); lo = nlo; hi = nhi; __syncwarp(); }
       }
       for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
@@ -1047,6 +1096,7 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
 static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
                         int want_ops, int adaptive, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters, double* ms, size_t total_mem, int active_lanes = 1) {
     // WFA: fast kernel (packed words + smem ring) for every job, then the general kernel for whatever did not fit
+    { static std::once_flag once; std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(k_wfa_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES)); }); }
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
@@ -1061,7 +1111,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       if (g_lap) (*g_lap)("wfa prep kernel"); DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
       { KTimer kt(st, &ms[11]);
         for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (n + WF_WARPS - 1) / WF_WARPS);
-          k_wfa_fast<<<blocks, WF_WARPS * 32, 0, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
+          k_wfa_fast<<<blocks, WF_WARPS * 32, WF_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
           k_wfa_bt<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
       counters[14] = per_round; counters[15] = (u64)lmax; if (g_lap) (*g_lap)("wfa rounds");
       std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
@@ -1213,11 +1263,10 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   u32 nj = (u32)jobs.size(); std::vector<ExtOut> hext; std::vector<WfaOut> hw; std::vector<u64> hops;
   if (nj) {
     DBuf<HspJob> d_jobs(nj, st); d_jobs.from_host(jobs.data(), nj); DBuf<u32> ecnt(2 * (u64)nj + 1, st); DBuf<i32> eres(4 * (u64)nj, st);
-    { KTimer kt(st, &ix->ms[13]); k_extend<true><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p, nullptr, nullptr, nullptr, nullptr, nullptr); KERNEL_CHECK(); }
-    std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); const u64 nwp = (2 * (u64)nj + 31) / 32; std::vector<u64> hso(nwp + 1, 0);   // per warp: 32 x the longest anchor list of its 32 (job, side) threads
-    for (u64 w = 0; w < nwp; w++) { u32 mx = 0; for (u64 i = w * 32; i < std::min<u64>(2 * (u64)nj, w * 32 + 32); i++) mx = std::max(mx, hec[i]); hso[w + 1] = hso[w] + 32ull * mx; } u64 ES = hso.back();
-    DBuf<u64> soff(nwp + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i16> esc(ES + 2, st);
-    { KTimer kt(st, &ix->ms[13]); k_extend<false><<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, nullptr, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK(); }
+    { KTimer kt(st, &ix->ms[13]); k_extend_count<<<cdiv(2 * (i64)nj, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, ecnt.p); KERNEL_CHECK(); }
+    std::vector<u32> hec = ecnt.to_host(2 * (u64)nj); std::vector<u64> hso(2 * (u64)nj + 1, 0); for (u64 i = 0; i < 2 * (u64)nj; i++) hso[i + 1] = hso[i] + hec[i]; u64 ES = hso.back();
+    DBuf<u64> soff(2 * (u64)nj + 1, st); soff.from_host(hso.data(), hso.size()); DBuf<u16> anc(ES + 2, st), pj(ES + 2, st); DBuf<i16> esc(ES + 2, st);
+    { KTimer kt(st, &ix->ms[13]); k_extend_run<<<cdiv(2 * (i64)nj * 32, 128), 128, 0, st>>>(d_jobs.p, nj, B.packed.p, B.boff.p, I.d_g2bit, I.d_g_off, soff.p, anc.p, esc.p, pj.p, eres.p); KERNEL_CHECK(); }
     lap("extend kernels"); DBuf<ExtOut> d_ext(nj, st); k_extend_final<<<cdiv(nj, 128), 128, 0, st>>>(d_jobs.p, nj, eres.p, d_ext.p); KERNEL_CHECK(); hext = d_ext.to_host(nj);
     wfa_run_all(st, ix->sm_count, d_jobs, d_ext, hext, nj, B.packed.p, B.amask.p, B.boff.p, I.d_g2bit, I.d_g_off, prm->output_seq, prm->wfa_adaptive, hw, hops, ix->counters, ix->ms, ix->total_mem, ix->active_lanes);
   }
