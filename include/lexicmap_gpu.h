@@ -39,7 +39,7 @@ typedef struct lmg_params {
   double  min_pident;        /* -i/--align-min-match-pident 70 */
   double  min_qcov_hsp;      /* -q/--min-qcov-per-hsp 0 */
   int32_t wfa_adaptive;      /* 1 = WFA adaptive wavefront reduction (MinWFLen 10, MaxDistDiff 50) as the reference enables at lib-index-search.go:1911; 0 = exact */
-  int32_t lanes;              /* concurrent sub-batches per call (own stream + host thread each); 0 = automatic (up to 3 for large batches, else 1) */
+  int32_t lanes;              /* concurrent sub-batches per call (own stream + host thread each); 0 = automatic (up to 6 for large batches, else 1) */
 } lmg_params;
 
 typedef struct lmg_info {          /* IndexInfo, lib-index-build.go:1914-1932 */

@@ -20,6 +20,9 @@
 #include <mutex>
 #include <atomic>
 #include <thread>
+#include <condition_variable>
+#include <functional>
+#include <exception>
 #include <set>
 #include <array>
 
@@ -255,12 +258,27 @@ struct QBatch {  // device-side query batch
   DBuf<u64> qkeys; DBuf<u32> qvals;    // per-query sorted (k-mer, loc) tables
 };
 
+// Host worker pool of one search context. The host phases between kernels (window geometry, contig mapping, scoring, row building) are
+// split into static chunks; workers sleep on a condition variable between phases — OpenMP teams spin at their barriers, and with several
+// lanes per call the spinning teams oversubscribed the cores and produced 30-50 ms stalls.
+struct HostPool {
+  std::vector<std::thread> th; std::mutex mu; std::condition_variable cv_go, cv_done; std::function<void(int)> fn; int nchunks = 0, next = 0, pending = 0; u64 gen = 0; bool quit = false; std::exception_ptr err;
+  void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { u64 seen = 0; for (;;) { std::unique_lock<std::mutex> lk(mu); cv_go.wait(lk, [&] { return quit || gen != seen; }); if (quit) return; seen = gen; work(lk); } }); }
+  void work(std::unique_lock<std::mutex>& lk) { while (next < nchunks) { int c = next++; lk.unlock(); try { fn(c); } catch (...) { lk.lock(); if (!err) err = std::current_exception(); lk.unlock(); } lk.lock(); if (--pending == 0) cv_done.notify_all(); } }
+  // runs f(0..n-1), the caller takes part; returns when every chunk is done
+  void run(int n, int max_workers, const std::function<void(int)>& f) { if (n <= 0) return; if (n == 1 || max_workers <= 1) { for (int c = 0; c < n; c++) f(c); return; }
+    if ((int)th.size() < max_workers - 1) start(max_workers - 1 - (int)th.size());
+    std::unique_lock<std::mutex> lk(mu); fn = f; nchunks = n; next = 0; pending = n; err = nullptr; gen++; cv_go.notify_all(); work(lk); cv_done.wait(lk, [&] { return pending == 0; }); nchunks = 0; std::exception_ptr e = err; lk.unlock(); if (e) std::rethrow_exception(e); }
+  ~HostPool() { { std::lock_guard<std::mutex> lk(mu); quit = true; } cv_go.notify_all(); for (auto& t : th) t.join(); }
+};
+
 // One search context: the shared HBM image plus this context's stream, arena, scratch and timers. The handle returned by lmg_index_open
 // is lane 0 and owns the image; further lanes (same image, own stream/arena) are created on demand so that big batches can be split into
 // sub-batches whose host phases (window geometry, contig mapping, scoring) overlap the other sub-batch's kernels.
 struct lmg_index {
   Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0;
+  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
+  int host_threads() const { int hc = (int)std::thread::hardware_concurrency(); if (hc <= 0) hc = 8; return std::max(1, std::min(32, hc / (2 * std::max(1, active_lanes)))); }   // workers per lane: half the cores over the active lanes
   lmg_index(Image* p, bool own) : imgp(p), img(*p), owner(own) {}
 };
 
@@ -1163,15 +1181,15 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   if (Cn.n == 0) { T.mark(); finish_times(4); return; }
   // ---- windows (lib-index-search.go:1987-2051)
   const int K = I.k, extLen = prm->ext_len; std::vector<WinItem> items(Cn.n);
-#pragma omp parallel for schedule(static) num_threads(std::max(1, std::min(16, omp_get_max_threads())))
-  for (i64 c = 0; c < (i64)Cn.n; c++) { const ChainRec& r = Cn.h[c]; u64 key = S.h_key[r.seg]; WinItem w; w.q = (u32)(key >> 36); w.g = (u32)((key >> 2) & 0x3FFFFFFFFull); w.chain = (u32)c;
+  const int HT = ix->host_threads();
+  ix->pool.run(HT, HT, [&](int ci) { for (i64 c = (i64)Cn.n * ci / HT, cE = (i64)Cn.n * (ci + 1) / HT; c < cE; c++) { const ChainRec& r = Cn.h[c]; u64 key = S.h_key[r.seg]; WinItem w; w.q = (u32)(key >> 36); w.g = (u32)((key >> 2) & 0x3FFFFFFFFull); w.chain = (u32)c;
     i32 qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); i32 qb = r.q0, tb = r.t0, qe = r.q1 + r.len1 - 1, te = r.t1 + r.len1 - 1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1;
     bool rc = (r.nseeds == 1) ? (qrc != trc) : (tb > r.t1); i32 tBegin, tEnd;
     if (rc) { tBegin = r.t1 - extLen; if (tBegin < 0) tBegin = 0; tEnd = tb + r.len1 - 1 + extLen; } else { tBegin = tb - extLen; if (tBegin < 0) tBegin = 0; tEnd = te + extLen; }
     w.qBegin = qb - std::min(qb, extLen); w.qEnd = qe + std::min(qlen - qe - 1, extLen);
     i32 nb = (i32)I.h_nbases[w.g];
     i32 start = std::max(tBegin, 0), end = tEnd; if (end >= nb - 1) end = nb - 1; if (end < start) end = start; i32 sl = end - start + 1; if (sl < tEnd - tBegin + 1) tEnd -= tEnd - tBegin + 1 - sl;   // SubSeq3 clamp + :2045-2047
-    w.tBegin = tBegin; w.tEnd = tEnd; w.W = sl; w.rc = rc; w.mp = 11 + (sl >= 1000000 ? 8 : sl >= 250000 ? 6 : sl >= 50000 ? 4 : sl >= 10000 ? 2 : 0); items[c] = w; }
+    w.tBegin = tBegin; w.tEnd = tEnd; w.W = sl; w.rc = rc; w.mp = 11 + (sl >= 1000000 ? 8 : sl >= 250000 ? 6 : sl >= 50000 ? 4 : sl >= 10000 ? 2 : 0); items[c] = w; } });
   u32 nit = Cn.n; DBuf<WinItem> d_items(nit, st); d_items.from_host(items.data(), nit);
   lap("windows host"); DBuf<u64> tkeys; DBuf<u32> tvals, toff; build_tree_tables(ix, B, tkeys, tvals, toff); lap("tree tables");
   // ---- K4 anchors: per-query prefix hash, one pass into capacity-bounded regions (exact rerun for the rare overflow), per-window sort
@@ -1229,9 +1247,8 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   { // segments (query, genome) are independent: process them in parallel, concatenate in order
     std::vector<std::pair<u32, u32>> segs; { u32 c = 0; while (c < nit) { u32 seg = Cn.h[c].seg, e = c; while (e < nit && Cn.h[e].seg == seg) e++; segs.push_back({c, e}); c = e; } }
     std::vector<size_t> c2beg(nit + 1, c2.size()); { size_t x = c2.size(); for (i64 it = (i64)nit - 1; it >= 0; it--) { while (x > 0 && c2[x - 1].item >= (u32)it) x--; c2beg[it] = x; } }
-    const int NT = std::max(1, std::min(32, omp_get_max_threads())); std::vector<std::vector<HostCluster>> segCl(NT); std::vector<std::vector<HspJob>> segJobs(NT);
-#pragma omp parallel for schedule(static, 1) num_threads(NT)
-    for (int ti = 0; ti < NT; ti++) { std::vector<HostCluster>& clusters_l = segCl[ti]; std::vector<HspJob>& jobs_l = segJobs[ti]; size_t s0 = segs.size() * ti / NT, s1 = segs.size() * (ti + 1) / NT; std::vector<std::array<int, 6>> keys;
+    const int NT = HT; std::vector<std::vector<HostCluster>> segCl(NT); std::vector<std::vector<HspJob>> segJobs(NT);
+    ix->pool.run(NT, HT, [&](int ti) { std::vector<HostCluster>& clusters_l = segCl[ti]; std::vector<HspJob>& jobs_l = segJobs[ti]; size_t s0 = segs.size() * ti / NT, s1 = segs.size() * (ti + 1) / NT; std::vector<std::array<int, 6>> keys;
      for (size_t si = s0; si < s1; si++) { u32 c = segs[si].first, cEnd = segs[si].second, seg = Cn.h[c].seg;
       keys.clear(); int iSeq = 0, iSeqPre = -1;
       for (u32 it = c; it < cEnd; it++) { const WinItem& w = items[it]; const auto& SS = I.seq_sizes[w.g]; const int numSeqs = (int)SS.size(); const bool rc = w.rc; const i32 tBegin = w.tBegin, tEnd = w.tEnd, tlenSeq = w.W;
@@ -1255,7 +1272,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
             if (iSeqPre >= 0 && iSeq != iSeqPre) { int iSeq0 = iSeq; iSeq = iSeqPre; HostHsp h; convert(h, r, tpoB, iSeq); flush(true, iSeq); iSeqPre = -1;
               std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (std::find(keys.begin(), keys.end(), key) == keys.end()) { cur.hsps.push_back(h); keys.push_back(key); } iSeq = iSeq0; continue; } }
           iSeqPre = iSeq; HostHsp h; convert(h, r, tpoB, iSeq); std::array<int, 6> key{h.qb, h.qe, h.tb, h.te, iSeq, (int)rc}; if (std::find(keys.begin(), keys.end(), key) == keys.end()) { cur.hsps.push_back(h); keys.push_back(key); } }
-        if (iSeq >= 0) flush(false, iSeq); } } }
+        if (iSeq >= 0) flush(false, iSeq); } } });
     size_t ncl = 0, njb = 0; for (size_t si = 0; si < segCl.size(); si++) { ncl += segCl[si].size(); njb += segJobs[si].size(); } clusters.reserve(ncl); jobs.reserve(njb);
     for (size_t si = 0; si < segCl.size(); si++) { int jo = (int)jobs.size(); for (HostCluster& cl : segCl[si]) { for (HostHsp& h : cl.hsps) if (h.job >= 0) h.job += jo; clusters.push_back(std::move(cl)); } jobs.insert(jobs.end(), segJobs[si].begin(), segJobs[si].end()); } }
   lap("contig mapping");
@@ -1274,8 +1291,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   T.mark();                                                                                              // [5] extend + wfa
   // ---- finishing: scores, filters, ordering, rows (lib-index-search.go:2266-2357, :2701-2932; search.go:437-533)
   const double lnK = std::log(0.41), totalBases = (double)I.total_bases;
-#pragma omp parallel for schedule(static) num_threads(std::max(1, std::min(16, omp_get_max_threads())))
-  for (i64 cli = 0; cli < (i64)clusters.size(); cli++) { HostCluster& cl = clusters[cli]; i32 qlen = 0; const WinItem& w = items[cl.item]; qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); double maxSim = 0; bool has = false;
+  ix->pool.run(HT, HT, [&](int ci) { for (i64 cli = (i64)clusters.size() * ci / HT, cE = (i64)clusters.size() * (ci + 1) / HT; cli < cE; cli++) { HostCluster& cl = clusters[cli]; i32 qlen = 0; const WinItem& w = items[cl.item]; qlen = (i32)(B.h_off[w.q + 1] - B.h_off[w.q]); double maxSim = 0; bool has = false;
     for (HostHsp& h : cl.hsps) { if (h.dead) continue; const WfaOut& o = hw[h.job]; const ExtOut& e = hext[h.job]; i32 ql = e.qe - e.qs, tl = e.te - e.ts;
       if (!o.has_m) { h.dead = true; continue; }   // trimOps == nil -> evalue MaxFloat64 > max_evalue
       int _s = o.bscore; if (_s & 1) _s--; double bs = (0.625 * (double)_s - lnK) / M_LN2; h.score = o.bscore; h.bitscore = (int)bs; h.evalue = totalBases * std::pow(2, -bs) * (double)ql; if (h.evalue > prm->max_evalue) { h.dead = true; continue; }
@@ -1287,15 +1303,14 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
         std::vector<u64> ops(hops.begin() + o.ops_off, hops.begin() + o.ops_off + o.ops_n); std::reverse(ops.begin(), ops.end()); int a = -1, b = -1; for (size_t i = 0; i < ops.size(); i++) if ((ops[i] >> 32) == 'M') { if (a < 0) a = (int)i; b = (int)i; }
         for (int i = a; i >= 0 && i <= b; i++) { char c = (char)(ops[i] >> 32); if (c == 'D') c = 'I'; else if (c == 'I') c = 'D'; h.cigar += std::to_string((u32)(ops[i] & 0xffffffffu)); h.cigar.push_back(c); } }
       double sim = (double)h.bitscore * h.pident; if (sim > maxSim) maxSim = sim; has = true; }
-    cl.has = has; cl.sim = maxSim; }
+    cl.has = has; cl.sim = maxSim; } });
   lap("score clusters");
   // group clusters per segment -> genomes -> queries; whole queries are independent, so static chunks of queries run in parallel
   struct GenomeOut { u32 seg; std::vector<const HostCluster*> sds; double af; };
-  const int NTF = std::max(1, std::min(32, omp_get_max_threads())); std::vector<size_t> cut(NTF + 1, clusters.size()); cut[0] = 0;
+  const int NTF = HT; std::vector<size_t> cut(NTF + 1, clusters.size()); cut[0] = 0;
   for (int t = 1; t < NTF; t++) { size_t x = clusters.size() * t / NTF; while (x > 0 && x < clusters.size() && (u32)(S.h_key[clusters[x].seg] >> 36) == (u32)(S.h_key[clusters[x - 1].seg] >> 36)) x++; cut[t] = std::max(x, cut[t - 1]); }
   std::vector<std::vector<lmg_hsp>> trows(NTF); std::vector<std::string> tpool(NTF); std::vector<std::vector<u32>> trg(NTF);
-#pragma omp parallel for schedule(static, 1) num_threads(NTF)
-  for (int ti = 0; ti < NTF; ti++) {
+  ix->pool.run(NTF, HT, [&](int ti) {
     std::vector<GenomeOut> gouts; std::vector<lmg_hsp>& rows = trows[ti]; std::string& pool = tpool[ti]; std::vector<u32>& rg = trg[ti];
     { size_t x = cut[ti]; while (x < cut[ti + 1]) { u32 seg = clusters[x].seg; GenomeOut g; g.seg = seg; g.af = 0; size_t y = x; while (y < cut[ti + 1] && clusters[y].seg == seg) { if (clusters[y].has) g.sds.push_back(&clusters[y]); y++; } x = y; if (g.sds.empty()) continue;
         u32 q = (u32)(S.h_key[seg] >> 36); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
@@ -1313,7 +1328,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
         int cls = 1, j = 1; for (const HostCluster* sd : ord) { for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[gd].size(); r.chunk_idx = 0; r.n_chunks = 1; r.seq_len = (i32)I.seq_sizes[gd][sd->iseq];
             r.cls = cls; r.hsp = j; r.qb = h.qb; r.qe = h.qe; r.tb = h.tb; r.te = h.te; r.rc = sd->rc; r.alen = h.alen; r.matches = h.matched; r.gaps = h.gaps; r.score = h.score; r.bitscore = h.bitscore; r.evalue = h.evalue; r.qcov_hsp = h.af; r.pident = h.pident; r.qcov_gnm = g->af;
             r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; rows.push_back(r); rg.push_back(gd); j++; } cls++; } }
-      x = y; } }
+      x = y; } });
   { size_t nr = 0; for (auto& v : trows) nr += v.size(); R.rows.reserve(nr); R.row_genome.reserve(nr); for (int ti = 0; ti < NTF; ti++) { u64 po = R.pool.size(); for (lmg_hsp& r : trows[ti]) { r.cigar_off += po; R.rows.push_back(r); } R.pool += tpool[ti]; R.row_genome.insert(R.row_genome.end(), trg[ti].begin(), trg[ti].end()); } R.img = &I; }
   lap("group+rows");
   T.mark(); finish_times(7);                                                                             // [6] finish (host)
@@ -1339,10 +1354,10 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
 }
 static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }
 static lmg_index* lane_ctx(lmg_index* ix, int l) { if (l == 0) return ix; while ((int)ix->lanes.size() < l) { ix->lanes.push_back(make_ctx(ix->imgp, false, ix->img.device)); ix->lanes.back()->lane_id = (int)ix->lanes.size(); } return ix->lanes[l - 1]; }
-// number of concurrent sub-batches: explicit (params.lanes / LMG_LANES) or up to 3 for batches big enough to amortise the split
-// (measured on the 10,000 x 1-kb bench: 1 lane 175 ms, 2 lanes 134 ms, 3 lanes 127 ms, 4 lanes 140 ms per batch; exclusive GPU phases were slower)
-static int pick_lanes(const lmg_params* p, int nq, u64 bases) { int L = (p && p->lanes > 0) ? p->lanes : 0; if (!L) { const char* e = getenv("LMG_LANES"); if (e) L = atoi(e); } bool forced = L > 0; if (!L) L = 3; L = std::max(1, std::min(L, 8));
-  if (!forced) while (L > 1 && (nq < 1000 * L || bases < (u64)1000000 * L)) L--; return std::max(1, std::min(L, std::max(nq, 1))); }
+// number of concurrent sub-batches: explicit (params.lanes / LMG_LANES) or up to 6 for batches big enough to amortise the split
+// (10,000 x 1-kb bench, ms per batch: 1 lane 124-140, 3 lanes 102, 4 lanes 88, 6 lanes 81-84, 8 lanes 85, 12 lanes 87; exclusive GPU phases were slower)
+static int pick_lanes(const lmg_params* p, int nq, u64 bases) { int L = (p && p->lanes > 0) ? p->lanes : 0; if (!L) { const char* e = getenv("LMG_LANES"); if (e) L = atoi(e); } bool forced = L > 0; if (!L) L = 6; L = std::max(1, std::min(L, 16));
+  if (!forced) while (L > 1 && (nq < 800 * L || bases < (u64)800000 * L)) L--; return std::max(1, std::min(L, std::max(nq, 1))); }
 static std::vector<int> lane_cuts(const u64* off, int nq, int L) { std::vector<int> cut(L + 1, nq); cut[0] = 0; u64 tot = off[nq] - off[0]; int q = 0; for (int l = 1; l < L; l++) { u64 want = off[0] + tot * l / L; while (q < nq && off[q] < want) q++; cut[l] = std::max(q, cut[l - 1]); } return cut; }
 
 int lmg_index_open(const char* dir, int device, int shard, int n_shards, lmg_index** out) {
