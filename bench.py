@@ -251,6 +251,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_probe = float(np.mean(probe_ms)) * 1e-3
     achieved = alg_bytes / t_probe / 1e9 if t_probe > 0 else 0.0
+    traffic = None   # DRAM bytes of the kernel per step from the committed `ncu --set full` capture of this workload (profiles/), if present
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if tr.get("workload_queries") == CFG["n_queries"] and tr.get("workload_genomes") == CFG["families"] * CFG["members"]:
+            traffic = float(tr["dram_bytes_per_step"])   # per step, like algorithmic_bytes_per_step (a step launches the kernel once per lane)
+    except Exception:
+        pass
     # the same kernel alone on the GPU (one lane, so no other lane's kernels share the SMs / HBM during its launches)
     p1 = idx.default_params(lanes=1)
     iso = []
@@ -269,7 +276,7 @@ def main():
            "e2e": {"value": bp_all / (t_e2e * 1e-3), "unit": "bp/s", "h2d_bytes_per_step": int(packed[0].nbytes + packed[1].nbytes), "d2h_bytes_per_step": int(nrows * 136), "ms_per_step": t_e2e},
            "gpu_launches": launches, "rows_per_step": rows_all,
            "stage_ms": {k: float(v) / a.steps for k, v in zip(["h2d", "sketch", "seed_probe", "chain", "pseudo_align", "extend_wfa", "host_finish", "total"], stage_ms)},
-           "roofline": {"bound": "hbm", "kernel": "k_probe_find2 (seed index lookup of the surviving probes)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "roofline": {"bound": "hbm", "kernel": "k_probe_find2 (seed index lookup of the surviving probes)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": t_probe * 1e3, "launches_per_step": config_lanes,
                         "alone": {"kernel_ms": t_iso * 1e3, "achieved": alg_bytes / t_iso / 1e9 if t_iso > 0 else 0.0, "frac": (alg_bytes / t_iso / 1e9 / peak) if t_iso > 0 else 0.0, "note": "same batch through one lane: no concurrent kernels"}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},

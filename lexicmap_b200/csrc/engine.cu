@@ -278,7 +278,10 @@ struct HostPool {
 struct lmg_index {
   Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
   double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
-  int host_threads() const { int hc = (int)std::thread::hardware_concurrency(); if (hc <= 0) hc = 8; return std::max(1, std::min(32, hc / (2 * std::max(1, active_lanes)))); }   // workers per lane: half the cores over the active lanes
+  // workers per lane: half of this process's cores over the active lanes. LMG_HOST_CORES (or OMP_NUM_THREADS, which launchers such as torchrun
+  // set per rank) tells how many cores the process may use when several ranks share a node.
+  int host_threads() const { static const int hc = [] { int v = 0; if (const char* e = getenv("LMG_HOST_CORES")) v = atoi(e); if (v <= 0) if (const char* e = getenv("OMP_NUM_THREADS")) v = atoi(e); if (v <= 0) v = (int)std::thread::hardware_concurrency(); return v > 0 ? v : 8; }();
+    return std::max(1, std::min(32, hc / (2 * std::max(1, active_lanes)))); }
   lmg_index(Image* p, bool own) : imgp(p), img(*p), owner(own) {}
 };
 
