@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
 // Wavefronts live in HBM as u16 offsets in a fixed-stride layout: level L (score 2L), component c, diagonal k at
 // slab[L*3*WFS + c*WFS + k + WFK0]; every level writes [glo-PAD, ghi+PAD] (NULL outside its reach) so neither the forward pass nor
 // the backtrace needs bounds checks or a directory. The last 5 M levels and 2 I/D levels are mirrored in shared memory (ring).
-// Jobs that do not fit (|k| >= 128, score >= 2*WF_LMAX, sequences >= 65000) report status 1 and go to the general kernel k_wfa.
+// Jobs that do not fit (|k| >= 128, score >= 2*WF_LMAX, sequences >= 32000) report status 1 and go to the general kernel k_wfa.
 #define WF_WMAX 256
 #define WF_PAD 8
 #define WFS (WF_WMAX + 2 * WF_PAD)
@@ -1027,12 +1027,13 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
       const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
       if (nqw + nA + ntw <= WF_SEQW) { u64* sq = seqb; for (u32 i = lane; i < nqw + nA; i += 32) sq[i] = Q[i]; for (u32 i = lane; i < ntw; i += 32) sq[nqw + nA + i] = T[i]; __syncwarp(); Q = sq; A = sq + nqw; T = sq + nqw + nA; } }
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
-    if (plen >= 65000 || tlen >= 65000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    if (plen >= 32000 || tlen >= 32000 || kend <= -(WF_WMAX / 2) + 2 || kend >= WF_WMAX / 2 - 2 || plen <= 0 || tlen <= 0) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
     auto extend = [&](i32 k, i32 h) { i32 v = h - k; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
     // level 0. History of levels L-1..L-4: effective lo/hi (after reduction), null bits (1 M, 2 I, 4 D). Every level writes the diagonals
     // [min(lo, rlo) - PAD, max(hi, rhi) + PAD] where [rlo,rhi] spans the effective ranges of the last 4 non-null levels, so later levels and
     // the backtrace can read k-1 / k+1 of any source level without bounds checks.
     i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
+    for (int t = lane; t < 9 * WFS / 2; t += 32) ((u32*)&R[0][0])[t] = 0xFFFFFFFFu; __syncwarp();   // every ring row starts null: levels below 0 need no special case
     { i32 h0 = 0; if (lane == 0) h0 = extend(0, 0); h0 = __shfl_sync(FULLMASK, h0, 0);
       for (i32 k = -WF_PAD + lane; k <= WF_PAD; k += 32) { u16 mv = (k == 0) ? (u16)h0 : (u16)0xFFFF; R[0][k + WFK0] = mv; slab[k + WFK0] = mv; slab[WFS + k + WFK0] = 0xFFFF; slab[2 * WFS + k + WFK0] = 0xFFFF; R[5][k + WFK0] = 0xFFFF; R[7][k + WFK0] = 0xFFFF; }
       hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; __syncwarp(); }
@@ -1051,9 +1052,10 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
       for (i32 k = k0; k <= wh + WF_PAD; k += 32, itb <<= 1) {
         u16 om = 0xFFFF, oi = 0xFFFF, od = 0xFFFF, dd = 0xFFFF; int x = k + WFK0;
         if (!allnull && k >= lo && k <= hi) {
-          i32 a = (L >= OE2) ? (i32)M4[x - 1] : 0xFFFF, b = (i32)I1[x - 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 ins = max(a, b); ins = (ins < 0) ? -1 : ins + 1;
-          a = (L >= OE2) ? (i32)M4[x + 1] : 0xFFFF; b = (i32)D1[x + 1]; a = (a == 0xFFFF) ? -1 : a; b = (b == 0xFFFF) ? -1 : b; i32 del = max(a, b);
-          i32 mis = (L >= X2) ? (i32)M2[x] : 0xFFFF; mis = (mis == 0xFFFF) ? -1 : mis + 1;
+          // offsets are < 32000 here, so the u16 cells read as signed 16-bit give -1 for NULL (0xFFFF) directly
+          i32 ins = max((i32)(i16)M4[x - 1], (i32)(i16)I1[x - 1]); ins = (ins < 0) ? -1 : ins + 1;
+          i32 del = max((i32)(i16)M4[x + 1], (i32)(i16)D1[x + 1]);
+          i32 mis = (i32)(i16)M2[x]; mis = (mis < 0) ? -1 : mis + 1;
           const i32 hmax = min(tlen, plen + k);   // h <= tlen and v = h - k <= plen; h >= 0 and v >= 0 hold by construction
           if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
           i32 mm = max(mis, max(ins, del)); if (mm >= 0) { mm = extend(k, mm); bitM |= itb; om = (u16)mm; i32 dv = max(plen - (mm - k), tlen - mm); dd = (u16)dv; mind = min(mind, dv); } if (ins >= 0) { bitI |= itb; oi = (u16)ins; } if (del >= 0) { bitD |= itb; od = (u16)del; }
@@ -1224,18 +1226,19 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<C2Rec> c2;
   if (NA > 0) {
     // compact layout for everything but the raw anchors: cbeg = exclusive prefix sum of the per-window counts
-    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); std::vector<u64> hcbeg(nit + 1, 0); std::vector<u32> bins[4];
-    for (u32 i = 0; i < nit; i++) { u32 c = hcnt[i]; hcbeg[i + 1] = hcbeg[i] + c; if (c) bins[c <= 64 ? 0 : c <= 512 ? 1 : c <= 4096 ? 2 : 3].push_back(i); }
+    DBuf<u64> aend(nit, st); aend.from_host(haend.data(), nit); std::vector<u64> hcbeg(nit + 1, 0); std::vector<u32> bins[5];
+    for (u32 i = 0; i < nit; i++) { u32 c = hcnt[i]; hcbeg[i + 1] = hcbeg[i] + c; if (c) bins[c <= 64 ? 0 : c <= 256 ? 1 : c <= 1024 ? 2 : c <= 4096 ? 3 : 4].push_back(i); }
     DBuf<u64> cbeg(nit + 1, st); cbeg.from_host(hcbeg.data(), nit + 1); DBuf<u64> lo1(NA + 2, st);
-    { std::vector<u32> all; u32 boff[5] = {0, 0, 0, 0, 0}; for (int k3 = 0; k3 < 4; k3++) { all.insert(all.end(), bins[k3].begin(), bins[k3].end()); boff[k3 + 1] = (u32)all.size(); } DBuf<u32> dl(all.size() + 1, st); dl.from_host(all.data(), all.size());
+    { std::vector<u32> all; u32 boff[6] = {0, 0, 0, 0, 0, 0}; for (int k3 = 0; k3 < 5; k3++) { all.insert(all.end(), bins[k3].begin(), bins[k3].end()); boff[k3 + 1] = (u32)all.size(); } DBuf<u32> dl(all.size() + 1, st); dl.from_host(all.data(), all.size());
       if (boff[1] > boff[0]) { k_pa_sort<64, 32><<<cdiv(boff[1] - boff[0], 4), 128, 4 * 64 * 8, st>>>(dl.p + boff[0], boff[1] - boff[0], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
-      if (boff[2] > boff[1]) { k_pa_sort<512, 128><<<boff[2] - boff[1], 128, 512 * 8, st>>>(dl.p + boff[1], boff[2] - boff[1], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
-      if (boff[3] > boff[2]) { k_pa_sort<4096, 256><<<boff[3] - boff[2], 256, 4096 * 8, st>>>(dl.p + boff[2], boff[3] - boff[2], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
-      if (boff[4] > boff[3]) {   // rare: > 4096 anchors in one window
+      if (boff[2] > boff[1]) { k_pa_sort<256, 128><<<boff[2] - boff[1], 128, 256 * 8, st>>>(dl.p + boff[1], boff[2] - boff[1], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[3] > boff[2]) { k_pa_sort<1024, 256><<<boff[3] - boff[2], 256, 1024 * 8, st>>>(dl.p + boff[2], boff[3] - boff[2], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[4] > boff[3]) { k_pa_sort<4096, 512><<<boff[4] - boff[3], 512, 4096 * 8, st>>>(dl.p + boff[3], boff[4] - boff[3], abeg.p, cbeg.p, cnt.p, lo0.p, lo1.p); KERNEL_CHECK(); }
+      if (boff[5] > boff[4]) {   // rare: > 4096 anchors in one window
         std::vector<u64> hb(nit), he(nit); for (u32 i = 0; i < nit; i++) { hb[i] = hcbeg[i]; he[i] = hcnt[i] > 4096 ? hcbeg[i + 1] : hcbeg[i]; } DBuf<u64> sb(nit, st), se(nit, st), tmpc(NA + 2, st); sb.from_host(hb.data(), nit); se.from_host(he.data(), nit);
-        k_pa_gather<<<boff[4] - boff[3], 256, 0, st>>>(dl.p + boff[3], boff[4] - boff[3], abeg.p, cbeg.p, cnt.p, lo0.p, tmpc.p); KERNEL_CHECK();
+        k_pa_gather<<<boff[5] - boff[4], 256, 0, st>>>(dl.p + boff[4], boff[5] - boff[4], abeg.p, cbeg.p, cnt.p, lo0.p, tmpc.p); KERNEL_CHECK();
         size_t tb = 0; cub::DeviceSegmentedSort::SortKeys(nullptr, tb, tmpc.p, lo1.p, (int)NA, (int)nit, sb.p, se.p, st); cub::DeviceSegmentedSort::SortKeys(ix->tmp.get(tb), tb, tmpc.p, lo1.p, (int)NA, (int)nit, sb.p, se.p, st); CUB_CHECK(); CUDA_CHECK(cudaStreamSynchronize(st)); }
-      if (dbgt) fprintf(stderr, "[lmg host] pa anchors %llu in %u windows (%.1f GB of slots): bins %zu / %zu / %zu / %zu\n", (unsigned long long)NA, nit, habeg[nit] * 8e-9, bins[0].size(), bins[1].size(), bins[2].size(), bins[3].size()); }
+      if (dbgt) fprintf(stderr, "[lmg host] pa anchors %llu in %u windows (%.1f GB of slots): bins %zu / %zu / %zu / %zu / %zu\n", (unsigned long long)NA, nit, habeg[nit] * 8e-9, bins[0].size(), bins[1].size(), bins[2].size(), bins[3].size(), bins[4].size()); }
     if (dbgt) cudaStreamSynchronize(st); lap("k4 seg sort");
     Chain2Params P2; P2.max_gap = prm->align_max_gap; P2.min_score = (int)((double)prm->align_min_len * prm->min_pident / 100); P2.min_align_len = prm->align_min_len; P2.band_base = prm->align_band; P2.band_count = prm->align_band / 2; P2.k = K;
     DBuf<i32> sc(NA + 2, st); DBuf<u32> pred(NA + 2, st); DBuf<u64> stack(NA + 2, st); u32 capc = (u32)std::min<u64>(NA, 0x7fffffffu); DBuf<C2Rec> d_c2(capc, st); DBuf<u32> nout(1, st); nout.zero();
@@ -1352,7 +1355,7 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
   if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
   // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
   auto raise = [&](const void* f) { cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, f)); CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin - fa.sharedSizeBytes))); };
-  if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 256>); }
+  if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 512>); }
   return ix;
 }
 static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }

@@ -154,3 +154,8 @@ def test_long_queries_match_oracle(long_case):
     _rows_equal(gr, orr, gs, os_, gc, oc)
     ga, oa = g.anchors(seqs), o.anchors(seqs)
     assert ga.tobytes() == oa.tobytes()
+    # the 3-kb reads alone: tables of ~5,900 rows still take the fused capture kernel (shared-memory table + owner array)
+    s3 = seqs[:6]
+    gr, gs, gc = g.search(s3, g.default_params(output_seq=1))
+    orr, os_, oc = o.search(s3, o.default_params(output_seq=1), threads=8)
+    _rows_equal(gr, orr, gs, os_, gc, oc)
