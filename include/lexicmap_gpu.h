@@ -62,7 +62,8 @@ typedef struct lmg_hsp {
   int32_t  rc;          /* sstr: 0 '+', 1 '-' */
   int32_t  alen, matches, gaps, score, bitscore, pad0;
   double   evalue, qcov_hsp, pident, qcov_gnm;
-  uint64_t cigar_off;   /* into the string pool; SAM convention (I/D already swapped, lib-index-search.go:2331-2338) */
+  uint64_t cigar_off;   /* into the string pool; SAM convention (I/D already swapped, lib-index-search.go:2331-2338). With output_seq the
+                           pool entry of a row is cigar (cigar_len bytes) | qseq | sseq | align (alen bytes each; cigar.AlignmentText, :2342-2346) */
   uint32_t cigar_len;
   uint32_t pad;
 } lmg_hsp;

@@ -31,6 +31,18 @@ ANCHOR_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("qbegin", "<i4"),
 CHAIN_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("score", "<f4"), ("n_seeds", "<i4"), ("q0", "<i4"), ("t0", "<i4"), ("len0", "<i4"),
                         ("q1", "<i4"), ("t1", "<i4"), ("len1", "<i4"), ("rc", "<i4")])
 
+def split_align_text(rows, pool):
+    """with output_seq the pool entry of a row is cigar | qseq | sseq | align (alen bytes each); returns [(qseq, sseq, align)] or None"""
+    if not len(rows) or len(pool) < int(rows["cigar_off"][-1]) + int(rows["cigar_len"][-1]) + 3 * int(rows["alen"][-1]) or not int(rows["cigar_len"].max()):
+        return None
+    out = []
+    for o, l, a in zip(rows["cigar_off"], rows["cigar_len"], rows["alen"]):
+        b = int(o) + int(l)
+        a = int(a)
+        out.append((pool[b:b + a].decode(), pool[b + a:b + 2 * a].decode(), pool[b + 2 * a:b + 3 * a].decode()))
+    return out
+
+
 _lib = None
 
 
@@ -173,6 +185,7 @@ class Index:
             self.lib.lmg_results_seq_id(r, i, C.byref(s))
             seqids.append(s.value.decode())
         cig = [pool[int(o):int(o) + int(l)].decode() for o, l in zip(rows["cigar_off"], rows["cigar_len"])]
+        self.last_align_text = split_align_text(rows, pool)
         self.lib.lmg_results_free(r)
         return rows, seqids, cig
 
@@ -182,8 +195,8 @@ class Index:
         self.lib.lmg_last_timing(self.h, ms.ctypes.data, cnt.ctypes.data)
         return ms, cnt
 
-    def format_tsv(self, rows, seqids, qids, qlens, cigars=None):
-        """printResult (search.go:437-533): 20 columns (+cigar with -a)."""
+    def format_tsv(self, rows, seqids, qids, qlens, cigars=None, texts=None):
+        """printResult (search.go:437-533): 20 columns; with -a also cigar, qseq, sseq, align (`texts` = self.last_align_text)."""
         out = []
         for i, r in enumerate(rows):
             q = int(r["query"])
@@ -192,6 +205,8 @@ class Index:
                 r["qb"] + 1, r["qe"] + 1, r["tb"] + 1, r["te"] + 1, "-" if r["rc"] else "+", r["seq_len"], r["evalue"], r["bitscore"])
             if cigars is not None:
                 line += "\t" + cigars[i]
+                if texts is not None:
+                    line += "\t%s\t%s\t%s" % texts[i]
             out.append(line)
         return out
 

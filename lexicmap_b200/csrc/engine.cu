@@ -254,7 +254,7 @@ __global__ void k_probe_emit(ProbeParams P, const ProbeHit* __restrict__ hits, c
 // =====================================================================================================
 struct QBatch {  // device-side query batch
   int nq = 0; u64 total_bases = 0, total_k = 0;
-  DBuf<u8> ascii, packed, amask; DBuf<u64> off, boff, koff; std::vector<u64> h_off, h_boff, h_koff;
+  DBuf<u8> ascii, packed, amask; DBuf<u64> off, boff, koff; std::vector<u64> h_off, h_boff, h_koff; std::vector<u8> h_ascii;   // h_ascii: host copy of the query bytes (alignment text of -a output)
   DBuf<u64> qkeys; DBuf<u32> qvals;    // per-query sorted (k-mer, loc) tables
 };
 
@@ -301,7 +301,7 @@ static void upload_queries(lmg_index* ix, const u8* seqs, const u64* off, int nq
   for (int q = 0; q < nq; q++) { u64 L = B.h_off[q + 1] - B.h_off[q]; if (L >= (1ull << 27)) throw std::runtime_error("query longer than 2^27 bases is not supported");
     B.h_boff[q] = b; b += (((L + 3) >> 2) + 16 + 15) & ~15ull; B.h_koff[q] = kk; kk += (L >= (u64)k) ? 2 * (L - k + 1) : 0; }
   B.h_boff[nq] = b; B.h_koff[nq] = kk; B.total_k = kk;
-  B.ascii.alloc(B.total_bases + 16, st); B.ascii.from_host(seqs + off[0], B.total_bases); B.off.alloc(nq + 1, st); B.off.from_host(B.h_off.data(), nq + 1);
+  B.h_ascii.assign(seqs + off[0], seqs + off[0] + B.total_bases); B.ascii.alloc(B.total_bases + 16, st); B.ascii.from_host(B.h_ascii.data(), B.total_bases); B.off.alloc(nq + 1, st); B.off.from_host(B.h_off.data(), nq + 1);
   B.boff.alloc(nq + 1, st); B.boff.from_host(B.h_boff.data(), nq + 1); B.koff.alloc(nq + 1, st); B.koff.from_host(B.h_koff.data(), nq + 1);
   B.packed.alloc(b + 64, st); B.packed.zero(); B.amask.alloc(b + 64, st); B.amask.zero();
 }
@@ -1168,7 +1168,7 @@ static void build_tree_tables(lmg_index* ix, QBatch& B, DBuf<u64>& tkeys, DBuf<u
   k_tree_offsets<<<cdiv(B.nq + 1, 128), 128, 0, st>>>(pos.p, B.koff.p, B.nq, n, total, toff.p); KERNEL_CHECK(); CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-struct HostHsp { i32 qb, qe, tb, te, aligned_q, tpo, max_ext; int job = -1; bool dead = false; i32 alen = 0, matched = 0, gaps = 0, score = 0, bitscore = 0; double evalue = 0, af = 0, pident = 0; std::string cigar; };
+struct HostHsp { i32 qb, qe, tb, te, aligned_q, tpo, max_ext; int job = -1; bool dead = false; i32 alen = 0, matched = 0, gaps = 0, score = 0, bitscore = 0; double evalue = 0, af = 0, pident = 0; std::string cigar, text; };   // text = qseq | sseq | align, alen bytes each (-a output)
 struct HostCluster { u32 seg; u32 item; bool rc, variantA; int nseeds, iseq; std::vector<HostHsp> hsps; double sim = 0; bool has = false; };
 
 struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u32> row_genome; const Image* img = nullptr; };   // sseqid of row i = img->seq_ids[row_genome[i]][rows[i].seq_idx]
@@ -1307,7 +1307,14 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
       if (h.af < prm->min_qcov_hsp || h.pident < prm->min_pident) { h.dead = true; continue; }
       if (prm->output_seq) { // ops were written last-op-first; trim to first M..last M; swap I/D for SAM (:2331-2338)
         std::vector<u64> ops(hops.begin() + o.ops_off, hops.begin() + o.ops_off + o.ops_n); std::reverse(ops.begin(), ops.end()); int a = -1, b = -1; for (size_t i = 0; i < ops.size(); i++) if ((ops[i] >> 32) == 'M') { if (a < 0) a = (int)i; b = (int)i; }
-        for (int i = a; i >= 0 && i <= b; i++) { char c = (char)(ops[i] >> 32); if (c == 'D') c = 'I'; else if (c == 'I') c = 'D'; h.cigar += std::to_string((u32)(ops[i] & 0xffffffffu)); h.cigar.push_back(c); } }
+        // alignment text (cigar.AlignmentText(&_qseq, &_tseq, true), :2342): first M .. last M over the query bytes and the target strand that was aligned
+        const u8* qs = B.h_ascii.data() + B.h_off[w.q]; const u8* g2h = I.h_g2bit.data() + I.h_g_off[w.g]; i32 qi = h.qb; const i64 t0 = (i64)h.tpo + h.tb, t1 = (i64)h.tpo + h.te; i64 ti = 0; std::string qt, tt, at; qt.reserve(h.alen); tt.reserve(h.alen); at.reserve(h.alen);
+        auto qch = [&](i32 x) -> char { char c = (char)qs[x]; return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; };   // the reference upper-cases the query on input (search.go:582-587)
+        auto tch = [&](i64 x) -> char { i64 pos = cl.rc ? t1 - x : t0 + x; u32 bb = (g2h[pos >> 2] >> (6 - 2 * (pos & 3))) & 3; return "ACGT"[cl.rc ? 3 - bb : bb]; };
+        for (int i = a; i >= 0 && i <= b; i++) { char c = (char)(ops[i] >> 32); u32 n = (u32)(ops[i] & 0xffffffffu);
+          for (u32 x = 0; x < n; x++) { if (c == 'M' || c == 'X') { qt.push_back(qch(qi++)); tt.push_back(tch(ti++)); at.push_back(c == 'M' ? '|' : ' '); } else if (c == 'I') { qt.push_back('-'); tt.push_back(tch(ti++)); at.push_back(' '); } else { qt.push_back(qch(qi++)); tt.push_back('-'); at.push_back(' '); } }
+          if (c == 'D') c = 'I'; else if (c == 'I') c = 'D'; h.cigar += std::to_string(n); h.cigar.push_back(c); }
+        h.text = qt + tt + at; }
       double sim = (double)h.bitscore * h.pident; if (sim > maxSim) maxSim = sim; has = true; }
     cl.has = has; cl.sim = maxSim; } });
   lap("score clusters");
@@ -1333,7 +1340,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
         for (size_t i = 0; i < g->sds.size(); i++) { if (used[i]) continue; for (size_t j = i; j < g->sds.size(); j++) if (!used[j] && g->sds[j]->iseq == g->sds[i]->iseq) { used[j] = 1; ord.push_back(g->sds[j]); } }
         int cls = 1, j = 1; for (const HostCluster* sd : ord) { for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[gd].size(); r.chunk_idx = 0; r.n_chunks = 1; r.seq_len = (i32)I.seq_sizes[gd][sd->iseq];
             r.cls = cls; r.hsp = j; r.qb = h.qb; r.qe = h.qe; r.tb = h.tb; r.te = h.te; r.rc = sd->rc; r.alen = h.alen; r.matches = h.matched; r.gaps = h.gaps; r.score = h.score; r.bitscore = h.bitscore; r.evalue = h.evalue; r.qcov_hsp = h.af; r.pident = h.pident; r.qcov_gnm = g->af;
-            r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; rows.push_back(r); rg.push_back(gd); j++; } cls++; } }
+            r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; pool += h.text; rows.push_back(r); rg.push_back(gd); j++; } cls++; } }
       x = y; } });
   { size_t nr = 0; for (auto& v : trows) nr += v.size(); R.rows.reserve(nr); R.row_genome.reserve(nr); for (int ti = 0; ti < NTF; ti++) { u64 po = R.pool.size(); for (lmg_hsp& r : trows[ti]) { r.cigar_off += po; R.rows.push_back(r); } R.pool += tpool[ti]; R.row_genome.insert(R.row_genome.end(), trg[ti].begin(), trg[ti].end()); } R.img = &I; }
   lap("group+rows");

@@ -23,6 +23,7 @@ struct Image {
   u8* d_g2bit = nullptr; u64* d_g_off = nullptr; u32 *d_g_nbases = nullptr, *d_g_seq_off = nullptr, *d_seq_sizes = nullptr; u32* d_batch_base = nullptr;
   // host metadata
   std::vector<u64> h_masks; std::vector<std::string> genome_names; std::vector<u64> genome_bgi; std::vector<std::vector<std::string>> seq_ids; std::vector<std::vector<u32>> seq_sizes;
+  std::vector<u8> h_g2bit; std::vector<u64> h_g_off;   // host copy of the 2-bit genomes: alignment text of the -a output
   std::vector<u32> batch_base, h_nbases; std::unordered_map<u64, u32> bgi2dense; lmi::IndexInfo info;
 
   template <class T> T* up(const std::vector<T>& h) { T* d = nullptr; size_t b = std::max<size_t>(h.size(), 1) * sizeof(T) + 64; CUDA_CHECK(cudaMalloc((void**)&d, b)); if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); bytes += b; return d; }
@@ -44,7 +45,7 @@ struct Image {
     }
     { auto gm = lmi::read_genome_map(dir + "/genomes.map.bin"); for (auto& e : gm) { auto it = bgi2dense.find(e.second); if (it != bgi2dense.end()) genome_names[it->second] = e.first; } }
     g2bit.resize(g2bit.size() + 64, 0); g_off.push_back(g2bit.size()); G = (int)genome_bgi.size();
-    h_nbases = g_nbases; d_g2bit = up(g2bit); d_g_off = up(g_off); d_g_nbases = up(g_nbases); d_g_seq_off = up(g_seq_off); d_seq_sizes = up(seqsz); d_batch_base = up(batch_base);
+    h_nbases = g_nbases; h_g_off = g_off; h_g2bit = g2bit; d_g2bit = up(g2bit); d_g_off = up(g_off); d_g_nbases = up(g_nbases); d_g_seq_off = up(g_seq_off); d_seq_sizes = up(seqsz); d_batch_base = up(batch_base);
     // ---- seeds: decode every chunk (host, one thread per chunk), flatten
     std::vector<lmi::KvChunk> chunks(info.chunks);
 #pragma omp parallel for schedule(dynamic, 1)

@@ -20,7 +20,7 @@ static void usage() {
           "lexicmap-gpu search: B200 implementation of `lexicmap search` (same flags, same TSV)\n\n"
           "Usage:\n  lexicmap-gpu search -d <index.lmi> [flags] <query.fasta[.gz]> ...\n\nFlags (defaults as the reference):\n"
           "  -d, --index string                 index directory created by `lexicmap index`\n  -o, --out-file string              out file (default \"-\")\n"
-          "  -a, --all                          output more columns: cigar (qseq/sseq/align are not produced by the GPU path yet)\n"
+          "  -a, --all                          output more columns: cigar, qseq, sseq, align\n"
           "      --show-sseq-idx                prefix sseqid with c<chunk>/<chunks>:s<seq>/<seqs>:\n"
           "  -p, --seed-min-prefix int          (default 15)\n  -P, --seed-min-single-prefix int   (default 17)\n      --seed-max-gap int             (default 50)\n      --seed-max-dist int            (default 1000)\n"
           "  -n, --top-n-genomes int            (default 0)\n  -N, --top-n-chains int             (default 0)\n      --align-ext-len int            (default 1000)\n      --align-max-gap int            (default 20)\n"
@@ -69,7 +69,7 @@ int main(int argc, char** argv) {
       fprintf(out, "%s\t%llu\t%u\t%s\t", ids[h.query].c_str(), (unsigned long long)(off[h.query + 1] - off[h.query]), h.hits, gname);
       if (o.show_idx) fprintf(out, "c%u/%u:s%u/%u:", h.chunk_idx + 1, h.n_chunks, h.seq_idx + 1, h.n_seqs);
       fprintf(out, "%s\t%.3f\t%d\t%d\t%.3f\t%d\t%.3f\t%d\t%d\t%d\t%d\t%d\t%c\t%d\t%.2e\t%d", sid, h.qcov_gnm, h.cls, h.hsp, h.qcov_hsp, h.alen, h.pident, h.gaps, h.qb + 1, h.qe + 1, h.tb + 1, h.te + 1, h.rc ? '-' : '+', h.seq_len, h.evalue, h.bitscore);
-      if (o.all) { fprintf(out, "\t"); fwrite(pool + h.cigar_off, 1, h.cigar_len, out); fprintf(out, "\t\t\t"); }
+      if (o.all) { const char* t = pool + h.cigar_off + h.cigar_len; fprintf(out, "\t"); fwrite(pool + h.cigar_off, 1, h.cigar_len, out); for (int x = 0; x < 3; x++) { fprintf(out, "\t"); fwrite(t + (size_t)x * h.alen, 1, h.alen, out); } }   // pool entry: cigar | qseq | sseq | align
       fprintf(out, "\n"); }
     lmg_results_free(r); total += ids.size(); ids.clear(); seqs.clear(); off.assign(1, 0); fflush(out);
   };

@@ -108,7 +108,13 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
           c.aligned_q = c.qe - c.qb + 1; c.aligned_len = cg.align_len; c.matched = cg.matches; c.gaps = cg.gaps; c.af = (double)c.aligned_q / (double)qlen * 100; if (c.af > 100) c.af = 100;
           c.pident = (double)c.matched / (double)cg.align_len * 100;
           if (c.af < P.min_qcov_hsp || c.pident < P.min_pident) { c.dead = true; continue; }
-          if (P.output_seq) { c.cigar.clear(); for (uint64_t op : trim_ops(cg.ops)) { char o = (char)(op >> 32); if (o == 'D') o = 'I'; else if (o == 'I') o = 'D'; c.cigar += std::to_string((uint32_t)(op & 0xffffffffu)); c.cigar.push_back(o); } }
+          if (P.output_seq) { c.cigar.clear(); c.qseq.clear(); c.tseq.clear(); c.align.clear(); int qi = ex.start1 + cg.qbegin - 1, ti = ex.start2 + cg.tbegin - 1;   // AlignmentText(&_qseq, &_tseq, true): first M .. last M
+            for (uint64_t op : trim_ops(cg.ops)) { char o = (char)(op >> 32); uint32_t n = (uint32_t)(op & 0xffffffffu);
+              for (uint32_t x = 0; x < n; x++) {   // WFA ops: I consumes the target only, D the query only (swapped below for SAM, :2331-2338)
+                if (o == 'M' || o == 'X') { c.qseq.push_back((char)s[qi++]); c.tseq.push_back((char)tseq[ti++]); c.align.push_back(o == 'M' ? '|' : ' '); }
+                else if (o == 'I') { c.qseq.push_back('-'); c.tseq.push_back((char)tseq[ti++]); c.align.push_back(' '); }
+                else { c.qseq.push_back((char)s[qi++]); c.tseq.push_back('-'); c.align.push_back(' '); } }
+              if (o == 'D') o = 'I'; else if (o == 'I') o = 'D'; c.cigar += std::to_string(n); c.cigar.push_back(o); } }
           double sim = (double)c.bitscore * c.pident; if (sim > maxSim) maxSim = sim; hasResult = true;
         }
         if (hasResult) { SD sd; sd.rc = rc; sd.nseeds = nSeeds; sd.sim = maxSim; sd.seq_idx = iSeqUse; sd.nseqs = (int)gm.seq_ids.size(); sd.seqlen = gm.seq_sizes[iSeqUse]; sd.seqid = gm.seq_ids[iSeqUse]; sd.chains = chains2; r.sds.push_back(std::move(sd)); }
@@ -170,7 +176,7 @@ static void rows_of(uint32_t q, const std::vector<GenomeRes>& res, Rows& R) {  /
   for (const GenomeRes& r : res) { int cls = 1, j = 1;
     for (const SD& sd : r.sds) { for (const Chain2& c : sd.chains) { if (c.dead) continue; lmo_hsp h; memset(&h, 0, sizeof h); h.query = q; h.hits = (uint32_t)res.size(); h.genome = r.bgi; h.seq_idx = sd.seq_idx; h.n_seqs = sd.nseqs; h.chunk_idx = 0; h.n_chunks = 1; h.seq_len = sd.seqlen;
         h.cls = cls; h.hsp = j; h.qb = c.qb; h.qe = c.qe; h.tb = c.tb; h.te = c.te; h.rc = sd.rc; h.alen = c.aligned_len; h.matches = c.matched; h.gaps = c.gaps; h.score = c.score; h.bitscore = c.bitscore; h.evalue = c.evalue;
-        h.qcov_hsp = c.af; h.pident = c.pident; h.qcov_gnm = r.af; h.cigar_off = R.pool.size(); h.cigar_len = (uint32_t)c.cigar.size(); R.pool += c.cigar; R.rows.push_back(h); R.seqids.push_back(sd.seqid); j++; } cls++; } }
+        h.qcov_hsp = c.af; h.pident = c.pident; h.qcov_gnm = r.af; h.cigar_off = R.pool.size(); h.cigar_len = (uint32_t)c.cigar.size(); R.pool += c.cigar; R.pool += c.qseq; R.pool += c.tseq; R.pool += c.align; /* pool entry: cigar | qseq | sseq | align (alen bytes each) */ R.rows.push_back(h); R.seqids.push_back(sd.seqid); j++; } cls++; } }
 }
 }  // namespace
 

@@ -120,9 +120,14 @@ class Oracle:
         seqids = [self.lib.lmo_row_seqid(r, i).decode() for i in range(n)]
         cig = []
         if n:
-            end = int(rows["cigar_off"][-1] + rows["cigar_len"][-1])
+            has_text = int(rows["cigar_len"].max()) > 0
+            end = int(rows["cigar_off"][-1] + rows["cigar_len"][-1]) + (3 * int(rows["alen"][-1]) if has_text else 0)
             pool = C.string_at(pool_p, end) if end else b""
             cig = [pool[int(o):int(o) + int(l)].decode() for o, l in zip(rows["cigar_off"], rows["cigar_len"])]
+            self.last_align_text = []
+            for o, l, a in zip(rows["cigar_off"], rows["cigar_len"], rows["alen"]):
+                b, a = int(o) + int(l), int(a)
+                self.last_align_text.append((pool[b:b + a].decode(), pool[b + a:b + 2 * a].decode(), pool[b + 2 * a:b + 3 * a].decode()) if has_text else ("", "", ""))
         self.lib.lmo_rows_free(r)
         return rows, seqids, cig
 
@@ -192,7 +197,7 @@ class Oracle:
         return n, lens[:min(n, cap)], vals[:min(n, cap)]
 
 
-def format_tsv(rows, seqids, qids, qlens, genome_name, cigars=None):
+def format_tsv(rows, seqids, qids, qlens, genome_name, cigars=None, texts=None):
     """Reference TSV rows (search.go:426-518)."""
     out = []
     for i, r in enumerate(rows):
@@ -202,5 +207,7 @@ def format_tsv(rows, seqids, qids, qlens, genome_name, cigars=None):
             r["qb"] + 1, r["qe"] + 1, r["tb"] + 1, r["te"] + 1, "-" if r["rc"] else "+", r["seq_len"], r["evalue"], r["bitscore"])
         if cigars is not None:
             line += "\t" + cigars[i]
+            if texts is not None:
+                line += "\t%s\t%s\t%s" % texts[i]
         out.append(line)
     return out

@@ -72,6 +72,7 @@ def test_search_rows_match_oracle(gpu_small, oracle_small, small_queries):
     orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
     assert len(orr) > 50
     _rows_equal(gr, orr, gs, os_, gc, oc)
+    assert gpu_small.last_align_text == oracle_small.last_align_text   # qseq / sseq / align columns of the -a output
 
 
 @pytest.mark.parametrize("lanes", [2, 3, 5])

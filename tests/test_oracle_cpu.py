@@ -140,7 +140,7 @@ def test_oracle_reproduces_reference_demo_rows(tmp_path):
     o = Oracle(idx)
     ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.gene.fasta"))
     rows, sid, cig = o.search(seqs, o.default_params(output_seq=1), threads=8)
-    mine = format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name, cig)
+    mine = format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name, cig, o.last_align_text)
 
     def key(f):
         return (f[0], f[3], f[4], f[12], f[13], f[14], f[15], f[16])
@@ -157,6 +157,7 @@ def test_oracle_reproduces_reference_demo_rows(tmp_path):
     for f in gold_a:
         if key(f) in mm:
             assert mm[key(f)][20] == f[20], "CIGAR differs"
+            assert mm[key(f)][21:24] == f[21:24], "qseq / sseq / align text differs"   # cigar.AlignmentText of the absent wfa module, pinned by the golden -a rows
             n += 1
     assert n == 14
 
@@ -166,6 +167,24 @@ def test_oracle_small_fixture_regression(oracle_small, small_queries):
     ids, seqs = small_queries
     rows, sid, cig = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
     mine = format_tsv(rows, sid, ids, [len(s) for s in seqs], oracle_small.genome_name, cig)
+    # alignment text is consistent with the CIGAR (incl. gap columns, which the reference's golden -a rows do not contain)
+    import re
+    for c, (qs, ts, al), r in zip(cig, oracle_small.last_align_text, rows):
+        assert len(qs) == len(ts) == len(al) == r["alen"]
+        pos = 0
+        for n_, op in re.findall(r"(\d+)([MXID])", c):
+            n_ = int(n_)
+            seg_q, seg_t, seg_a = qs[pos:pos + n_], ts[pos:pos + n_], al[pos:pos + n_]
+            if op == "M":
+                assert seg_a == "|" * n_ and seg_q.upper() == seg_t
+            elif op == "X":
+                assert seg_a == " " * n_ and all(a.upper() != b for a, b in zip(seg_q, seg_t))
+            elif op == "I":
+                assert seg_t == "-" * n_ and "-" not in seg_q and seg_a == " " * n_
+            else:
+                assert seg_q == "-" * n_ and "-" not in seg_t and seg_a == " " * n_
+            pos += n_
+        assert pos == r["alen"] and qs.replace("-", "").upper() == seqs[r["query"]][r["qb"]:r["qe"] + 1].upper()
     gold = os.path.join(GOLD, "small_expected.tsv")
     if os.environ.get("LMG_REGEN_GOLDEN"):
         open(gold, "w").write("\n".join(mine) + "\n")
