@@ -17,7 +17,7 @@ typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t
 // blocks had to be re-mapped between calls; a grow-only arena that is reset after every batch is deterministic.
 struct Arena {
   struct Chunk { char* base; size_t size; };
-  std::vector<Chunk> chunks; size_t cur = 0, off = 0;
+  std::vector<Chunk> chunks; size_t cur = 0, off = 0; u64 epoch = 1;   // epoch: bumped by reset(); a buffer from an earlier epoch is already gone and must not rewind the cursor
   static size_t al(size_t b) { return (b + 511) & ~(size_t)511; }
   void* alloc(size_t bytes) {
     bytes = al(bytes + 64);
@@ -28,7 +28,7 @@ struct Arena {
     void* p = chunks[cur].base + off; off += bytes; return p;
   }
   void free(void* p, size_t bytes) { bytes = al(bytes + 64); if (cur < chunks.size() && (char*)p + bytes == chunks[cur].base + off) off -= bytes; }   // LIFO frees are recycled
-  void reset() { cur = 0; off = 0; if (chunks.size() > 1) { size_t tot = 0; for (auto& c : chunks) { tot += c.size; cudaFree(c.base); } chunks.clear(); Chunk c; c.size = tot; if (cudaMalloc((void**)&c.base, tot) == cudaSuccess) chunks.push_back(c); else cudaGetLastError(); } }
+  void reset() { cur = 0; off = 0; epoch++; if (chunks.size() > 1) { size_t tot = 0; for (auto& c : chunks) { tot += c.size; cudaFree(c.base); } chunks.clear(); Chunk c; c.size = tot; if (cudaMalloc((void**)&c.base, tot) == cudaSuccess) chunks.push_back(c); else cudaGetLastError(); } }
   void release() { for (auto& c : chunks) cudaFree(c.base); chunks.clear(); cur = off = 0; }
 };
 static thread_local Arena* g_arena = nullptr;
@@ -36,17 +36,17 @@ struct ArenaScope { Arena* prev; ArenaScope(Arena* a) : prev(g_arena) { g_arena 
 
 // device buffer: from the current arena when one is active, otherwise stream-ordered cudaMallocAsync
 template <class T> struct DBuf {
-  T* p = nullptr; size_t n = 0; cudaStream_t st = 0; Arena* ar = nullptr;
+  T* p = nullptr; size_t n = 0; cudaStream_t st = 0; Arena* ar = nullptr; u64 ep = 0;
   DBuf() {}
   DBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
-  void alloc(size_t n_, cudaStream_t s) { free(); n = n_; st = s; if (!n) return; if (g_arena) { ar = g_arena; p = (T*)ar->alloc(n * sizeof(T)); } else { ar = nullptr; CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T) + 64, s)); } }
-  void free() { if (p) { if (ar) ar->free(p, n * sizeof(T)); else cudaFreeAsync(p, st); p = nullptr; n = 0; ar = nullptr; } }
+  void alloc(size_t n_, cudaStream_t s) { free(); n = n_; st = s; if (!n) return; if (g_arena) { ar = g_arena; ep = ar->epoch; p = (T*)ar->alloc(n * sizeof(T)); } else { ar = nullptr; CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T) + 64, s)); } }
+  void free() { if (p) { if (ar) { if (ar->epoch == ep) ar->free(p, n * sizeof(T)); } else cudaFreeAsync(p, st); p = nullptr; n = 0; ar = nullptr; } }
   void zero() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
   void fill_ff() { if (p) CUDA_CHECK(cudaMemsetAsync(p, 0xff, n * sizeof(T), st)); }
   ~DBuf() { free(); }
   DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; ar = o.ar; o.p = nullptr; o.n = 0; }
-  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; st = o.st; ar = o.ar; o.p = nullptr; o.n = 0; } return *this; }
+  DBuf(DBuf&& o) noexcept { p = o.p; n = o.n; st = o.st; ar = o.ar; ep = o.ep; o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; st = o.st; ar = o.ar; ep = o.ep; o.p = nullptr; o.n = 0; } return *this; }
   std::vector<T> to_host(size_t cnt = (size_t)-1) const { if (cnt == (size_t)-1) cnt = n; std::vector<T> h(cnt); if (cnt) { CUDA_CHECK(cudaMemcpyAsync(h.data(), p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st)); } return h; }
   void from_host(const T* h, size_t cnt) { if (cnt) CUDA_CHECK(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st)); }
 };

@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap,
 // in ten), tests its anchor bit and emits the suffix probe. Nothing per (query, mask) slot goes to HBM — only the surviving probes do.
 // DUMP additionally writes the per-slot capture arrays for lmg_mask_batch.
 template <bool DUMP>
-__global__ void __launch_bounds__(256) k_capture2(const u64* __restrict__ qkeys, const u64* __restrict__ koff, const u64* __restrict__ masks, ProbeParams P, CapSoA cap, u32* __restrict__ owner_g, u32 max_n, int use_tma,
+__global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys, const u64* __restrict__ koff, const u64* __restrict__ masks, ProbeParams P, CapSoA cap, u32* __restrict__ owner_g, u32 max_n, int use_tma,
                                                   const u32* __restrict__ mask_pstart, int mask_pbits, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
-  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; u32* own = (u32*)(stab + max_n); __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024]; __shared__ u32 lcb[256];   // lcb: low-complexity flag per table row (rows <= 8192)
+  extern __shared__ __align__(128) u8 smem_raw[]; u64* stab = (u64*)smem_raw; u32* own = (u32*)(stab + max_n); __shared__ __align__(8) u64 mbar; __shared__ u32 pst[1025], pen[1024]; __shared__ u32 lcb[512];   // lcb: low-complexity flag per table row (rows <= 16384)
   const int q = blockIdx.x, m = P.m, k = P.k, lane = threadIdx.x & 31; const u64 o = koff[q]; const u32 n = (u32)(koff[q + 1] - o);
   if (n == 0) { if (DUMP) for (int i = threadIdx.x; i < m; i += blockDim.x) { u64 w = (u64)q * m + i; cap.kmer[w] = 0; cap.lo[w] = 0; cap.n[w] = 0; cap.smask[w] = 0; } return; }
   if (use_tma) { if (threadIdx.x == 0) mbar_init(&mbar, 1); __syncthreads(); if (threadIdx.x == 0) { u32 bytes = ((n * 8u) + 15u) & ~15u; tma_load_1d(stab, qkeys + o, bytes, &mbar); } for (u32 t = threadIdx.x; t < n; t += blockDim.x) own[t] = 0xFFFFFFFFu; mbar_wait(&mbar, 0); }
@@ -286,6 +286,8 @@ struct lmg_index {
 };
 
 static thread_local std::string g_err;
+// a sub-batch whose intermediate lists exceed a 2^31 index space or the device arena: the caller halves it and retries
+struct BatchTooLarge : std::runtime_error { using std::runtime_error::runtime_error; };
 // host-side lap timer (LMG_DEBUG_TIMING=1): prints the wall time since the previous lap of the calling thread
 struct LapTimer { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); bool on = getenv("LMG_DEBUG_TIMING") != nullptr; int lane = 0;
   void operator()(const char* what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lmg host L%d] %-18s %.2f ms\n", lane, what, std::chrono::duration<double, std::milli>(n - t0).count()); t0 = n; } };
@@ -338,7 +340,8 @@ static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Sur
   ProbeParams P = probe_params(I, prm->min_prefix); const u64 nslot = (u64)B.nq * I.m, nprobe = nslot * 2; DBuf<u32> nsv(1, st); DBuf<u64> dstats(8, st);
   if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); cudaEventCreate(&ix->kev[2]); }
   u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
-  const bool fused = maxn <= 8192 && maxn * 12 + 16384 <= ix->smem_optin && !getenv("LMG_NO_FUSED_CAPTURE"); ix->ms[8] = 0;
+  const bool fused = maxn <= 16384 && maxn * 12 + 16384 <= ix->smem_optin && !getenv("LMG_NO_FUSED_CAPTURE"); ix->ms[8] = 0;
+  const int cthreads = maxn <= 4096 ? 256 : 1024;   // big tables leave room for one CTA per SM only: make it a full one
   if (dump_cap) { dump_cap->kmer.alloc(nslot, st); dump_cap->lo.alloc(nslot, st); dump_cap->n.alloc(nslot, st); dump_cap->smask.alloc(nslot, st); dump_owner->alloc(B.total_k + 2, st); dump_owner->fill_ff(); }
   CapBufs capl; DBuf<u32> ownl; CapBufs* cap = dump_cap ? dump_cap : &capl; DBuf<u32>* owner = dump_owner ? dump_owner : &ownl;
   if (!fused) { if (!dump_cap) { capl.kmer.alloc(nslot, st); capl.lo.alloc(nslot, st); capl.n.alloc(nslot, st); capl.smask.alloc(nslot, st); ownl.alloc(B.total_k + 2, st); ownl.fill_ff(); }
@@ -350,8 +353,8 @@ static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Sur
   u64 capS = std::max<u64>(1u << 20, nprobe / 4);
   for (int attempt = 0; attempt < 2; attempt++) { SV.d.alloc(capS, st); nsv.zero(); dstats.zero();
     if (fused) { u32 mx = (u32)((maxn + 1) & ~1ull); size_t smem = (size_t)mx * 12 + 16;
-      if (dump_cap) { k_capture2<true><<<B.nq, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), owner->p, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); }
-      else { k_capture2<false><<<B.nq, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), nullptr, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); } }
+      if (dump_cap) { k_capture2<true><<<B.nq, cthreads, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), owner->p, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); }
+      else { k_capture2<false><<<B.nq, cthreads, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), nullptr, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); } }
     else { cudaEventRecord(ix->kev[0], st); k_probe_filter<<<cdiv((i64)nslot, 256), 256, 0, st>>>(P, cap->soa(), owner->p, B.koff.p, nslot, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); cudaEventRecord(ix->kev[1], st); }
     SV.n = nsv.to_host()[0]; if (SV.n <= capS) break; capS = nprobe; }
   if (!fused) { float fa = 0; cudaEventSynchronize(ix->kev[1]); cudaEventElapsedTime(&fa, ix->kev[0], ix->kev[1]); ix->ms[8] = fa; ix->counters[12] = (u64)(fa * 1000); } else ix->counters[12] = 0;
@@ -374,7 +377,7 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivor
   { DBuf<u64> cnt(nhit + 1, st); k_hit_counts<<<cdiv(nhit + 1, 256), 256, 0, st>>>(hits.p, nhit, cnt.p); KERNEL_CHECK();
     size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, hoff.p, (int)(nhit + 1), st); cub::DeviceScan::ExclusiveSum(ix->tmp.get(tb), tb, cnt.p, hoff.p, (int)(nhit + 1), st); CUB_CHECK(); }
   u64 total; CUDA_CHECK(cudaMemcpyAsync(&total, hoff.p + nhit, 8, cudaMemcpyDeviceToHost, st)); CUDA_CHECK(cudaStreamSynchronize(st));
-  A.n = total; if (stats) ix->counters[5] = total; if (total == 0) return; if (total >= (1ull << 31)) throw std::runtime_error("more than 2^31 anchors in one batch; use smaller batches");
+  A.n = total; if (stats) ix->counters[5] = total; if (total == 0) return; if (total >= (1ull << 31)) throw BatchTooLarge("more than 2^31 anchors in one batch; use smaller batches");
   DBuf<u64> hi0(total, st), lo0(total, st); A.hi.alloc(total, st); A.lo.alloc(total, st);
   k_probe_emit<<<cdiv(nhit, 128), 128, 0, st>>>(P, hits.p, hoff.p, nhit, B.qvals.p, B.koff.p, I.d_batch_base, hi0.p, lo0.p); KERNEL_CHECK();
   radix_sort_pairs(ix, lo0, A.lo, hi0, A.hi, total, 0, 64);             // by lo
@@ -645,6 +648,25 @@ __global__ void __launch_bounds__(128) k_pa_anchors2(const WinItem* __restrict__
   if (threadIdx.x == 0) counts[it] = s_base;
 }
 
+// helpers of k_pa_anchors3 (plain functions, no early returns around the barriers of the caller)
+__device__ __forceinline__ void pa3_push(u32* qu, u32* cnt, bool have, u32 e, int lane) {   // warp-aggregated append to a shared-memory queue
+  u32 bal = __ballot_sync(FULLMASK, have); u32 base = 0; int ldr = bal ? (__ffs(bal) - 1) : 0; if (bal && lane == ldr) base = atomicAdd(cnt, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr);
+  if (have) qu[base + __popc(bal & ((1u << lane) - 1))] = e;
+}
+__device__ __forceinline__ u64 pa3_key(const u32* sw, u32 e, u64 ttt) {   // k-mer (strand e&1) at window position e>>1
+  u32 idx = e >> 1; u32 wi = idx >> 4, sh = (idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2; return (e & 1) ? kmer_reverse62(~km & ttt, 31) : km;
+}
+// anchors of one candidate: table rows [l,h) share >= mp bases with `key`; keep those inside the query region, append to the window's slot range
+__device__ __forceinline__ void pa3_emit(const u64* sk, const u32* sv, u32 e, u64 key, u32 l, u32 h, u32 begin, u32 end, u32* s_base, u32 cap, u64* out_base) {
+  const int K = 31; const u32 idx = e >> 1; const bool rcs = e & 1; u32 c = 0;
+  for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); bool ok; if (!rcs) { u32 p = vv >> 1; ok = !((vv & 1) == 1 || p < begin || p + (u32)lp > end); } else { u32 p = (vv >> 1) + (u32)K - (u32)lp; ok = !((vv & 1) == 0 || p + (u32)lp < begin || p > end); } c += ok ? 1u : 0u; }
+  if (c) { u32 wpos = atomicAdd(s_base, c);
+    if ((u64)wpos + c <= (u64)cap) { u64* out = out_base + wpos;
+      for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]);
+        if (!rcs) { u32 p = vv >> 1; if (!((vv & 1) == 1 || p < begin || p + (u32)lp > end)) *out++ = pack_lo((i32)p, (u32)lp, (i32)idx, 0, 0); }
+        else { u32 p = (vv >> 1) + (u32)K - (u32)lp; if (!((vv & 1) == 0 || p + (u32)lp < begin || p > end)) *out++ = pack_lo((i32)p, (u32)lp, (i32)idx + K - lp, 1, 1); } } } }
+}
+
 // ---- K4 v3: one CTA per QUERY. The query's sorted (k-mer, loc) table is staged in shared memory once and reused by all of the query's
 // target windows (typically one per candidate genome), so every table probe is a shared-memory binary search instead of an L2 round trip.
 // Windows are packed into shared memory one at a time. Queries whose table does not fit use k_pa_anchors2 (table in L2).
@@ -668,33 +690,38 @@ __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
     __syncthreads();   // previous window fully consumed (and, first time, table loaded)
     i32 nw = (w.W + 15) / 16 + 2;
+#ifdef LMG_DEBUG_PA3
+    { u32 dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn)); if (threadIdx.x == 0 && ((size_t)max_tn * 12 + (size_t)nw * 4 > dyn || tn > max_tn)) printf("PA3 smem: max_tn %u tn %u nw %d dyn %u it %u W %d\n", max_tn, tn, nw, dyn, it, w.W); }
+#endif
     for (i32 x = threadIdx.x; x < nw; x += 256) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
     if (threadIdx.x == 0) { s_base = 0; nfast = 0; nslow = 0; } __syncthreads();
-    const i32 np = w.W - K + 1;
-    auto key_at = [&](u32 e) -> u64 { u32 idx = e >> 1; u32 wi = idx >> 4, sh = (idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2; return (e & 1) ? kmer_reverse62(~km & ttt, K) : km; };
-    auto emit = [&](u32 e, u64 key, u32 l, u32 h) { const u32 idx = e >> 1; u32 c = 0;
-      if (!(e & 1)) { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; } }
-      else { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; } }
-      if (!c) return; u32 wpos = atomicAdd(&s_base, c); if ((u64)wpos + c > (u64)cap) return; u64* out = a_lo + base0 + wpos;
-      if (!(e & 1)) { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = vv >> 1; if ((vv & 1) == 1 || p < begin || p + (u32)lp > end) continue; *out++ = pack_lo((i32)p, (u32)lp, (i32)idx, 0, 0); } }
-      else { for (u32 u = l; u < h; u++) { u32 vv = sv[u]; int lp = lcp31(key, sk[u]); u32 p = (vv >> 1) + (u32)K - (u32)lp; if ((vv & 1) == 0 || p + (u32)lp < begin || p > end) continue; *out++ = pack_lo((i32)p, (u32)lp, (i32)idx + K - lp, 1, 1); } } };
-    auto push = [&](u32* qu, u32* cnt, bool have, u32 e) { u32 bal = __ballot_sync(FULLMASK, have); if (!bal) return; u32 base = 0; int ldr = __ffs(bal) - 1; if (lane == ldr) base = atomicAdd(cnt, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr); if (have) qu[base + __popc(bal & ((1u << lane) - 1))] = e; };
-    auto drain = [&](bool all) {   // uniform across the CTA
-      __syncthreads(); u32 nf = nfast;
-      while (nf >= 256 || (all && nf > 0)) { u32 take = min(nf, 256u), start = nf - take; bool slow = false; u32 e = 0;
-        if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = key_at(e); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
+    const i32 np = w.W - K + 1; u64* const out_base = a_lo + base0;
+    for (i32 base = 0;; base += 256) {
+      const bool more = (base < np) && tn;   // uniform: another slice of window positions to scan
+      if (more) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
+        if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
+          if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
+            u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
+            hb = ((u32)(kr >> 40) * 2654435761u) >> 17; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
+        pa3_push(qfast, &nfast, c1, (u32)idx << 1, lane); pa3_push(qfast, &nfast, c2, ((u32)idx << 1) | 1u, lane); }
+      // drain: full chunks of 256 candidates while scanning, everything at the end. Every thread reads the counters between two barriers.
+      for (;;) {
+        __syncthreads(); const u32 nf = nfast, ns0 = nslow; __syncthreads();
+        const bool go = more ? (nf >= 256) : (nf > 0);
+        if (!go) { if (!more && ns0 > 0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } }
+          break; }
+        const u32 take = min(nf, 256u), start = nf - take; bool slow = false; u32 e = 0;
+        if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = pa3_key(sw, e, ttt); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
           while (x < y) { u32 m = (x + y) >> 1; if (sk[m] < left) x = m + 1; else y = m; } u32 en = x; while (en < tn && sk[en] <= right) en++;
-          if (en > x) emit(e, key, x, en); else slow = quirk_possible(sk, tn, x, key, p); }
-        __syncthreads(); if (threadIdx.x == 0) nfast = start; push(qslow, &nslow, slow, e); __syncthreads(); nf = start;
-        u32 ns = nslow; if (ns >= 256 || (all && nf == 0 && ns > 0)) { while (ns > 0) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = key_at(e2); u32 l, h; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) emit(e2, key, l, h); } ns = st2; } __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } }
-      if (all) { u32 ns = nslow; if (ns > 0) { while (ns > 0) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = key_at(e2); u32 l, h; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) emit(e2, key, l, h); } ns = st2; } __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } } };
-    for (i32 base = 0; base < np && tn; base += 256) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
-      if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
-        if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
-          u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
-          hb = ((u32)(kr >> 40) * 2654435761u) >> 17; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
-      push(qfast, &nfast, c1, (u32)idx << 1); push(qfast, &nfast, c2, ((u32)idx << 1) | 1u); drain(false); }
-    drain(true);
+          if (en > x) pa3_emit(sk, sv, e, key, x, en, begin, end, &s_base, cap, out_base); else slow = quirk_possible(sk, tn, x, key, p); }
+        __syncthreads(); if (threadIdx.x == 0) nfast = start; pa3_push(qslow, &nslow, slow, e, lane);
+        __syncthreads(); const u32 ns1 = nslow; __syncthreads();
+        if (ns1 >= 256) {   // the rare radix-tree emulations, again a full chunk at a time
+          for (u32 ns = ns1; ns > 0;) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; }
+          __syncthreads(); if (threadIdx.x == 0) nslow = 0; }
+      }
+      if (!more) break;
+    }
     __syncthreads(); if (threadIdx.x == 0) counts[it] = s_base;
   }
 }
@@ -1215,12 +1242,17 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   lap("k4 host prep");
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than W+226: capacities become the exact counts
     for (u32 i = 0; i < nit; i++) habeg[i + 1] = habeg[i] + hcap[i];
-    if (habeg[nit] >= (1ull << 31)) throw std::runtime_error("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
+    u64 slot_limit = 1ull << 31; if (const char* e = getenv("LMG_SLOT_LIMIT")) slot_limit = strtoull(e, nullptr, 10);   // test hook: forces the halving path on small batches
+    if (habeg[nit] >= slot_limit) throw BatchTooLarge("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
     { KTimer kt(st, &ix->ms[14]);
       if (!qlist.empty()) { k_pa_anchors3<<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); }
       if (!rest.empty()) { k_pa_anchors2<<<(u32)rest.size(), 128, smemW, st>>>(d_items.p, d_rest.p, (u32)rest.size(), I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); } }
-    hcnt = cnt.to_host(nit); bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
+    hcnt = cnt.to_host(nit);
+    if (getenv("LMG_DEBUG_PA3RUNS") && !qlist.empty()) { for (int rep = 0; rep < 3; rep++) { k_pa_anchors3<<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK();
+        std::vector<u32> h2 = cnt.to_host(nit); int nd = 0; for (u32 i = 0; i < nit; i++) if (h2[i] != hcnt[i]) { if (nd < 6) fprintf(stderr, "[pa3 debug L%d pass %d rep %d] item %u q %u W %d mp %d tn %u cap %u: %u vs %u\n", ix->lane_id, pass, rep, i, items[i].q, items[i].W, items[i].mp, htoff[items[i].q + 1] - htoff[items[i].q], hcap[i], hcnt[i], h2[i]); nd++; }
+        fprintf(stderr, "[pa3 debug L%d pass %d rep %d] %d of %u windows differ\n", ix->lane_id, pass, rep, nd, nit); } }
+    bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
     if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
   lap("pa_anchors");
   std::vector<C2Rec> c2;
@@ -1418,13 +1450,24 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
 struct lmg_queries { std::vector<QBatch> parts; std::vector<int> cut; };
 // Runs the pipeline over L sub-batches concurrently (one host thread, stream and arena per lane) and concatenates the rows in query order.
 // Queries are independent all the way through the reference path (search.go:437-533 handles one query at a time), so the split is exact.
+// one lane's share of a call; halves the range (recursively) when an intermediate list does not fit
+static void search_range(lmg_index* lx, const lmg_params* p, const u8* seqs, const u64* off, int n, lmg_results& R, QBatch* staged) {
+  try { ArenaReset ar_(lx); search_pipeline(lx, p, seqs, off, n, R, staged); return; }
+  catch (BatchTooLarge& e) { if (n < 2) throw std::runtime_error(std::string(e.what()) + " (a single query)"); }
+  if (staged) { seqs = staged->h_ascii.data(); off = staged->h_off.data(); }   // the host copy made at upload time
+  R = lmg_results(); const u64 mid = off[0] + (off[n] - off[0]) / 2; int h = 1; while (h < n - 1 && off[h] < mid) h++;
+  lmg_results R2; double ms[16]; u64 cn[16]; search_range(lx, p, seqs, off, h, R, nullptr); for (int i = 0; i < 16; i++) { ms[i] = lx->ms[i]; cn[i] = lx->counters[i]; }
+  search_range(lx, p, seqs, off + h, n - h, R2, nullptr); for (int i = 0; i < 16; i++) if (i != 12) { lx->ms[i] += ms[i]; if (i != 14) lx->counters[i] += cn[i]; }
+  u64 po = R.pool.size(); for (lmg_hsp& r : R2.rows) { r.query += (u32)h; r.cigar_off += po; R.rows.push_back(r); } R.pool += R2.pool; R.row_genome.insert(R.row_genome.end(), R2.row_genome.begin(), R2.row_genome.end()); R.img = &lx->img;
+}
+
 static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, const u64* off, int nq, lmg_results& R, lmg_queries* staged) {
   auto w0 = std::chrono::steady_clock::now(); const int dev = ix->img.device; CUDA_CHECK(cudaSetDevice(dev));
   std::vector<int> cut = staged ? staged->cut : lane_cuts(off, nq, pick_lanes(p, nq, off[nq] - off[0])); const int L = (int)cut.size() - 1;
-  if (L == 1) { ix->active_lanes = 1; ArenaReset ar_(ix); search_pipeline(ix, p, seqs, off, nq, R, staged ? &staged->parts[0] : nullptr); }
+  if (L == 1) { ix->active_lanes = 1; search_range(ix, p, seqs, off, nq, R, staged ? &staged->parts[0] : nullptr); }
   else {
     std::vector<lmg_results> Rl(L); std::vector<std::string> err(L); std::vector<lmg_index*> lx(L); for (int l = 0; l < L; l++) { lx[l] = lane_ctx(ix, l); lx[l]->active_lanes = L; }
-    auto work = [&](int l) { try { CUDA_CHECK(cudaSetDevice(dev)); ArenaReset ar_(lx[l]); int n = cut[l + 1] - cut[l]; if (n > 0) search_pipeline(lx[l], p, seqs, staged ? nullptr : off + cut[l], n, Rl[l], staged ? &staged->parts[l] : nullptr); else { for (double& m : lx[l]->ms) m = 0; for (u64& c : lx[l]->counters) c = 0; } }
+    auto work = [&](int l) { try { CUDA_CHECK(cudaSetDevice(dev)); int n = cut[l + 1] - cut[l]; if (n > 0) search_range(lx[l], p, seqs, staged ? nullptr : off + cut[l], n, Rl[l], staged ? &staged->parts[l] : nullptr); else { for (double& m : lx[l]->ms) m = 0; for (u64& c : lx[l]->counters) c = 0; } }
       catch (std::exception& e) { err[l] = e.what(); if (err[l].empty()) err[l] = "error"; cudaGetLastError(); } };
     std::vector<std::thread> th; for (int l = 1; l < L; l++) th.emplace_back(work, l); work(0); for (auto& t : th) t.join();
     for (int l = 0; l < L; l++) if (!err[l].empty()) throw std::runtime_error(err[l]);

@@ -94,6 +94,23 @@ def test_search_lanes_match_oracle(gpu_small, oracle_small, small_queries, lanes
     _rows_equal(gr, orr, gs, os_, gc, oc)
 
 
+def test_oversized_batch_is_halved(gpu_small, oracle_small, small_queries):
+    """a sub-batch whose pseudo-alignment slot space would overflow is split in two and retried (recursively); rows are unchanged.
+    LMG_SLOT_LIMIT lowers the 2^31 limit so that the 29-query batch has to be halved several times."""
+    ids, seqs = small_queries
+    orr, os_, oc = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
+    os.environ["LMG_SLOT_LIMIT"] = "60000"
+    try:
+        gr, gs, gc = gpu_small.search(seqs, gpu_small.default_params(output_seq=1))
+        q = gpu_small.stage(seqs)
+        gr2, gs2, gc2 = gpu_small.search_staged(q, gpu_small.default_params(output_seq=1, lanes=2))
+        gpu_small.free_staged(q)
+    finally:
+        del os.environ["LMG_SLOT_LIMIT"]
+    _rows_equal(gr, orr, gs, os_, gc, oc)
+    _rows_equal(gr2, orr, gs2, os_, gc2, oc)
+
+
 def test_search_filters_match_oracle(gpu_small, oracle_small, small_queries):
     ids, seqs = small_queries
     kw = dict(min_qcov_hsp=50.0, min_pident=80.0, min_qcov_genome=60.0, top_n_genomes=3, max_evalue=1e-20)
