@@ -670,33 +670,31 @@ __device__ __forceinline__ void pa3_emit(const u64* sk, const u32* sv, u32 e, u6
 // ---- K4 v3: one CTA per QUERY. The query's sorted (k-mer, loc) table is staged in shared memory once and reused by all of the query's
 // target windows (typically one per candidate genome), so every table probe is a shared-memory binary search instead of an L2 round trip.
 // Windows are packed into shared memory one at a time. Queries whose table does not fit use k_pa_anchors2 (table in L2).
-__global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
+template <int NT>   // threads per CTA: 256, or 1024 when the table leaves room for a single CTA per SM anyway (5-kb queries)
+__global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
                                                      const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn) {
   __shared__ u32 s_base; __shared__ u32 bloom[1024]; __shared__ u32 pdir[257];   // bloom: 32768 bits over hashed 11-base prefixes; pdir: first table row of every 4-base prefix
   extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
   const u32 q = qlist[blockIdx.x]; const u32 t0q = toff[q], tn = toff[q + 1] - t0q; const int K = 31;
-  for (u32 i = threadIdx.x; i < 1024; i += 256) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += 256) pdir[i] = tn;
-  for (u32 i = threadIdx.x; i < tn; i += 256) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
+  for (u32 i = threadIdx.x; i < 1024; i += NT) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += NT) pdir[i] = tn;
+  for (u32 i = threadIdx.x; i < tn; i += NT) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
   __syncthreads();
-  for (u32 i = threadIdx.x; i < tn; i += 256) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> 17; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
+  for (u32 i = threadIdx.x; i < tn; i += NT) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> 17; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
   __syncthreads();
   if (threadIdx.x == 0) { u32 nxt = tn; for (int b = 255; b >= 0; b--) { if (pdir[b] == tn) pdir[b] = nxt; else nxt = pdir[b]; } pdir[256] = tn; }   // empty buckets -> start of the next one
   const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const int lane = threadIdx.x & 31;
   // Work compaction: most window positions fail the Bloom / prefix pre-check, and of those that search the table only a few take the
   // radix-tree emulation. Doing everything in one pass ran at ~10 active lanes per instruction; instead positions that pass the pre-check
   // are queued (position << 1 | strand) and searched 256 at a time, and the rare slow-path searches are queued again.
-  __shared__ u32 qfast[1024], qslow[768]; __shared__ u32 nfast, nslow;
+  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nfast, nslow;
   for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
     __syncthreads();   // previous window fully consumed (and, first time, table loaded)
     i32 nw = (w.W + 15) / 16 + 2;
-#ifdef LMG_DEBUG_PA3
-    { u32 dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn)); if (threadIdx.x == 0 && ((size_t)max_tn * 12 + (size_t)nw * 4 > dyn || tn > max_tn)) printf("PA3 smem: max_tn %u tn %u nw %d dyn %u it %u W %d\n", max_tn, tn, nw, dyn, it, w.W); }
-#endif
-    for (i32 x = threadIdx.x; x < nw; x += 256) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
+    for (i32 x = threadIdx.x; x < nw; x += NT) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
     if (threadIdx.x == 0) { s_base = 0; nfast = 0; nslow = 0; } __syncthreads();
     const i32 np = w.W - K + 1; u64* const out_base = a_lo + base0;
-    for (i32 base = 0;; base += 256) {
+    for (i32 base = 0;; base += NT) {
       const bool more = (base < np) && tn;   // uniform: another slice of window positions to scan
       if (more) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
         if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
@@ -707,17 +705,17 @@ __global__ void __launch_bounds__(256) k_pa_anchors3(const WinItem* __restrict__
       // drain: full chunks of 256 candidates while scanning, everything at the end. Every thread reads the counters between two barriers.
       for (;;) {
         __syncthreads(); const u32 nf = nfast, ns0 = nslow; __syncthreads();
-        const bool go = more ? (nf >= 256) : (nf > 0);
-        if (!go) { if (!more && ns0 > 0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } }
+        const bool go = more ? (nf >= NT) : (nf > 0);
+        if (!go) { if (!more && ns0 > 0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } }
           break; }
-        const u32 take = min(nf, 256u), start = nf - take; bool slow = false; u32 e = 0;
+        const u32 take = min(nf, (u32)NT), start = nf - take; bool slow = false; u32 e = 0;
         if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = pa3_key(sw, e, ttt); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
           while (x < y) { u32 m = (x + y) >> 1; if (sk[m] < left) x = m + 1; else y = m; } u32 en = x; while (en < tn && sk[en] <= right) en++;
           if (en > x) pa3_emit(sk, sv, e, key, x, en, begin, end, &s_base, cap, out_base); else slow = quirk_possible(sk, tn, x, key, p); }
         __syncthreads(); if (threadIdx.x == 0) nfast = start; pa3_push(qslow, &nslow, slow, e, lane);
         __syncthreads(); const u32 ns1 = nslow; __syncthreads();
-        if (ns1 >= 256) {   // the rare radix-tree emulations, again a full chunk at a time
-          for (u32 ns = ns1; ns > 0;) { u32 tk = min(ns, 256u), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; }
+        if (ns1 >= NT) {   // the rare radix-tree emulations, again a full chunk at a time
+          for (u32 ns = ns1; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; }
           __syncthreads(); if (threadIdx.x == 0) nslow = 0; }
       }
       if (!more) break;
@@ -1228,7 +1226,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<u32> htoff = toff.to_host(B.nq + 1); std::vector<u64> hhoff(B.nq + 1, 0); for (int q = 0; q < B.nq; q++) { u32 n = htoff[q + 1] - htoff[q]; u64 H = 0; if (n) { H = 16; while (H < 2ull * n) H <<= 1; } hhoff[q + 1] = hhoff[q] + H; }
   // queries -> item ranges (items are ordered by (query, genome)); per-query kernel when table + window fit in shared memory
   std::vector<u32> qbeg(B.nq, 0), qend(B.nq, 0), qlist, rest; { u32 i = 0; while (i < nit) { u32 q = items[i].q, j = i; while (j < nit && items[j].q == q) j++; qbeg[q] = i; qend[q] = j; i = j; } }
-  u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 2048, 200 * 1024);
+  u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 36 * 1024, 190 * 1024);   // dynamic part; the 1,024-thread variant has 33 KB of static queues
   for (int q = 0; q < B.nq; q++) if (qend[q] > qbeg[q]) { u32 tn = htoff[q + 1] - htoff[q]; i32 mw = 0; for (u32 i = qbeg[q]; i < qend[q]; i++) mw = std::max(mw, items[i].W); size_t need = (size_t)tn * 12 + ((size_t)(mw + 15) / 16 + 2) * 4 + 64;
       if (need <= smem_cap3) { qlist.push_back(q); max_tn = std::max(max_tn, tn); maxW3 = std::max(maxW3, mw); } else for (u32 i = qbeg[q]; i < qend[q]; i++) rest.push_back(i); }
   if (rest.empty()) std::fill(hhoff.begin(), hhoff.end(), 0);   // the L2-resident hash index is only needed by the fallback kernel
@@ -1237,7 +1235,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>((i64)std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
   size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
   DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
-  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
+  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 36 * 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
   DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
   lap("k4 host prep");
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than W+226: capacities become the exact counts
@@ -1246,12 +1244,10 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     if (habeg[nit] >= slot_limit) throw BatchTooLarge("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
     { KTimer kt(st, &ix->ms[14]);
-      if (!qlist.empty()) { k_pa_anchors3<<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); }
+      if (!qlist.empty()) { if (smem3 > 64 * 1024) { k_pa_anchors3<1024><<<(u32)qlist.size(), 1024, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); }
+        else { k_pa_anchors3<256><<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); } }
       if (!rest.empty()) { k_pa_anchors2<<<(u32)rest.size(), 128, smemW, st>>>(d_items.p, d_rest.p, (u32)rest.size(), I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); } }
     hcnt = cnt.to_host(nit);
-    if (getenv("LMG_DEBUG_PA3RUNS") && !qlist.empty()) { for (int rep = 0; rep < 3; rep++) { k_pa_anchors3<<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK();
-        std::vector<u32> h2 = cnt.to_host(nit); int nd = 0; for (u32 i = 0; i < nit; i++) if (h2[i] != hcnt[i]) { if (nd < 6) fprintf(stderr, "[pa3 debug L%d pass %d rep %d] item %u q %u W %d mp %d tn %u cap %u: %u vs %u\n", ix->lane_id, pass, rep, i, items[i].q, items[i].W, items[i].mp, htoff[items[i].q + 1] - htoff[items[i].q], hcap[i], hcnt[i], h2[i]); nd++; }
-        fprintf(stderr, "[pa3 debug L%d pass %d rep %d] %d of %u windows differ\n", ix->lane_id, pass, rep, nd, nit); } }
     bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
     if (!over) break; if (pass == 1) throw std::runtime_error("pseudo-alignment anchor capacity overflow after exact sizing"); for (u32 i = 0; i < nit; i++) hcap[i] = hcnt[i]; }
   lap("pa_anchors");
@@ -1394,7 +1390,7 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
   if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
   // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
   auto raise = [&](const void* f) { cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, f)); CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin - fa.sharedSizeBytes))); };
-  if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3); raise((const void*)k_pa_sort<4096, 512>); }
+  if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3<256>); raise((const void*)k_pa_anchors3<1024>); raise((const void*)k_pa_sort<4096, 512>); }
   return ix;
 }
 static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }

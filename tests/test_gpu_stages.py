@@ -177,3 +177,26 @@ def test_long_queries_match_oracle(long_case):
     gr, gs, gc = g.search(s3, g.default_params(output_seq=1))
     orr, os_, oc = o.search(s3, o.default_params(output_seq=1), threads=8)
     _rows_equal(gr, orr, gs, os_, gc, oc)
+
+
+@pytest.fixture(scope="module")
+def c3_case(workdir):
+    """BASELINE.json configs[2] in miniature: 5-kb plasmid-scale queries (k-mer tables of ~10,000 rows: fused capture kernel with 1,024-thread
+    CTAs, one pseudo-alignment CTA per SM, windows of ~7 kb with thousands of anchors) against a 400-genome index."""
+    from conftest import make_index, make_queries
+    from oracle_binding import Oracle, read_fasta
+    import lexicmap_b200
+    idx = make_index(workdir, "c3mini", "20,20,200000,31,20", chunks=16)
+    _, seqs = read_fasta(make_queries(workdir, idx, "c3mini_q", 160, 5000, seed=41))
+    return lexicmap_b200.Index(idx, device=0), Oracle(idx), seqs
+
+
+def test_5kb_queries_match_oracle(c3_case):
+    g, o, seqs = c3_case
+    orr, os_, oc = o.search(seqs, o.default_params(output_seq=1), threads=os.cpu_count() or 8)
+    assert len(orr) > 2000
+    for lanes in (1, 2):
+        gr, gs, gc = g.search(seqs, g.default_params(output_seq=1, lanes=lanes))
+        _rows_equal(gr, orr, gs, os_, gc, oc)
+    again = g.search(seqs, g.default_params(output_seq=1, lanes=2))
+    _rows_equal(again[0], orr, again[1], os_, again[2], oc)
