@@ -139,8 +139,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    workload = "%d synthetic %d-bp queries vs %d-genome synthetic index (%dx%dx%d bp), BASELINE.json configs[1]" % (
-        CFG["n_queries"], CFG["query_len"], CFG["families"] * CFG["members"], CFG["families"], CFG["members"], CFG["genome_len"])
+    is_c2 = (CFG["families"], CFG["members"], CFG["genome_len"], CFG["n_queries"], CFG["query_len"]) == (50, 20, 1000000, 10000, 1000)
+    workload = "%d synthetic %d-bp queries vs %d-genome synthetic index (%dx%dx%d bp), %s" % (
+        CFG["n_queries"], CFG["query_len"], CFG["families"] * CFG["members"], CFG["families"], CFG["members"], CFG["genome_len"],
+        "BASELINE.json configs[1]" if is_c2 else "LMG_BENCH_* override (not a BASELINE.json config as is)")
     config = {"workload": workload, "queries_per_gpu": CFG["n_queries"], "query_len": CFG["query_len"], "genomes": CFG["families"] * CFG["members"], "masks": 20000,
               "sharding": "by query, index replicated" if a.gpus > 1 else "single GPU", "l2": "index image (>1 GB) and per-batch buffers exceed the 126 MB L2; no explicit flush",
               "seeds": [CFG["genome_seed"], CFG["query_seed"]]}
