@@ -284,7 +284,7 @@ def main():
            "cpu_baseline": {"value": cpu_bps, "unit": "bp/s", "cores": threads, "kind": "port", "sample": "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)},
            "debug": {"staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage],
                      "kernel_ms": {k: float(kern_ms[i]) / a.steps for k, i in [("wfa_prep+general", 10), ("wfa_fwd+bt", 11), ("extend", 13), ("pa_anchors", 14), ("pa_chain", 15)]},
-                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14]), "wfa_lmax": int(kcnt[15])},
+                     "wfa_jobs": int(kcnt[9]), "wfa_fallback_first": int(kcnt[10]), "wfa_general_jobs": int(kcnt[11]), "probe_find_us": int(kcnt[13]), "probe_survivors": int(kcnt[1]), "probe_issued": int(kcnt[0]), "wfa_per_round": int(kcnt[14])},
            "clocks": sampler.summary()}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)

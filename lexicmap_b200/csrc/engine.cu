@@ -120,40 +120,9 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 pad; };  // mask_dir = mask<<1 | dir ; [lo,lo+n) = query table rows (locs)
 struct ProbeParams { const u64 *bucket_off, *keys, *val_off, *vals; const u32 *anchor_start, *anchor_bits; int m, k, NA, mask_prefix, anchor_prefix, p; };
 
-// one thread per (query, mask, direction). dir 0: captured k-mer against its own mask bucket, values must have reverse flag 0;
-// dir 1: base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
+// Probe semantics (kv.Searcher.Search / Search2): dir 0 = captured k-mer against its own mask bucket, values must have reverse flag 0;
+// dir 1 = base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
 // semantics, kv-searcher.go:466-488). Range = keys in [kmer & ~low, kmer | low] at/after the anchor start (:282-304, :349-355).
-__global__ void __launch_bounds__(256) k_probe_find(ProbeParams P, CapSoA cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nprobe,
-                                                    ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u64* __restrict__ stats) {
-  u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0;
-  if (t < nprobe) {
-    u64 qi = t >> 1; int dir = (int)(t & 1); u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); Capture c; c.kmer = cap.kmer[qi]; c.lo = 0; c.n = 0; c.smask = 0; bool go = c.kmer != 0;
-    if (go && dir == 1) { c.lo = cap.lo[qi]; c.smask = cap.smask[qi]; go = owner[koff[q] + c.lo] == (u32)i; }
-    if (go) {
-      u64 kmer = dir ? kmer_reverse62(c.kmer, P.k) : c.kmer; int bucket = dir ? (int)c.smask : i;
-      int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low;
-      u32 a = (u32)((left >> ((P.k - P.mask_prefix - P.anchor_prefix) << 1)) & (u64)(P.NA - 1));
-      u64 aslot = (u64)bucket * P.NA + a; u32 as = ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) ? P.anchor_start[aslot] : 0xFFFFFFFFu;
-      if (as != 0xFFFFFFFFu) {
-        u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; u64 lo = b0 + as, hi = b1;
-        // galloping lower_bound(left) from the anchor start
-        u64 step = 1, l = lo; while (l + step < hi && P.keys[l + step] < left) { l += step; step <<= 1; steps++; }
-        u64 r = min(hi, l + step); if (P.keys[l] >= left) r = l; else l = l + 1;
-        while (l < r) { u64 mid = (l + r) >> 1; if (P.keys[mid] < left) l = mid + 1; else r = mid; steps++; }
-        u64 e0 = l; u32 ne = 0, na = 0; const int want = dir;
-        while (e0 + ne < hi && P.keys[e0 + ne] <= right) { u64 v0 = P.val_off[e0 + ne], v1 = P.val_off[e0 + ne + 1]; if (v1 > v0 && (int)(P.vals[v0] & 1) == want) na += (u32)(v1 - v0); ne++; }
-        if (na) { if (dir == 0) c.lo = cap.lo[qi]; c.n = cap.n[qi]; have = true; h.q = q; h.mask_dir = (u32)(i << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = c.lo; h.n = c.n; h.kmer = kmer; h.nanch = na * c.n; h.pad = 0; }
-        if (stats) { atomicAdd((unsigned long long*)&stats[1], 1ull); atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); }
-      }
-      if (stats) atomicAdd((unsigned long long*)&stats[0], 1ull);
-    }
-  }
-  // warp-aggregated append
-  u32 bal = __ballot_sync(FULLMASK, have);
-  if (bal) { int lane = threadIdx.x & 31; u32 base = 0; if (lane == __ffs(bal) - 1) base = atomicAdd(nhits, __popc(bal)); base = __shfl_sync(FULLMASK, base, __ffs(bal) - 1);
-    if (have) hits[base + __popc(bal & ((1u << lane) - 1))] = h; }
-}
-
 // ---- two-phase probe. Phase A (k_probe_filter, one thread per (query, mask)): everything that can be decided from coalesced / L2-resident
 // data — captured k-mer present, first-owner test of the reversed k-mer, anchor presence bit — and compaction of the surviving probes.
 // Phase B (k_probe_find2, one thread per survivor): the dependent random HBM accesses (anchor start, key search, value flags) with all
@@ -567,36 +536,6 @@ __device__ __forceinline__ bool tree_search_in(const u64* __restrict__ a, u32 n,
 }
 __device__ __forceinline__ bool tree_search(const u64* __restrict__ a, u32 n, u64 key, int p, u32* rlo, u32* rhi) { return tree_search_in(a, n, 0, n, key, p, rlo, rhi); }
 
-// one CTA per window; threads over target positions. EMIT=false: count anchors; EMIT=true: write them (packed like seed anchors).
-template <bool EMIT>
-__global__ void __launch_bounds__(128) k_pa_anchors(const WinItem* __restrict__ items, u32 nitems, const u8* __restrict__ g2bit, const u64* __restrict__ g_off, const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff,
-                                                    u32* __restrict__ counts, const u64* __restrict__ aoff, u64* __restrict__ a_lo) {
-  typedef cub::BlockScan<u32, 128> Scan; __shared__ typename Scan::TempStorage tmp; __shared__ u32 s_base;
-  u32 it = blockIdx.x; if (it >= nitems) return; WinItem w = items[it]; const int K = 31; const u8* g2 = g2bit + g_off[w.g]; const u64* tk = tkeys + toff[w.q]; const u32* tv = tvals + toff[w.q]; u32 tn = toff[w.q + 1] - toff[w.q];
-  i32 np = w.W - K + 1; u32 total = 0; if (threadIdx.x == 0) s_base = 0; __syncthreads();
-  const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
-  for (i32 t0 = 0; t0 < np; t0 += 128) {
-    i32 idx = t0 + (i32)threadIdx.x; u32 c = 0; u64 km = 0, kr = 0; bool ok = false; u32 l1 = 0, h1 = 0, l2 = 0, h2 = 0; bool f1 = false, f2 = false;
-    if (idx < np) { for (int j = 0; j < K; j++) { u64 b = win_base(g2, w.tBegin, w.tEnd, w.rc, idx + j); km = (km << 2) | b; kr = (kr >> 2) | ((3 - b) << 60); }
-      ok = !(km == 0 || km == ccc || km == ggg || km == ttt); }
-    if (ok && tn) {
-      f1 = tree_search(tk, tn, km, w.mp, &l1, &h1);
-      if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; c++; }
-      f2 = tree_search(tk, tn, kr, w.mp, &l2, &h2);
-      if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; c++; }
-    }
-    if (!EMIT) { total += c; }
-    else {
-      u32 ex, agg; Scan(tmp).ExclusiveSum(c, ex, agg); u64 wpos = aoff[it] + s_base + ex; __syncthreads(); if (threadIdx.x == 0) s_base += agg;
-      if (c) {
-        if (f1) for (u32 u = l1; u < h1; u++) { u32 v = tv[u]; int lp = lcp31(km, tk[u]); u32 p = v >> 1; if ((v & 1) == 1 || p < begin || p + (u32)lp > end) continue; a_lo[wpos++] = pack_lo((i32)p, (u32)lp, idx, 0, 0); }
-        if (f2) for (u32 u = l2; u < h2; u++) { u32 v = tv[u]; int lp = lcp31(kr, tk[u]); u32 p = (v >> 1) + (u32)K - (u32)lp; if ((v & 1) == 0 || p + (u32)lp < begin || p > end) continue; a_lo[wpos++] = pack_lo((i32)p, (u32)lp, idx + K - lp, 1, 1); }
-      }
-      __syncthreads();
-    }
-  }
-  if (!EMIT) { typedef cub::BlockReduce<u32, 128> Red; __shared__ typename Red::TempStorage rt; u32 s = Red(rt).Sum(total); if (threadIdx.x == 0) counts[it] = s; }
-}
 
 // ---- K4 v2: per-query hash index over the 11-base prefixes of the table (the default minimum prefix), window staged in shared memory
 // slot = prefix22 << 42 | start24 << 18 | count18 ; empty = ~0
