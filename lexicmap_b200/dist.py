@@ -24,3 +24,40 @@ def reduce_counters(rows, bases, step_ms, device=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return float(t[0]), float(t[1]), float(m[0])
+
+
+def merge_genome_shards(parts):
+    """Merge the results of the same query batch searched against the genome shards of one index (`lmg_index_open(..., shard, n_shards)`:
+    every shard holds all masks but only the seed values / genomes with dense_id % n_shards == shard; SURVEY.md §8e option 2, the offline
+    equivalent is `lexicmap utils merge-search-results`, merge-search-results.go:143-153,318-320).
+    parts: [(rows, seqids, cigars), ...] one per shard. Per query: `hits` becomes the number of genomes over all shards and the genomes are
+    re-ordered exactly as the unsharded search orders them (stable by genome index in its batch, then stable by the best
+    bitscore x pident of the genome, lib-index-search.go:1848-1853,2919-2921); rows inside a genome keep their order.
+    Returns (rows, seqids, cigars)."""
+    import numpy as np
+    groups = {}   # query -> list of (bgi, sim, part, first_row, last_row)
+    for pi, (rows, _, _) in enumerate(parts):
+        n = len(rows)
+        i = 0
+        while i < n:
+            j = i
+            q, g = rows["query"][i], rows["genome"][i]
+            while j < n and rows["query"][j] == q and rows["genome"][j] == g:
+                j += 1
+            sim = float(np.max(rows["bitscore"][i:j].astype(np.float64) * rows["pident"][i:j]))
+            groups.setdefault(int(q), []).append((int(g), sim, pi, i, j))
+            i = j
+    out_rows, out_ids, out_cig = [], [], []
+    for q in sorted(groups):
+        gs = sorted(groups[q], key=lambda t: t[0])                 # dense order (batch-major, index in batch): the unsharded segment order
+        gs = sorted(gs, key=lambda t: t[0] & 131071)               # stable, :1848-1853
+        gs = sorted(gs, key=lambda t: -t[1])                       # stable, best similarity first, :2919-2921
+        for g, _, pi, i, j in gs:
+            rows, ids, cig = parts[pi]
+            r = rows[i:j].copy()
+            r["hits"] = len(gs)
+            out_rows.append(r)
+            out_ids += ids[i:j]
+            out_cig += cig[i:j]
+    dtype = parts[0][0].dtype
+    return (np.concatenate(out_rows) if out_rows else np.zeros(0, dtype)), out_ids, out_cig

@@ -38,3 +38,26 @@ def test_shards_are_contiguous_and_balanced():
     assert cuts[0][0] == 0 and cuts[-1][1] == len(lens)
     for a, b in zip(cuts, cuts[1:]):
         assert a[1] == b[0]
+
+
+def test_merge_genome_shards_restores_unsharded_rows(oracle_small, small_queries):
+    """host merge of genome-sharded results (SURVEY.md §8e option 2): split the oracle's rows by genome into 3 pseudo-shards
+    (per-shard `hits`), merge, compare with the original ordering and hits column"""
+    import numpy as np
+    from lexicmap_b200.dist import merge_genome_shards
+    ids, seqs = small_queries
+    rows, sid, cig = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
+    assert len(rows) > 50
+    parts = []
+    for sh in range(3):
+        keep = [i for i in range(len(rows)) if ((int(rows["genome"][i]) >> 17) * 7 + (int(rows["genome"][i]) & 131071)) % 3 == sh]
+        r = rows[keep].copy()
+        for q in np.unique(r["query"]):
+            m = r["query"] == q
+            r["hits"][m] = len(np.unique(r["genome"][m]))
+        parts.append((r, [sid[i] for i in keep], [cig[i] for i in keep]))
+    mr, ms, mc = merge_genome_shards(parts)
+    assert ms == sid and mc == cig
+    for f in rows.dtype.names:
+        if f not in ("cigar_off", "pad", "pad0"):
+            assert np.array_equal(mr[f], rows[f]), f

@@ -200,3 +200,21 @@ def test_5kb_queries_match_oracle(c3_case):
         _rows_equal(gr, orr, gs, os_, gc, oc)
     again = g.search(seqs, g.default_params(output_seq=1, lanes=2))
     _rows_equal(again[0], orr, again[1], os_, again[2], oc)
+
+
+def test_genome_sharded_image_merges_to_the_unsharded_result(small_index, gpu_small, small_queries):
+    """SURVEY.md §8e option 2: the image split by genome over 2 and 3 shards; every shard searches the whole batch, the host merge
+    (hits summed, genomes re-ordered) reproduces the unsharded rows exactly."""
+    import lexicmap_b200
+    from lexicmap_b200.dist import merge_genome_shards
+    ids, seqs = small_queries
+    ref = gpu_small.search(seqs, gpu_small.default_params(output_seq=1))
+    for n in (2, 3):
+        parts = []
+        for sh in range(n):
+            g = lexicmap_b200.Index(small_index, device=0, shard=sh, n_shards=n)
+            parts.append(g.search(seqs, g.default_params(output_seq=1)))
+            g.close()
+        assert sum(len(p[0]) for p in parts) == len(ref[0])
+        mr, ms, mc = merge_genome_shards(parts)
+        _rows_equal(mr, ref[0], ms, ref[1], mc, ref[2])
