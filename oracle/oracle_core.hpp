@@ -5,10 +5,10 @@
 //
 // PARITY PINNING STATUS
 //   * formats / seed lookup: pinned by the reference's own known-answer test kv/kv-data_test.go:30-361
-//     (restated in tests/test_oracle_kat.py) and util/varint-GB_test.go (round trip).
+//     (restated in tests/test_oracle_cpu.py::test_kv_known_answer) and util/varint-GB_test.go (round trip).
 //   * chaining, pseudo-alignment: the reference tests carry inputs but no expected outputs
 //     (lib-chaining_test.go, lib-seq_compare_test.go) -> "parity unpinned" at unit level; pinned end-to-end
-//     against demo/q.gene.fasta.lexicmap.tsv rows (tests/test_oracle_demo.py, runs where /root/reference exists).
+//     against demo/q.gene.fasta.lexicmap.tsv rows (tests/test_oracle_cpu.py::test_oracle_reproduces_reference_demo_rows, runs where the demo genomes of /root/reference exist).
 //   * LexicHash masking (github.com/shenwei356/lexichash v0.5.5) and WFA (github.com/shenwei356/wfa v0.5.0)
 //     are third-party Go modules whose source is NOT under /root/reference -> "parity unpinned": restated from
 //     the call sites, the published algorithm (LexicHash: argmin(kmer XOR mask); WFA: Marco-Sola et al. 2021 with
