@@ -223,3 +223,28 @@ def test_no_gpu_means_loud_failure(small_index):
 def test_tsv_number_formats():
     # Go's %.3f / %.2e == C printf == Python % (two-digit exponent), search.go:492-518
     assert "%.2e" % 5.17090374e-304 == "5.17e-304" and "%.2e" % 0.0 == "0.00e+00" and "%.2e" % 1.72e-43 == "1.72e-43" and "%.3f" % 99.8054 == "99.805"
+
+
+def test_all_columns_pool_layout_and_formatters(oracle_small, small_queries):
+    """`-a` output: the string pool entry of a row is cigar | qseq | sseq | align; the product-side splitter (lexicmap_b200.api) recovers the
+    same texts as the oracle binding, and both TSV formatters write identical 24-column lines (search.go:505-518)."""
+    from lexicmap_b200.api import split_align_text
+    ids, seqs = small_queries
+    rows, sid, cig = oracle_small.search(seqs, oracle_small.default_params(output_seq=1))
+    texts = oracle_small.last_align_text
+    pool = b"".join((c + q + s + a).encode() for c, (q, s, a) in zip(cig, texts))
+    r2 = rows.copy()
+    off = 0
+    for i in range(len(r2)):
+        r2["cigar_off"][i] = off
+        off += int(r2["cigar_len"][i]) + 3 * int(r2["alen"][i])
+    assert split_align_text(r2, pool) == texts
+    assert split_align_text(rows[:0], b"") is None
+    lines = format_tsv(rows, sid, ids, [len(s) for s in seqs], oracle_small.genome_name, cig, texts)
+
+    class _Fake:   # the product formatter only needs genome_name
+        genome_name = staticmethod(oracle_small.genome_name)
+    import lexicmap_b200.api as api
+    assert api.Index.format_tsv(_Fake, rows, sid, ids, [len(s) for s in seqs], cig, texts) == lines
+    f = lines[0].split("\t")
+    assert len(f) == 24 and len(f[21]) == len(f[22]) == len(f[23]) == int(f[9])
