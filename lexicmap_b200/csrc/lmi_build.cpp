@@ -164,7 +164,53 @@ static inline bool tuple_less(const Tuple& a, const Tuple& b) {
   if (a.src != b.src) return a.src < b.src; return a.value < b.value;
 }
 
-struct BuildOpts { int k = 31, masks = 20000, chunks = 16, partitions = 4096, contig_interval = 1000; int64_t seed = 1; int threads = 0; };
+// ------------------------------------------------------------------ seed-desert filling (lib-index-build.go:1086-1413)
+// After the first round (one captured k-mer per mask, all its positions) consecutive seeds may be far apart. Every gap of >= max_desert
+// bases is walked in steps of seed_dist: around each step (seed_dist/2 bases upstream, then downstream) the first position is taken whose
+// k-mer (either strand) is captured by some mask when the REGION (gap +- 1000 bp) is masked on its own without the shorter-prefix fallback
+// (lh.MaskKnownDistinctPrefixes(region, nil, false), :1199), is not low-complexity and does not touch a contig interval / gap region.
+struct ExtraSeed { uint32_t mask; uint64_t kmer; uint32_t loc; };   // loc = pos<<1 | strand
+struct DesertScratch { std::vector<uint64_t> best; std::vector<uint32_t> stamp, touched; uint32_t epoch = 0; std::vector<uint64_t> kl; std::vector<int32_t> l2m, l2mrc; };
+static void fill_deserts(const uint8_t* seq, size_t n, int k, const std::vector<uint64_t>& masks, const std::vector<uint32_t>& pstart, int p,
+                         const std::vector<std::pair<int64_t, int64_t>>& skip, const Capture& cap, int maxDesert, int seedDist, std::vector<ExtraSeed>& out, DesertScratch& S) {
+  if (n < (size_t)k) return; const int seedPosR = seedDist / 2; const size_t m = masks.size(); const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  if (S.best.size() != m) { S.best.assign(m, 0); S.stamp.assign(m, 0); S.epoch = 0; }
+  std::vector<uint32_t> locs; for (size_t j = 0; j < m; j++) if (!cap.locs[j].empty() && !is_low_complexity(cap.kmer[j], k)) for (uint32_t l : cap.locs[j]) locs.push_back(l);
+  std::sort(locs.begin(), locs.end()); locs.push_back((uint32_t)(n - k) << 1);   // pseudo position at the end (:1139)
+  auto in_itree = [&](int64_t pos) { for (const auto& r : skip) { if (r.first - k + 1 > pos) break; if (pos <= r.second) return true; } return false; };   // :978, :1001 (regions widened by k-1 to the left)
+  const uint64_t ccc = kmer_ns(1, k), ggg = kmer_ns(2, k), ttt = kmask;
+  auto usable = [&](uint64_t km) { return km != 0 && km != ccc && km != ggg && km != ttt && !is_low_complexity_dust(km, k); };
+  uint32_t pre = 0;
+  for (uint32_t pos2str : locs) { const uint32_t pos = pos2str >> 1, d = pos - pre; if (d < (uint32_t)maxDesert) { pre = pos; continue; }
+    int start = (int)pre - 1000, posOfPre = 1000; if (start < 0) { posOfPre += start; start = 0; } int end = (int)pos + 1000 + k; if (end > (int)n) end = (int)n;
+    const int posOfCur = posOfPre + (int)d, nk = end - start - k + 1; if (nk <= 0) { pre = pos; continue; }
+    // k-mers of the region, both strands (kmerList, :1184-1192)
+    S.kl.resize(2 * (size_t)nk); { uint64_t fw = 0, rc = 0; for (int i = start; i < end; i++) { fw = ((fw << 2) | seq[i]) & kmask; rc = (rc >> 2) | ((uint64_t)(3 - seq[i]) << (2 * (k - 1))); if (i - start + 1 >= k) { int q = i - start + 1 - k; S.kl[2 * q] = fw; S.kl[2 * q + 1] = rc; } } }
+    // region masking without fallback: per mask the XOR-argmin over the region k-mers sharing its p-base prefix; loc2maskidx = the LAST mask capturing a position (:1220-1233)
+    S.epoch++; S.touched.clear();
+    for (int q = 0; q < nk; q++) for (int st = 0; st < 2; st++) { uint64_t km = S.kl[2 * q + st]; uint64_t pre_ = km >> (2 * (k - p));
+      for (uint32_t j = pstart[pre_]; j < pstart[pre_ + 1]; j++) { uint64_t h = km ^ masks[j]; if (S.stamp[j] != S.epoch) { S.stamp[j] = S.epoch; S.best[j] = h; S.touched.push_back(j); } else if (h < S.best[j]) S.best[j] = h; } }
+    S.l2m.assign(nk, -1); S.l2mrc.assign(nk, -1);
+    for (int q = 0; q < nk; q++) for (int st = 0; st < 2; st++) { uint64_t km = S.kl[2 * q + st]; uint64_t pre_ = km >> (2 * (k - p));
+      for (uint32_t j = pstart[pre_]; j < pstart[pre_ + 1]; j++) if ((km ^ masks[j]) == S.best[j]) (st ? S.l2mrc : S.l2m)[q] = (int32_t)j; }   // ascending j: the last one stays
+    auto probe = [&](int j, int& im, uint64_t& km, uint32_t& kpos) -> bool { if (j < 0 || j >= nk || in_itree((int64_t)start + j)) return false;
+      uint64_t a = S.kl[2 * j]; if (usable(a) && S.l2m[j] >= 0) { im = S.l2m[j]; km = a; kpos = (uint32_t)(start + j) << 1; return true; }
+      uint64_t b = S.kl[2 * j + 1]; if (usable(b) && S.l2mrc[j] >= 0) { im = S.l2mrc[j]; km = b; kpos = ((uint32_t)(start + j) << 1) | 1u; return true; } return false; };
+    int j = posOfPre + seedDist;
+    for (;;) { if (j >= posOfCur) break;
+      int dstart = j + 1, uend = j - seedPosR; bool ok = false; int im = -1; uint64_t km = 0; uint32_t kpos = 0;
+      for (; j > uend; j--) if (probe(j, im, km, kpos)) { ok = true; break; }                       // upstream scan (:1241-1296)
+      if (ok) { out.push_back({(uint32_t)im, km, kpos}); j += seedDist; continue; }
+      if (dstart >= posOfCur) break;
+      int dend = dstart + seedPosR; if (dend >= posOfCur) dend = posOfCur - 1;
+      for (j = dstart; j < dend; j++) if (probe(j, im, km, kpos)) { ok = true; break; }               // downstream scan (:1322-1372)
+      if (ok) { out.push_back({(uint32_t)im, km, kpos}); j += seedDist; continue; }
+      j += seedDist; }                                                                                // could not fill here (gap, interval, repeats), :1392-1401
+    pre = pos; }
+}
+
+struct BuildOpts { int k = 31, masks = 20000, chunks = 16, partitions = 4096, contig_interval = 1000; int64_t seed = 1; int threads = 0;
+  bool fill_deserts = false; int max_desert = 100, seed_dist = 50; };   // --fill-deserts, -D/--seed-max-desert, -d/--seed-in-desert-dist (index.go:582-586)
 
 template <class GetGenome>
 static void build_index(const std::string& out, size_t n_genomes, GetGenome get, const BuildOpts& o) {
@@ -173,8 +219,10 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
   std::vector<uint64_t> masks = gen_masks(k, o.masks, o.seed); write_masks(out + "/masks.bin", masks, k, o.seed);
   const int mask_prefix = std::max((int)(std::log2((double)o.masks) / 2), 1), anchor_prefix = std::max((int)(std::log2((double)o.partitions) / 2), 1);
   int nt = o.threads > 0 ? o.threads : omp_get_max_threads();
-  std::vector<std::vector<Tuple>> tl(nt); std::vector<GenomeRec> recs(n_genomes); int64_t total_bases = 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : total_bases)
+  int mask_p = 0; while ((1ull << (2 * (mask_p + 1))) <= masks.size()) mask_p++;   // same prefix directory as capture_sequence
+  std::vector<uint32_t> mask_pstart(((size_t)1 << (2 * mask_p)) + 1, 0); for (uint64_t mk : masks) mask_pstart[(mk >> (2 * (k - mask_p))) + 1]++; for (size_t i = 0; i + 1 < mask_pstart.size(); i++) mask_pstart[i + 1] += mask_pstart[i];
+  std::vector<std::vector<Tuple>> tl(nt); std::vector<GenomeRec> recs(n_genomes); int64_t total_bases = 0; long long n_extra = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : total_bases, n_extra)
   for (size_t gi = 0; gi < n_genomes; gi++) {
     InGenome g = get(gi); GenomeRec& r = recs[gi]; r.id = g.id; std::vector<uint8_t> codes; std::vector<std::pair<int64_t, int64_t>> skip;
     for (size_t c = 0; c < g.seqs.size(); c++) {
@@ -191,6 +239,11 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
     r.twobit.assign((codes.size() + 3) / 4, 0); for (size_t i = 0; i < codes.size(); i++) r.twobit[i >> 2] |= codes[i] << (6 - 2 * (i & 3));
     Capture cap; capture_sequence(codes.data(), codes.size(), k, masks, skip, cap);
     std::vector<Tuple>& T = tl[omp_get_thread_num()]; const uint64_t gshift = (uint64_t)gi << BITS_NONE_IDX;  // batch 0
+    if (o.fill_deserts) { static thread_local DesertScratch scratch; std::vector<ExtraSeed> ex; fill_deserts(codes.data(), codes.size(), k, masks, mask_pstart, mask_p, skip, cap, o.max_desert, o.seed_dist, ex, scratch);
+      for (const ExtraSeed& e : ex) { uint64_t rv = kmer_reverse(e.kmer, k); uint32_t dj = xor_argmin_mask(masks, rv);   // extra k-mers enter like captured ones, incl. the reversed copy (:726-760, :845-890)
+        T.push_back({e.mask, e.mask, e.kmer, gshift | (((uint64_t)e.loc << 1) & MASK_NONE_IDX)});
+        T.push_back({dj, e.mask | 0x80000000u, rv, gshift | ((((uint64_t)e.loc << 1) | 1) & MASK_NONE_IDX)}); }
+      n_extra += ex.size(); }
     for (size_t j = 0; j < masks.size(); j++) {
       uint64_t km = cap.kmer[j]; if (cap.locs[j].empty() || is_low_complexity(km, k)) continue;
       uint64_t rv = kmer_reverse(km, k); uint32_t dj = xor_argmin_mask(masks, rv);
@@ -221,10 +274,10 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
     }
     w.close();
   }
-  IndexInfo info; info.k = k; info.masks = o.masks; info.rand_seed = o.seed; info.max_desert = 0; info.seed_dist_in_desert = 0; info.chunks = o.chunks; info.partitions = o.partitions;
+  IndexInfo info; info.k = k; info.masks = o.masks; info.rand_seed = o.seed; info.max_desert = o.fill_deserts ? o.max_desert : 0; info.seed_dist_in_desert = o.fill_deserts ? o.seed_dist : 0; info.chunks = o.chunks; info.partitions = o.partitions;
   info.input_genomes = (int)n_genomes; info.input_bases = total_bases; info.genomes = (int)n_genomes; info.genome_batch_size = (int)n_genomes; info.contig_interval = o.contig_interval;
   write_info(out + "/info.toml", info);
-  fprintf(stderr, "[lmi-build] %zu genomes, %lld bases, %zu seed values, %d masks -> %s\n", n_genomes, (long long)total_bases, all.size(), o.masks, out.c_str());
+  fprintf(stderr, "[lmi-build] %zu genomes, %lld bases, %zu seed values (%lld from desert filling), %d masks -> %s\n", n_genomes, (long long)total_bases, all.size(), 2 * n_extra, o.masks, out.c_str());
 }
 
 // ------------------------------------------------------------------ synthetic queries from an index's genomes
@@ -258,6 +311,9 @@ int main(int argc, char** argv) {
     std::string cmd = argv[1];
     BuildOpts o; o.masks = atoi(arg(argc, argv, "--masks", "20000")); o.chunks = atoi(arg(argc, argv, "--chunks", "16")); o.partitions = atoi(arg(argc, argv, "--partitions", "4096"));
     o.seed = atoll(arg(argc, argv, "--rand-seed", "1")); o.threads = atoi(arg(argc, argv, "--threads", "0")); o.contig_interval = atoi(arg(argc, argv, "--contig-interval", "1000"));
+    for (int i = 2; i < argc; i++) if (!strcmp(argv[i], "--fill-deserts")) o.fill_deserts = true;
+    o.max_desert = atoi(arg(argc, argv, "--seed-max-desert", "100")); o.seed_dist = atoi(arg(argc, argv, "--seed-in-desert-dist", "50"));
+    if (o.fill_deserts && (o.seed_dist * 2 > o.max_desert || o.seed_dist < 2)) die("value of --seed-in-desert-dist should be smaller than 0.5 * --seed-max-desert");   // index.go:213
     if (cmd == "index") {
       std::string out = arg(argc, argv, "--out", ""); if (out.empty()) die("--out needed");
       std::string synth = arg(argc, argv, "--synth", ""), list = arg(argc, argv, "--in-list", "");

@@ -162,6 +162,41 @@ def test_oracle_reproduces_reference_demo_rows(tmp_path):
     assert n == 14
 
 
+@pytest.mark.skipif(not os.path.isdir(DEMO_REFS), reason="reference demo genomes not available on this box")
+def test_oracle_reproduces_reference_prophage_rows_with_desert_filling(tmp_path):
+    """Long-query pin: demo/q.prophage.fasta (33.6 kb) against demo/refs. The reference's index fills seed deserts (lib-index-build.go:1086-1413);
+    with the writer's restatement of that step (`--fill-deserts`) the oracle reproduces the reference's long HSPs exactly — alignments of
+    9,371 / 6,942 / 5,941 / 2,983 / 820 columns incl. gap columns, coordinates, pident, bit score, e-value and the genome coverage — which pins
+    chaining over many seeds, windows >= 10 kb (minimum prefix 13) and WFA-adaptive on long alignments. (Without desert filling the 9.4-kb and
+    6.9-kb HSPs come out fragmented.) Rows that depend on seeds of two low-identity genomes differ (other masks than the reference's)."""
+    lst = tmp_path / "refs.list"
+    lst.write_text("\n".join(os.path.join(DEMO_REFS, f) for f in sorted(os.listdir(DEMO_REFS))) + "\n")
+    idx = str(tmp_path / "demo_desert.lmi")
+    subprocess.check_call([_tools(), "index", "--in-list", str(lst), "--out", idx, "--fill-deserts"], stderr=subprocess.DEVNULL)
+    o = Oracle(idx)
+
+    def key(f):
+        return (f[0], f[3], f[4], f[12], f[13], f[14], f[15], f[16])
+    ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.prophage.fasta"))
+    rows, sid, cig = o.search(seqs, o.default_params(), threads=8)
+    mm = {key(l.split("\t")): l.split("\t") for l in format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name)}
+    gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLD, "demo_q.prophage.fasta.lexicmap.tsv"))][1:]
+    gm = {key(f): f for f in gold}
+    common = set(gm) & set(mm)
+    assert len(gold) == 9 and len(common) >= 5
+    for kx in common:
+        assert gm[kx][8:20] == mm[kx][8:20] and gm[kx][5] == mm[kx][5], (gm[kx], mm[kx])     # columns 9-20 and qcovGnm
+    assert {int(gm[kx][9]) for kx in common} >= {9371, 6942, 5941, 2983, 820}
+    # the gene queries on the same index: no row outside the reference's output, at least as many reproduced as without desert filling
+    ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.gene.fasta"))
+    rows, sid, cig = o.search(seqs, o.default_params(), threads=8)
+    mm = {key(l.split("\t")): l.split("\t") for l in format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name)}
+    gm = {key(f): f for f in (l.rstrip("\n").split("\t") for l in list(open(os.path.join(GOLD, "demo_q.gene.fasta.lexicmap.tsv")))[1:])}
+    assert not (set(mm) - set(gm)) and len(set(mm) & set(gm)) >= 80
+    for kx in set(mm) & set(gm):
+        assert gm[kx][8:20] == mm[kx][8:20]
+
+
 # ------------------------------------------------------------------ regression pin on a deterministic synthetic fixture
 def test_oracle_small_fixture_regression(oracle_small, small_queries):
     ids, seqs = small_queries
