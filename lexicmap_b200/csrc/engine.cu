@@ -1416,7 +1416,7 @@ static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, con
   ix->ms[12] = (double)L; ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
 }
 int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; if (n <= 0) { R->img = &ix->img; *out = R; return 0; }   // empty batch: no rows try { search_lanes(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; if (n <= 0) { R->img = &ix->img; *out = R; return 0; }   /* empty batch: no rows */ try { search_lanes(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
