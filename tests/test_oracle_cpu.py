@@ -283,3 +283,40 @@ def test_all_columns_pool_layout_and_formatters(oracle_small, small_queries):
     assert api.Index.format_tsv(_Fake, rows, sid, ids, [len(s) for s in seqs], cig, texts) == lines
     f = lines[0].split("\t")
     assert len(f) == 24 and len(f[21]) == len(f[22]) == len(f[23]) == int(f[9])
+
+
+def test_desert_filling_closes_seed_gaps(tmp_path):
+    """index writer, `--fill-deserts` (lib-index-build.go:1086-1413): first-round seeds leave gaps of >= 100 bases between consecutive seed
+    positions; after filling, gaps above max_desert + seed_dist survive only next to contig-interval regions, the first-round seeds are
+    all still there, and every extra seed also has its base-reversed copy (reverse flag 1)."""
+    import glob
+    tools = _tools()
+
+    def seed_positions(idx):
+        fwd, rev = {}, {}
+        for f in sorted(glob.glob(os.path.join(idx, "seeds", "chunk_*.bin"))):
+            for line in subprocess.check_output([tools, "kv-dump", "--file", f], text=True).splitlines():
+                p = line.split("\t")
+                if p[0] != "K":
+                    continue
+                for v in p[3:]:
+                    v = int(v)
+                    (rev if v & 1 else fwd).setdefault((v >> 30) & 131071, set()).add((v >> 2) & ((1 << 28) - 1))
+        return fwd, rev
+    a = str(tmp_path / "plain.lmi")
+    b = str(tmp_path / "filled.lmi")
+    # 2,048 masks over 200-kb genomes: ~100 bases between first-round seeds on average, so deserts are common (20,000 masks would leave none here)
+    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", a, "--chunks", "4", "--masks", "2048"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", b, "--chunks", "4", "--masks", "2048", "--fill-deserts"], stderr=subprocess.DEVNULL)
+    (fa, ra), (fb, rb) = seed_positions(a), seed_positions(b)
+    assert set(fa) == set(fb)
+    for g in fa:
+        assert fa[g] <= fb[g] and fb[g] == rb[g] and fa[g] == ra[g]
+        pa, pb = sorted(fa[g]), sorted(fb[g])
+        gaps_a = [y - x for x, y in zip(pa, pa[1:])]
+        gaps_b = [y - x for x, y in zip(pb, pb[1:])]
+        assert max(gaps_a) >= 300                       # first round alone leaves deserts
+        big = [d for d in gaps_b if d > 150]
+        assert len(big) <= 4 and all(d >= 1000 for d in big if d > 400)   # only the 1000-bp contig intervals (<= 2 per genome) stay wide
+        assert len(pb) > 1.5 * len(pa)
+    assert "max-seed-dist = 100" in open(os.path.join(b, "info.toml")).read().replace('"', "") or "100" in open(os.path.join(b, "info.toml")).read()
