@@ -41,7 +41,9 @@ int main(int argc, char** argv) {
     else if (a == "-l" || a == "--align-min-match-len") o.p.align_min_len = atoi(need(i)); else if (a == "-i" || a == "--align-min-match-pident") o.p.min_pident = atof(need(i));
     else if (a == "-q" || a == "--min-qcov-per-hsp") o.p.min_qcov_hsp = atof(need(i)); else if (a == "-Q" || a == "--min-qcov-per-genome") o.p.min_qcov_genome = atof(need(i));
     else if (a == "-e" || a == "--max-evalue") o.p.max_evalue = atof(need(i)); else if (a == "--gpu") o.device = atoi(need(i)); else if (a == "--quiet") o.quiet = true;
-    else if (a == "-j" || a == "--threads" || a == "-J" || a == "--max-query-conc" || a == "--max-open-files" || a == "--gc-interval") need(i);   // accepted, meaningless on the GPU path
+    else if (a == "-j" || a == "--threads" || a == "-J" || a == "--max-query-conc" || a == "--max-open-files" || a == "--gc-interval" || a == "-S" || a == "--max-seed-matching-conc") need(i);   // accepted, meaningless on the GPU path
+    else if (a == "-T" || a == "--taxdump" || a == "-G" || a == "--genome2taxid" || a == "-t" || a == "--taxids" || a == "--taxid-file" || a == "-k" || a == "--keep-genomes-without-taxid")
+      die("taxonomy filtering (" + a + ") is not part of the GPU search path; filter the TSV by sgenome afterwards");   // search.go:236-330, out of scope
     else if (a == "-w" || a == "--load-whole-seeds" || a == "--debug") {} else if (a == "-h" || a == "--help") { usage(); return 0; }
     else if (a[0] == '-' && a.size() > 1) die("unknown flag: " + a); else o.files.push_back(a); }
   // option checks, search.go:163-230
