@@ -146,7 +146,7 @@ def main():
     config = {"workload": workload, "queries_per_gpu": CFG["n_queries"], "query_len": CFG["query_len"], "genomes": CFG["families"] * CFG["members"], "masks": 20000,
               "sharding": "by query, index replicated" if a.gpus > 1 else "single GPU", "l2": "index image (>1 GB) and per-batch buffers exceed the 126 MB L2; no explicit flush",
               "seeds": [CFG["genome_seed"], CFG["query_seed"]],
-              "index": "built by lmi-tools with first-round LexicHash seeds only (the writer's --fill-deserts, the reference's default, is off: ~2x fewer seed values)"}
+              "index": "built by lmi-tools with first-round LexicHash seeds only (the writer's --fill-deserts, the reference's default, is off; it would add ~34 % seed values on these genomes)"}
     from oracle_binding import read_fasta
 
     if a.impl == "reference":
