@@ -55,6 +55,9 @@ def ensure_workload(rank):
         t = time.time()
         tmp = idx + ".tmp%d" % os.getpid()
         subprocess.check_call([tools, "index", "--synth", "%d,%d,%d,%d,20" % (CFG["families"], CFG["members"], CFG["genome_len"], CFG["genome_seed"]), "--out", tmp])
+        if os.path.isdir(idx):   # an interrupted earlier build (no info.toml)
+            import shutil
+            shutil.rmtree(idx)
         os.rename(tmp, idx)
         log("index built in %.1fs -> %s" % (time.time() - t, idx))
     qf = os.path.join(WORK, "%s_q%d_%d_r%d.fa" % (name, CFG["n_queries"], CFG["query_len"], rank))
