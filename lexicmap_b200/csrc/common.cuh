@@ -15,6 +15,7 @@ typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t
 
 // Per-index bump arena for the per-batch device buffers: cudaMallocAsync pools showed sporadic 200-300 ms stalls when multi-GB
 // blocks had to be re-mapped between calls; a grow-only arena that is reset after every batch is deterministic.
+struct ArenaExhausted : std::runtime_error { using std::runtime_error::runtime_error; };   // the caller may retry with a smaller batch
 struct Arena {
   struct Chunk { char* base; size_t size; };
   std::vector<Chunk> chunks; size_t cur = 0, off = 0; u64 epoch = 1;   // epoch: bumped by reset(); a buffer from an earlier epoch is already gone and must not rewind the cursor
@@ -24,7 +25,7 @@ struct Arena {
     while (cur < chunks.size() && off + bytes > chunks[cur].size) { cur++; off = 0; }
     if (cur >= chunks.size()) { size_t tot = 0; for (auto& c : chunks) tot += c.size; size_t sz = std::max(bytes, std::max<size_t>(tot / 4, (size_t)1 << 30)); Chunk c; c.size = sz;
       cudaError_t e = cudaMalloc((void**)&c.base, sz); if (e != cudaSuccess) { cudaGetLastError(); c.size = sz = bytes; e = cudaMalloc((void**)&c.base, sz); }
-      if (e != cudaSuccess) throw std::runtime_error(std::string("device arena: cudaMalloc failed: ") + cudaGetErrorString(e)); chunks.push_back(c); cur = chunks.size() - 1; off = 0; }
+      if (e != cudaSuccess) { cudaGetLastError(); throw ArenaExhausted(std::string("device arena: cudaMalloc failed: ") + cudaGetErrorString(e)); } chunks.push_back(c); cur = chunks.size() - 1; off = 0; }
     void* p = chunks[cur].base + off; off += bytes; return p;
   }
   void free(void* p, size_t bytes) { bytes = al(bytes + 64); if (cur < chunks.size() && (char*)p + bytes == chunks[cur].base + off) off -= bytes; }   // LIFO frees are recycled

@@ -25,6 +25,7 @@
 #include <exception>
 #include <set>
 #include <array>
+#include <memory>
 
 // =====================================================================================================
 // small device utilities
@@ -272,6 +273,8 @@ static void upload_queries(lmg_index* ix, const u8* seqs, const u64* off, int nq
   for (int q = 0; q < nq; q++) { u64 L = B.h_off[q + 1] - B.h_off[q]; if (L >= (1ull << 27)) throw std::runtime_error("query longer than 2^27 bases is not supported");
     B.h_boff[q] = b; b += (((L + 3) >> 2) + 16 + 15) & ~15ull; B.h_koff[q] = kk; kk += (L >= (u64)k) ? 2 * (L - k + 1) : 0; }
   B.h_boff[nq] = b; B.h_koff[nq] = kk; B.total_k = kk;
+  // 32-bit index spaces of one sub-batch: (query, mask) slots and k-mer table rows. Larger batches are halved by the caller (search_range).
+  if ((u64)nq * (u64)ix->img.m >= (1ull << 32) || kk >= (1ull << 31)) throw BatchTooLarge("sub-batch exceeds the 2^32 (query, mask) slots or 2^31 k-mer rows of one lane");
   B.h_ascii.assign(seqs + off[0], seqs + off[0] + B.total_bases); B.ascii.alloc(B.total_bases + 16, st); B.ascii.from_host(B.h_ascii.data(), B.total_bases); B.off.alloc(nq + 1, st); B.off.from_host(B.h_off.data(), nq + 1);
   B.boff.alloc(nq + 1, st); B.boff.from_host(B.h_boff.data(), nq + 1); B.koff.alloc(nq + 1, st); B.koff.from_host(B.h_koff.data(), nq + 1);
   B.packed.alloc(b + 64, st); B.packed.zero(); B.amask.alloc(b + 64, st); B.amask.zero();
@@ -454,7 +457,7 @@ template <class T, class KeyFn, class Less> static void bucket_sort(std::vector<
 }
 
 struct Segments { u32 nseg = 0; DBuf<u64> key, off; DBuf<u32> cn; DBuf<u64> c_lo; DBuf<float> score; std::vector<u64> h_key, h_off; };
-struct Chains { u32 n = 0; DBuf<ChainRec> rec; std::vector<ChainRec> h; std::vector<float> seg_score; };
+struct Chains { u32 n = 0; DBuf<ChainRec> rec; std::vector<ChainRec> h; std::vector<float> seg_score; std::vector<char> topn_sorted; };   // topn_sorted[q]: the top-N genome sort ran for query q (it fixes the order of equal genome indexes from different batches)
 
 static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segments& S, Chains& Cn) {
   cudaStream_t st = ix->st; u64 N = A.n; S.nseg = 0; Cn.n = 0; if (N == 0) return;
@@ -481,7 +484,7 @@ static void chain_stage(lmg_index* ix, const lmg_params* prm, Anchors& A, Segmen
   // drop genomes below min score (:1724), optional top-N genomes per query (:1780-1805), order chains by (segment, first TBegin, emission order) (:1967-1974)
   std::vector<char> keep(nseg, 1); for (u32 s = 0; s < nseg; s++) if (Cn.seg_score[s] < P.min_score) keep[s] = 0;
   if (prm->top_n_genomes > 0) { u32 s0 = 0; while (s0 < nseg) { u32 q = (u32)(S.h_key[s0] >> 36), s1 = s0; std::vector<u32> v; while (s1 < nseg && (u32)(S.h_key[s1] >> 36) == q) { if (keep[s1]) v.push_back(s1); s1++; }
-      if ((int)v.size() > prm->top_n_genomes) { std::stable_sort(v.begin(), v.end(), [&](u32 a, u32 b) { return Cn.seg_score[a] > Cn.seg_score[b]; }); for (size_t t = prm->top_n_genomes; t < v.size(); t++) keep[v[t]] = 0; } s0 = s1; } }
+      if ((int)v.size() > prm->top_n_genomes) { if (Cn.topn_sorted.size() <= q) Cn.topn_sorted.resize((size_t)q + 1, 0); Cn.topn_sorted[q] = 1; std::stable_sort(v.begin(), v.end(), [&](u32 a, u32 b) { return Cn.seg_score[a] > Cn.seg_score[b]; }); for (size_t t = prm->top_n_genomes; t < v.size(); t++) keep[v[t]] = 0; } s0 = s1; } }
   std::vector<ChainRec> kept; kept.reserve(nc); for (auto& r : Cn.h) if (keep[r.seg]) { r.score = Cn.seg_score[r.seg]; kept.push_back(r); }
   bucket_sort(kept, nseg, [](const ChainRec& a) { return a.seg; }, [](const ChainRec& a, const ChainRec& b) { if (a.t0 != b.t0) return a.t0 < b.t0; return a.ord < b.ord; });
   Cn.h.swap(kept); Cn.n = (u32)Cn.h.size();
@@ -1080,10 +1083,13 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
   outs[jb] = Rr;
 }
 
+// the dynamic shared-memory ceiling of a kernel is a per-device attribute: raise it once on every device this process runs alignments on
+static void wfa_raise_smem_limit() { static std::mutex mu; static std::set<int> done; int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); std::lock_guard<std::mutex> lk(mu); if (done.count(dev)) return;
+  CUDA_CHECK(cudaFuncSetAttribute(k_wfa_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES)); done.insert(dev); }
 static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBuf<ExtOut>& d_ext, const std::vector<ExtOut>& hext, u32 nj, const u8* qpacked, const u8* qamask, const u64* qboff, const u8* g2bit, const u64* g_off,
                         int want_ops, int adaptive, std::vector<WfaOut>& hw, std::vector<u64>& hops, u64* counters, double* ms, size_t total_mem, int active_lanes = 1) {
     // WFA: fast kernel (packed words + smem ring) for every job, then the general kernel for whatever did not fit
-    { static std::once_flag once; std::call_once(once, [] { CUDA_CHECK(cudaFuncSetAttribute(k_wfa_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES)); }); }
+    wfa_raise_smem_limit();
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
@@ -1135,7 +1141,7 @@ static void build_tree_tables(lmg_index* ix, QBatch& B, DBuf<u64>& tkeys, DBuf<u
 struct HostHsp { i32 qb, qe, tb, te, aligned_q, tpo, max_ext; int job = -1; bool dead = false; i32 alen = 0, matched = 0, gaps = 0, score = 0, bitscore = 0; double evalue = 0, af = 0, pident = 0; std::string cigar, text; };   // text = qseq | sseq | align, alen bytes each (-a output)
 struct HostCluster { u32 seg; u32 item; bool rc, variantA; int nseeds, iseq; std::vector<HostHsp> hsps; double sim = 0; bool has = false; };
 
-struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u32> row_genome; const Image* img = nullptr; };   // sseqid of row i = img->seq_ids[row_genome[i]][rows[i].seq_idx]
+struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u32> row_genome; std::shared_ptr<const std::vector<std::vector<std::string>>> seq_ids; };   // sseqid of row i = (*seq_ids)[row_genome[i]][rows[i].seq_idx]; the host-side id table is shared with the index and outlives lmg_index_close
 
 static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
@@ -1292,24 +1298,35 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<std::vector<lmg_hsp>> trows(NTF); std::vector<std::string> tpool(NTF); std::vector<std::vector<u32>> trg(NTF);
   ix->pool.run(NTF, HT, [&](int ti) {
     std::vector<GenomeOut> gouts; std::vector<lmg_hsp>& rows = trows[ti]; std::string& pool = tpool[ti]; std::vector<u32>& rg = trg[ti];
+    auto seg_q = [&](u32 seg) { return (u32)(S.h_key[seg] >> 36); }; auto seg_g = [&](u32 seg) { return (u32)((S.h_key[seg] >> 2) & 0x3FFFFFFFFull); };
+    // query coverage of a genome = union of its HSPs' query intervals (coverageLen lib-seq_compare.go:270-308); false = below -Q
+    auto coverage = [&](GenomeOut& g) { u32 q = seg_q(g.seg); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
+      int cov = 0; if (reg.size() == 1) cov = reg[0][1] - reg[0][0] + 1; else if (!reg.empty()) { std::stable_sort(reg.begin(), reg.end(), [](const std::array<int, 2>& a, const std::array<int, 2>& b) { return a[0] < b[0]; }); int s0 = reg[0][0], e0 = reg[0][1]; for (size_t i = 1; i < reg.size(); i++) { if (reg[i][0] > e0) { cov += e0 - s0 + 1; s0 = reg[i][0]; e0 = reg[i][1]; continue; } if (reg[i][1] <= e0) continue; e0 = reg[i][1]; } cov += e0 - s0 + 1; }
+      g.af = (double)cov / (double)qlen * 100; if (g.af > 100) g.af = 100; return g.af >= prm->min_qcov_genome; };
     { size_t x = cut[ti]; while (x < cut[ti + 1]) { u32 seg = clusters[x].seg; GenomeOut g; g.seg = seg; g.af = 0; size_t y = x; while (y < cut[ti + 1] && clusters[y].seg == seg) { if (clusters[y].has) g.sds.push_back(&clusters[y]); y++; } x = y; if (g.sds.empty()) continue;
-        u32 q = (u32)(S.h_key[seg] >> 36); i32 qlen = (i32)(B.h_off[q + 1] - B.h_off[q]); std::vector<std::array<int, 2>> reg; for (auto* sd : g.sds) for (const HostHsp& h : sd->hsps) if (!h.dead) reg.push_back({h.qb, h.qe});
-        int cov = 0; if (reg.size() == 1) cov = reg[0][1] - reg[0][0] + 1; else if (!reg.empty()) { std::stable_sort(reg.begin(), reg.end(), [](const std::array<int, 2>& a, const std::array<int, 2>& b) { return a[0] < b[0]; }); int s0 = reg[0][0], e0 = reg[0][1]; for (size_t i = 1; i < reg.size(); i++) { if (reg[i][0] > e0) { cov += e0 - s0 + 1; s0 = reg[i][0]; e0 = reg[i][1]; continue; } if (reg[i][1] <= e0) continue; e0 = reg[i][1]; } cov += e0 - s0 + 1; }
-        g.af = (double)cov / (double)qlen * 100; if (g.af > 100) g.af = 100; if (g.af < prm->min_qcov_genome) continue;
-        std::stable_sort(g.sds.begin(), g.sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); gouts.push_back(std::move(g)); } }
-    size_t x = 0; while (x < gouts.size()) { u32 q = (u32)(S.h_key[gouts[x].seg] >> 36); size_t y = x; while (y < gouts.size() && (u32)(S.h_key[gouts[y].seg] >> 36) == q) y++;
+        if (!I.has_chunks) { if (!coverage(g)) continue; std::stable_sort(g.sds.begin(), g.sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); }   // with split genomes in the index both wait for the merge (:2701)
+        gouts.push_back(std::move(g)); } }
+    size_t x = 0; while (x < gouts.size()) { u32 q = seg_q(gouts[x].seg); size_t y = x; while (y < gouts.size() && seg_q(gouts[y].seg) == q) y++;
       std::vector<GenomeOut*> rs; for (size_t z = x; z < y; z++) rs.push_back(&gouts[z]);
-      auto bgi_of = [&](const GenomeOut* g) { return I.genome_bgi[(u32)((S.h_key[g->seg] >> 2) & 0x3FFFFFFFFull)]; };
+      auto bgi_of = [&](const GenomeOut* g) { return I.genome_bgi[seg_g(g->seg)]; };
+      if (q < Cn.topn_sorted.size() && Cn.topn_sorted[q]) std::stable_sort(rs.begin(), rs.end(), [&](GenomeOut* a, GenomeOut* b) { return Cn.seg_score[a->seg] > Cn.seg_score[b->seg]; });   // the order the top-N selection left (:1780-1805)
       std::stable_sort(rs.begin(), rs.end(), [&](GenomeOut* a, GenomeOut* b) { return (bgi_of(a) & 131071) < (bgi_of(b) & 131071); });    // :1848-1853
+      if (I.has_chunks) {   // merge the chunks of a split genome into the first one (:2797-2852), then coverage, -Q and cluster order on the merged result (:2856-2897)
+        std::vector<GenomeOut*> kept; std::vector<std::pair<u32, GenomeOut*>> first;
+        for (GenomeOut* g : rs) { u32 grp = I.chunk_group[seg_g(g->seg)]; GenomeOut* tgt = nullptr; if (grp != 0xFFFFFFFFu) { for (auto& f : first) if (f.first == grp) tgt = f.second; if (!tgt) first.push_back({grp, g}); }
+          if (tgt) { tgt->sds.insert(tgt->sds.end(), g->sds.begin(), g->sds.end()); g->sds.clear(); } else kept.push_back(g); }
+        rs.clear(); for (GenomeOut* g : kept) { if (!coverage(*g)) continue; std::stable_sort(g->sds.begin(), g->sds.end(), [](const HostCluster* a, const HostCluster* b) { return a->sim > b->sim; }); rs.push_back(g); } }
       std::stable_sort(rs.begin(), rs.end(), [](GenomeOut* a, GenomeOut* b) { return a->sds[0]->sim > b->sds[0]->sim; });                  // :2919-2921
-      for (GenomeOut* g : rs) { u32 gd = (u32)((S.h_key[g->seg] >> 2) & 0x3FFFFFFFFull);
-        std::vector<const HostCluster*> ord; std::vector<char> used(g->sds.size(), 0);   // SortBySeqID :1042-1096
-        for (size_t i = 0; i < g->sds.size(); i++) { if (used[i]) continue; for (size_t j = i; j < g->sds.size(); j++) if (!used[j] && g->sds[j]->iseq == g->sds[i]->iseq) { used[j] = 1; ord.push_back(g->sds[j]); } }
-        int cls = 1, j = 1; for (const HostCluster* sd : ord) { for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[gd].size(); r.chunk_idx = 0; r.n_chunks = 1; r.seq_len = (i32)I.seq_sizes[gd][sd->iseq];
+      for (GenomeOut* g : rs) { u32 gd = seg_g(g->seg);
+        std::vector<const HostCluster*> ord; std::vector<char> used(g->sds.size(), 0);   // SortBySeqID :1042-1096 (compares the sequence IDs)
+        auto sid = [&](const HostCluster* c) -> const std::string& { return I.seq_ids[seg_g(c->seg)][c->iseq]; };
+        for (size_t i = 0; i < g->sds.size(); i++) { if (used[i]) continue; for (size_t j = i; j < g->sds.size(); j++) if (!used[j] && (g->sds[j] == g->sds[i] || sid(g->sds[j]) == sid(g->sds[i]))) { used[j] = 1; ord.push_back(g->sds[j]); } }
+        int cls = 1, j = 1; for (const HostCluster* sd : ord) { const u32 sg = seg_g(sd->seg);   // sg: the chunk this cluster was found in (== gd unless chunks were merged)
+          for (const HostHsp& h : sd->hsps) { if (h.dead) continue; lmg_hsp r; memset(&r, 0, sizeof r); r.query = q; r.hits = (u32)rs.size(); r.genome = I.genome_bgi[gd]; r.seq_idx = sd->iseq; r.n_seqs = (u32)I.seq_ids[sg].size(); r.chunk_idx = I.chunk_idx[sg]; r.n_chunks = I.chunk_n[sg]; r.seq_len = (i32)I.seq_sizes[sg][sd->iseq];
             r.cls = cls; r.hsp = j; r.qb = h.qb; r.qe = h.qe; r.tb = h.tb; r.te = h.te; r.rc = sd->rc; r.alen = h.alen; r.matches = h.matched; r.gaps = h.gaps; r.score = h.score; r.bitscore = h.bitscore; r.evalue = h.evalue; r.qcov_hsp = h.af; r.pident = h.pident; r.qcov_gnm = g->af;
-            r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; pool += h.text; rows.push_back(r); rg.push_back(gd); j++; } cls++; } }
+            r.cigar_off = pool.size(); r.cigar_len = (u32)h.cigar.size(); pool += h.cigar; pool += h.text; rows.push_back(r); rg.push_back(sg); j++; } cls++; } }
       x = y; } });
-  { size_t nr = 0; for (auto& v : trows) nr += v.size(); R.rows.reserve(nr); R.row_genome.reserve(nr); for (int ti = 0; ti < NTF; ti++) { u64 po = R.pool.size(); for (lmg_hsp& r : trows[ti]) { r.cigar_off += po; R.rows.push_back(r); } R.pool += tpool[ti]; R.row_genome.insert(R.row_genome.end(), trg[ti].begin(), trg[ti].end()); } R.img = &I; }
+  { size_t nr = 0; for (auto& v : trows) nr += v.size(); R.rows.reserve(nr); R.row_genome.reserve(nr); for (int ti = 0; ti < NTF; ti++) { u64 po = R.pool.size(); for (lmg_hsp& r : trows[ti]) { r.cigar_off += po; R.rows.push_back(r); } R.pool += tpool[ti]; R.row_genome.insert(R.row_genome.end(), trg[ti].begin(), trg[ti].end()); } R.seq_ids = I.seq_ids_p; }
   lap("group+rows");
   T.mark(); finish_times(7);                                                                             // [6] finish (host)
 }
@@ -1371,7 +1388,6 @@ int lmg_anchor_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, co
 }
 
 
-#define LMG_HAVE_CHAIN 1
 int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_chain** out, uint64_t* n_out) {
   try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); ArenaReset ar_(ix); QBatch B; upload_queries(ix, seqs, off, n, B); sketch_tables(ix, B); Survivors SV; probe_survivors(ix, B, p, SV, nullptr, nullptr);
     Anchors A; seed_probe(ix, B, p, SV, A, false); Segments S; Chains C; chain_stage(ix, p, A, S, C);
@@ -1381,7 +1397,6 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
     *out = o; *n_out = C.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 
-#define LMG_HAVE_SEARCH 1
 struct lmg_queries { std::vector<QBatch> parts; std::vector<int> cut; };
 // Runs the pipeline over L sub-batches concurrently (one host thread, stream and arena per lane) and concatenates the rows in query order.
 // Queries are independent all the way through the reference path (search.go:437-533 handles one query at a time), so the split is exact.
@@ -1389,15 +1404,17 @@ struct lmg_queries { std::vector<QBatch> parts; std::vector<int> cut; };
 static void search_range(lmg_index* lx, const lmg_params* p, const u8* seqs, const u64* off, int n, lmg_results& R, QBatch* staged) {
   try { ArenaReset ar_(lx); search_pipeline(lx, p, seqs, off, n, R, staged); return; }
   catch (BatchTooLarge& e) { if (n < 2) throw std::runtime_error(std::string(e.what()) + " (a single query)"); }
+  catch (ArenaExhausted& e) { cudaGetLastError(); if (n < 2) throw std::runtime_error(std::string(e.what()) + " (a single query)"); }   // the sub-batch's buffers do not fit in HBM next to the image: halve it
   if (staged) { seqs = staged->h_ascii.data(); off = staged->h_off.data(); }   // the host copy made at upload time
   R = lmg_results(); const u64 mid = off[0] + (off[n] - off[0]) / 2; int h = 1; while (h < n - 1 && off[h] < mid) h++;
   lmg_results R2; double ms[16]; u64 cn[16]; search_range(lx, p, seqs, off, h, R, nullptr); for (int i = 0; i < 16; i++) { ms[i] = lx->ms[i]; cn[i] = lx->counters[i]; }
   search_range(lx, p, seqs, off + h, n - h, R2, nullptr); for (int i = 0; i < 16; i++) if (i != 12) { lx->ms[i] += ms[i]; if (i != 14) lx->counters[i] += cn[i]; }
-  u64 po = R.pool.size(); for (lmg_hsp& r : R2.rows) { r.query += (u32)h; r.cigar_off += po; R.rows.push_back(r); } R.pool += R2.pool; R.row_genome.insert(R.row_genome.end(), R2.row_genome.begin(), R2.row_genome.end()); R.img = &lx->img;
+  u64 po = R.pool.size(); for (lmg_hsp& r : R2.rows) { r.query += (u32)h; r.cigar_off += po; R.rows.push_back(r); } R.pool += R2.pool; R.row_genome.insert(R.row_genome.end(), R2.row_genome.begin(), R2.row_genome.end()); R.seq_ids = lx->img.seq_ids_p;
 }
 
 static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, const u64* off, int nq, lmg_results& R, lmg_queries* staged) {
   auto w0 = std::chrono::steady_clock::now(); const int dev = ix->img.device; CUDA_CHECK(cudaSetDevice(dev));
+  if (ix->img.n_shards > 1 && p->top_n_genomes > 0) throw std::runtime_error("--top-n-genomes cannot be applied inside one genome shard (the top N are chosen over all genomes): search the shards without it and select after merging");
   std::vector<int> cut = staged ? staged->cut : lane_cuts(off, nq, pick_lanes(p, nq, off[nq] - off[0])); const int L = (int)cut.size() - 1;
   if (L == 1) { ix->active_lanes = 1; search_range(ix, p, seqs, off, nq, R, staged ? &staged->parts[0] : nullptr); }
   else {
@@ -1406,7 +1423,7 @@ static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, con
       catch (std::exception& e) { err[l] = e.what(); if (err[l].empty()) err[l] = "error"; cudaGetLastError(); } };
     std::vector<std::thread> th; for (int l = 1; l < L; l++) th.emplace_back(work, l); work(0); for (auto& t : th) t.join();
     for (int l = 0; l < L; l++) if (!err[l].empty()) throw std::runtime_error(err[l]);
-    size_t nr = 0, np = 0; for (auto& r : Rl) { nr += r.rows.size(); np += r.pool.size(); } R.rows.reserve(nr); R.row_genome.reserve(nr); R.pool.reserve(np); R.img = &ix->img;
+    size_t nr = 0, np = 0; for (auto& r : Rl) { nr += r.rows.size(); np += r.pool.size(); } R.rows.reserve(nr); R.row_genome.reserve(nr); R.pool.reserve(np); R.seq_ids = ix->img.seq_ids_p;
     for (int l = 0; l < L; l++) { u64 po = R.pool.size(); for (lmg_hsp& r : Rl[l].rows) { r.query += (u32)cut[l]; r.cigar_off += po; R.rows.push_back(r); } R.pool += Rl[l].pool; R.row_genome.insert(R.row_genome.end(), Rl[l].row_genome.begin(), Rl[l].row_genome.end()); }
     // timers and counters: summed over the lanes (the lanes overlap, so stage sums exceed the wall time in ms[7])
     double msum[16] = {0}; u64 csum[16] = {0}; for (int l = 0; l < L; l++) for (int i = 0; i < 16; i++) { msum[i] += lx[l]->ms[i]; csum[i] += lx[l]->counters[i]; }
@@ -1416,14 +1433,13 @@ static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, con
   ix->ms[12] = (double)L; ix->ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
 }
 int lmg_search_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; if (n <= 0) { R->img = &ix->img; *out = R; return 0; }   /* empty batch: no rows */ try { search_lanes(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; if (n <= 0) { R->seq_ids = ix->img.seq_ids_p; *out = R; return 0; }   /* empty batch: no rows */ try { search_lanes(ix, p, seqs, off, n, *R, nullptr); } catch (...) { delete R; throw; } *out = R; return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 int lmg_results_rows(const lmg_results* r, const lmg_hsp** rows, uint64_t* n_rows, const char** pool, uint64_t* pool_len) { *rows = r->rows.data(); *n_rows = r->rows.size(); if (pool) *pool = r->pool.data(); if (pool_len) *pool_len = r->pool.size(); return 0; }
-int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) { if (row >= r->rows.size() || !r->img) return -1; *seqid = r->img->seq_ids[r->row_genome[row]][r->rows[row].seq_idx].c_str(); return 0; }
+int lmg_results_seq_id(const lmg_results* r, uint64_t row, const char** seqid) { if (row >= r->rows.size() || !r->seq_ids) return -1; *seqid = (*r->seq_ids)[r->row_genome[row]][r->rows[row].seq_idx].c_str(); return 0; }
 void lmg_results_free(lmg_results* r) { delete r; }
 
-#define LMG_HAVE_WFA 1
 int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t n, int32_t adaptive, char** cigars, uint64_t* cigars_len) {
   try { CUDA_CHECK(cudaSetDevice(device)); cudaStream_t st = 0; std::vector<u8> qp, tp, qmk; std::vector<u64> qo(n + 1), to(n + 1); std::vector<HspJob> jobs(n); std::vector<ExtOut> ex(n);
     auto pack = [](const u8* s, u64 len, std::vector<u8>& out) { while (out.size() & 15) out.push_back(0); u64 o = out.size(); out.resize(o + (len + 3) / 4 + 16, 0); for (u64 i = 0; i < len; i++) out[o + (i >> 2)] |= (u8)(base2bit(s[i]) << (6 - 2 * (i & 3))); return o; };
@@ -1441,27 +1457,11 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
 
 int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_queries** out) {
   try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); lmg_queries* Q = new lmg_queries; Q->cut = lane_cuts(off, n, pick_lanes(nullptr, n, off[n] - off[0])); const int L = (int)Q->cut.size() - 1; Q->parts.resize(L);
-    for (int l = 0; l < L; l++) { lmg_index* lx = lane_ctx(ix, l); upload_queries(lx, seqs, off + Q->cut[l], Q->cut[l + 1] - Q->cut[l], Q->parts[l]); CUDA_CHECK(cudaStreamSynchronize(lx->st)); } *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+    for (int l = 0; l < L && n > 0; l++) { lmg_index* lx = lane_ctx(ix, l); upload_queries(lx, seqs, off + Q->cut[l], Q->cut[l + 1] - Q->cut[l], Q->parts[l]); CUDA_CHECK(cudaStreamSynchronize(lx->st)); } *out = Q; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int lmg_search_staged(lmg_index* ix, const lmg_params* p, lmg_queries* q, lmg_results** out) {
-  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; try { search_lanes(ix, p, nullptr, nullptr, q->cut.back(), *R, q); } catch (...) { delete R; throw; } *out = R; return 0; }
+  try { std::lock_guard<std::mutex> lk(ix->mu); lmg_results* R = new lmg_results; if (q->cut.back() <= 0) { R->seq_ids = ix->img.seq_ids_p; *out = R; return 0; }   /* empty batch: no rows, nothing launched */ try { search_lanes(ix, p, nullptr, nullptr, q->cut.back(), *R, q); } catch (...) { delete R; throw; } *out = R; return 0; }
   catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 void lmg_queries_free(lmg_index* ix, lmg_queries* q) { if (!q) return; cudaSetDevice(ix->img.device); delete q; }
 }  // extern "C"
-
-// ---- not yet implemented entry points (fail loudly)
-extern "C" {
-#ifndef LMG_HAVE_CHAIN
-int lmg_chain_batch(lmg_index*, const lmg_params*, const uint8_t*, const uint64_t*, int32_t, lmg_chain**, uint64_t*) { g_err = "lmg_chain_batch: not implemented"; return -2; }
-#endif
-#ifndef LMG_HAVE_SEARCH
-int lmg_search_batch(lmg_index*, const lmg_params*, const uint8_t*, const uint64_t*, int32_t, lmg_results**) { g_err = "lmg_search_batch: not implemented"; return -2; }
-int lmg_results_rows(const lmg_results*, const lmg_hsp**, uint64_t*, const char**, uint64_t*) { return -2; }
-int lmg_results_seq_id(const lmg_results*, uint64_t, const char**) { return -2; }
-void lmg_results_free(lmg_results*) {}
-#endif
-#ifndef LMG_HAVE_WFA
-int lmg_wfa_batch(int, const uint8_t*, const uint64_t*, int32_t, int32_t, char**, uint64_t*) { g_err = "lmg_wfa_batch: not implemented"; return -2; }
-#endif
-}

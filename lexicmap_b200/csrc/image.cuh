@@ -11,6 +11,7 @@
 #include "lmi_format.hpp"
 #include <omp.h>
 #include <unordered_map>
+#include <memory>
 
 struct Image {
   // scalars
@@ -22,14 +23,16 @@ struct Image {
   u32* d_mask_pstart = nullptr; int mask_pbits = 14;   // masks bucketed by their mask_prefix leading bases: [pstart[p], pstart[p+1])
   u8* d_g2bit = nullptr; u64* d_g_off = nullptr; u32 *d_g_nbases = nullptr, *d_g_seq_off = nullptr, *d_seq_sizes = nullptr; u32* d_batch_base = nullptr;
   // host metadata
-  std::vector<u64> h_masks; std::vector<std::string> genome_names; std::vector<u64> genome_bgi; std::vector<std::vector<std::string>> seq_ids; std::vector<std::vector<u32>> seq_sizes;
+  std::vector<u64> h_masks; std::vector<std::string> genome_names; std::vector<u64> genome_bgi; std::shared_ptr<std::vector<std::vector<std::string>>> seq_ids_p = std::make_shared<std::vector<std::vector<std::string>>>(); std::vector<std::vector<std::string>>& seq_ids = *seq_ids_p; std::vector<std::vector<u32>> seq_sizes; int n_shards = 1, shard = 0;
   std::vector<u8> h_g2bit; std::vector<u64> h_g_off;   // host copy of the 2-bit genomes: alignment text of the -a output
   std::vector<u32> batch_base, h_nbases; std::unordered_map<u64, u32> bgi2dense; lmi::IndexInfo info;
+  // split genomes (genomes.chunks.bin): per dense genome its chunk group (0xFFFFFFFF = not split), chunk index and chunk count (lib-index-search.go:504-537)
+  bool has_chunks = false; std::vector<u32> chunk_group, chunk_idx, chunk_n;
 
   template <class T> T* up(const std::vector<T>& h) { T* d = nullptr; size_t b = std::max<size_t>(h.size(), 1) * sizeof(T) + 64; CUDA_CHECK(cudaMalloc((void**)&d, b)); if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); bytes += b; return d; }
 
   void load(const std::string& dir, int dev, int shard, int n_shards) {
-    device = dev; CUDA_CHECK(cudaSetDevice(dev));
+    device = dev; CUDA_CHECK(cudaSetDevice(dev)); this->n_shards = n_shards; this->shard = shard;
     info = lmi::read_info(dir + "/info.toml"); k = info.k; m = info.masks; contig_interval = info.contig_interval; total_bases = info.input_bases;
     if (k != 31) lmi::die("only k=31 indexes are supported by the GPU path (SeqComparatorOptions.K is fixed to 31, search.go:361)");
     mask_prefix = std::max((int)(std::log2((double)m) / 2), 1); anchor_prefix = std::max((int)(std::log2((double)info.partitions) / 2), 1); NA = 1 << (2 * anchor_prefix);  // lib-index-search.go:467-469
@@ -45,6 +48,8 @@ struct Image {
     }
     { auto gm = lmi::read_genome_map(dir + "/genomes.map.bin"); for (auto& e : gm) { auto it = bgi2dense.find(e.second); if (it != bgi2dense.end()) genome_names[it->second] = e.first; } }
     g2bit.resize(g2bit.size() + 64, 0); g_off.push_back(g2bit.size()); G = (int)genome_bgi.size();
+    { auto gc = lmi::read_genome_chunks(dir + "/genomes.chunks.bin"); chunk_group.assign(G, 0xFFFFFFFFu); chunk_idx.assign(G, 0); chunk_n.assign(G, 1);
+      for (size_t gr = 0; gr < gc.size(); gr++) for (size_t i = 0; i < gc[gr].size(); i++) { auto it = bgi2dense.find(gc[gr][i]); if (it == bgi2dense.end()) lmi::die("genomes.chunks.bin names a genome that is not in the index"); has_chunks = true; chunk_group[it->second] = (u32)gr; chunk_idx[it->second] = (u32)i; chunk_n[it->second] = (u32)gc[gr].size(); } }
     h_nbases = g_nbases; h_g_off = g_off; h_g2bit = g2bit; d_g2bit = up(g2bit); d_g_off = up(g_off); d_g_nbases = up(g_nbases); d_g_seq_off = up(g_seq_off); d_seq_sizes = up(seqsz); d_batch_base = up(batch_base);
     // ---- seeds: decode every chunk (host, one thread per chunk), flatten
     std::vector<lmi::KvChunk> chunks(info.chunks);

@@ -6,8 +6,8 @@
 // positions, both strands (:1028); DUST / homopolymer filter (:1033-1046); value packing (:708-716); every
 // captured k-mer stored a second time base-reversed under argmin_j(mask_j XOR rev) with the reversed flag
 // (:776-890); per-chunk kv-data + anchor index (:1856-1901); genomes.bin, genomes.map.bin, masks.bin, info.toml.
-// NOT done (documented in DESIGN.md): seed-desert filling (:1086-1500) — indexes are written with
-// max-seed-dist = 0 in info.toml to mark that; genome splitting, batches > 1, merging, soft-masking.
+// Seed-desert filling (:1086-1500) is restated below and ON by default, as in `lexicmap index`
+// (--no-fill-deserts writes max-seed-dist = 0 in info.toml to mark its absence).
 //
 // LexicHash masks: the reference generates them with lexichash.NewWithSeed(k, m, seed, p) (Go math/rand; not
 // reproducible here). We generate our own mask set with the same structural properties documented in
@@ -210,53 +210,90 @@ static void fill_deserts(const uint8_t* seq, size_t n, int k, const std::vector<
 }
 
 struct BuildOpts { int k = 31, masks = 20000, chunks = 16, partitions = 4096, contig_interval = 1000; int64_t seed = 1; int threads = 0;
-  bool fill_deserts = false; int max_desert = 100, seed_dist = 50; };   // --fill-deserts, -D/--seed-max-desert, -d/--seed-in-desert-dist (index.go:582-586)
+  bool fill_deserts = true; int max_desert = 100, seed_dist = 50; int64_t max_genome = 15000000; int batch_size = 0; };   // -g/--max-genome (index.go:146), -b/--batch-size (0 = all genomes in one batch)
+  //   // on by default like `lexicmap index` (index.go:115-119,210-211); --no-fill-deserts, -D/--seed-max-desert, -d/--seed-in-desert-dist (index.go:582-586)
 
 template <class GetGenome>
 static void build_index(const std::string& out, size_t n_genomes, GetGenome get, const BuildOpts& o) {
-  if (n_genomes == 0) die("no genomes"); if (n_genomes > (1u << BITS_GENOME_IDX)) die("more than 131072 genomes per batch is not supported by this minimal writer");
-  const int k = o.k; mkdir_p(out); mkdir_p(out + "/seeds"); mkdir_p(batch_dir(out, 0));
+  if (n_genomes == 0) die("no genomes");
+  const int k = o.k; mkdir_p(out); mkdir_p(out + "/seeds");
   std::vector<uint64_t> masks = gen_masks(k, o.masks, o.seed); write_masks(out + "/masks.bin", masks, k, o.seed);
   const int mask_prefix = std::max((int)(std::log2((double)o.masks) / 2), 1), anchor_prefix = std::max((int)(std::log2((double)o.partitions) / 2), 1);
   int nt = o.threads > 0 ? o.threads : omp_get_max_threads();
   int mask_p = 0; while ((1ull << (2 * (mask_p + 1))) <= masks.size()) mask_p++;   // same prefix directory as capture_sequence
   std::vector<uint32_t> mask_pstart(((size_t)1 << (2 * mask_p)) + 1, 0); for (uint64_t mk : masks) mask_pstart[(mk >> (2 * (k - mask_p))) + 1]++; for (size_t i = 0; i + 1 < mask_pstart.size(); i++) mask_pstart[i + 1] += mask_pstart[i];
-  std::vector<std::vector<Tuple>> tl(nt); std::vector<GenomeRec> recs(n_genomes); int64_t total_bases = 0; long long n_extra = 0;
+  // Genome units: input genome gi is unit gi; a genome whose concatenated contigs exceed --max-genome is split at contig boundaries
+  // (lib-index-build.go:1573-1660) and its further chunks become extra units (provisional serial >= n_genomes, renumbered below in (gi, chunk) order).
+  // Unit u lives in genome batch u / batch_size as genome u % batch_size (batches of -b/--batch-size genomes, lib-index-build.go:560-720 + merge).
+  struct Extra { size_t gi; int chunk; uint32_t prov; GenomeRec rec; };
+  std::vector<std::vector<Tuple>> tl(nt); std::vector<GenomeRec> recs(n_genomes); std::vector<Extra> extras; std::vector<char> dropped(n_genomes, 0); int64_t total_bases = 0; long long n_extra = 0; uint32_t next_prov = (uint32_t)n_genomes;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(+ : total_bases, n_extra)
   for (size_t gi = 0; gi < n_genomes; gi++) {
-    InGenome g = get(gi); GenomeRec& r = recs[gi]; r.id = g.id; std::vector<uint8_t> codes; std::vector<std::pair<int64_t, int64_t>> skip;
-    for (size_t c = 0; c < g.seqs.size(); c++) {
-      if (c > 0) { skip.push_back({(int64_t)codes.size(), (int64_t)codes.size() + o.contig_interval - 1}); codes.insert(codes.end(), o.contig_interval, 0); }
-      const std::string& s = g.seqs[c]; size_t b0 = codes.size(); codes.resize(b0 + s.size());
-      // gap regions: runs of >= 5 N's are skip regions (lib-gaps.go; lib-index-build.go:992-1016)
-      size_t run = 0; for (size_t i = 0; i < s.size(); i++) { codes[b0 + i] = base2bit((uint8_t)s[i]); bool isn = (s[i] == 'N' || s[i] == 'n');
-        if (isn) run++; if ((!isn || i + 1 == s.size()) && run) { size_t end = isn ? i + 1 : i; if (run >= 5) skip.push_back({(int64_t)(b0 + end - run), (int64_t)(b0 + end - 1)}); run = 0; } }
-      r.seq_sizes.push_back((uint32_t)s.size()); r.seq_ids.push_back(g.seq_ids[c]); r.genome_size += (uint32_t)s.size();
-    }
-    std::sort(skip.begin(), skip.end());
-    if (codes.size() >= (1u << BITS_POSITION)) die("genome too large: " + g.id);
-    r.concat_len = (uint32_t)codes.size(); total_bases += r.genome_size;
-    r.twobit.assign((codes.size() + 3) / 4, 0); for (size_t i = 0; i < codes.size(); i++) r.twobit[i >> 2] |= codes[i] << (6 - 2 * (i & 3));
-    Capture cap; capture_sequence(codes.data(), codes.size(), k, masks, skip, cap);
-    std::vector<Tuple>& T = tl[omp_get_thread_num()]; const uint64_t gshift = (uint64_t)gi << BITS_NONE_IDX;  // batch 0
-    if (o.fill_deserts) { static thread_local DesertScratch scratch; std::vector<ExtraSeed> ex; fill_deserts(codes.data(), codes.size(), k, masks, mask_pstart, mask_p, skip, cap, o.max_desert, o.seed_dist, ex, scratch);
-      for (const ExtraSeed& e : ex) { uint64_t rv = kmer_reverse(e.kmer, k); uint32_t dj = xor_argmin_mask(masks, rv);   // extra k-mers enter like captured ones, incl. the reversed copy (:726-760, :845-890)
-        T.push_back({e.mask, e.mask, e.kmer, gshift | (((uint64_t)e.loc << 1) & MASK_NONE_IDX)});
-        T.push_back({dj, e.mask | 0x80000000u, rv, gshift | ((((uint64_t)e.loc << 1) | 1) & MASK_NONE_IDX)}); }
-      n_extra += ex.size(); }
-    for (size_t j = 0; j < masks.size(); j++) {
-      uint64_t km = cap.kmer[j]; if (cap.locs[j].empty() || is_low_complexity(km, k)) continue;
-      uint64_t rv = kmer_reverse(km, k); uint32_t dj = xor_argmin_mask(masks, rv);
-      for (uint32_t loc : cap.locs[j]) {
-        T.push_back({(uint32_t)j, (uint32_t)j, km, gshift | (((uint64_t)loc << 1) & MASK_NONE_IDX)});
-        T.push_back({dj, (uint32_t)j | 0x80000000u, rv, gshift | ((((uint64_t)loc << 1) | 1) & MASK_NONE_IDX)});
+    InGenome g = get(gi);
+    std::vector<std::pair<size_t, size_t>> chunks; { size_t c0 = 0; int64_t sz = 0; bool too_big = false;
+      for (size_t c = 0; c < g.seqs.size(); c++) { int64_t L = (int64_t)g.seqs[c].size(); if (o.max_genome > 0 && L > o.max_genome) { too_big = true; break; }    // a single sequence above the limit: the genome is skipped (:1596-1612)
+        if (o.max_genome > 0 && c > c0 && sz + L > o.max_genome) { chunks.push_back({c0, c}); c0 = c; sz = 0; }
+        sz += L + (c > c0 ? o.contig_interval : 0); }
+      if (too_big || g.seqs.empty()) { dropped[gi] = 1; fprintf(stderr, "[lmi-build] skipping %s: %s\n", g.id.c_str(), too_big ? "a sequence is larger than --max-genome" : "no valid sequences"); continue; }
+      chunks.push_back({c0, g.seqs.size()}); }
+    for (size_t ch = 0; ch < chunks.size(); ch++) {
+      GenomeRec rl; GenomeRec& r = ch == 0 ? recs[gi] : rl; uint32_t unit = (uint32_t)gi;
+      if (ch > 0) {
+#pragma omp critical(lmi_extra)
+        unit = next_prov++; }
+      r.id = g.id; std::vector<uint8_t> codes; std::vector<std::pair<int64_t, int64_t>> skip;
+      for (size_t c = chunks[ch].first; c < chunks[ch].second; c++) {
+        if (c > chunks[ch].first) { skip.push_back({(int64_t)codes.size(), (int64_t)codes.size() + o.contig_interval - 1}); codes.insert(codes.end(), o.contig_interval, 0); }
+        const std::string& s = g.seqs[c]; size_t b0 = codes.size(); codes.resize(b0 + s.size());
+        // gap regions: runs of >= 5 N's are skip regions (lib-gaps.go; lib-index-build.go:992-1016)
+        size_t run = 0; for (size_t i = 0; i < s.size(); i++) { codes[b0 + i] = base2bit((uint8_t)s[i]); bool isn = (s[i] == 'N' || s[i] == 'n');
+          if (isn) run++; if ((!isn || i + 1 == s.size()) && run) { size_t end = isn ? i + 1 : i; if (run >= 5) skip.push_back({(int64_t)(b0 + end - run), (int64_t)(b0 + end - 1)}); run = 0; } }
+        r.seq_sizes.push_back((uint32_t)s.size()); r.seq_ids.push_back(g.seq_ids[c]); r.genome_size += (uint32_t)s.size();
       }
+      std::sort(skip.begin(), skip.end());
+      if (codes.size() >= (1u << BITS_POSITION)) die("genome too large: " + g.id);
+      r.concat_len = (uint32_t)codes.size(); total_bases += r.genome_size;
+      r.twobit.assign((codes.size() + 3) / 4, 0); for (size_t i = 0; i < codes.size(); i++) r.twobit[i >> 2] |= codes[i] << (6 - 2 * (i & 3));
+      Capture cap; capture_sequence(codes.data(), codes.size(), k, masks, skip, cap);
+      std::vector<Tuple>& T = tl[omp_get_thread_num()]; const uint64_t gshift = (uint64_t)unit << BITS_NONE_IDX;  // unit serial for now; batch | index after renumbering
+      if (o.fill_deserts) { static thread_local DesertScratch scratch; std::vector<ExtraSeed> ex; fill_deserts(codes.data(), codes.size(), k, masks, mask_pstart, mask_p, skip, cap, o.max_desert, o.seed_dist, ex, scratch);
+        for (const ExtraSeed& e : ex) { uint64_t rv = kmer_reverse(e.kmer, k); uint32_t dj = xor_argmin_mask(masks, rv);   // extra k-mers enter like captured ones, incl. the reversed copy (:726-760, :845-890)
+          T.push_back({e.mask, e.mask, e.kmer, gshift | (((uint64_t)e.loc << 1) & MASK_NONE_IDX)});
+          T.push_back({dj, e.mask | 0x80000000u, rv, gshift | ((((uint64_t)e.loc << 1) | 1) & MASK_NONE_IDX)}); }
+        n_extra += ex.size(); }
+      for (size_t j = 0; j < masks.size(); j++) {
+        uint64_t km = cap.kmer[j]; if (cap.locs[j].empty() || is_low_complexity(km, k)) continue;
+        uint64_t rv = kmer_reverse(km, k); uint32_t dj = xor_argmin_mask(masks, rv);
+        for (uint32_t loc : cap.locs[j]) {
+          T.push_back({(uint32_t)j, (uint32_t)j, km, gshift | (((uint64_t)loc << 1) & MASK_NONE_IDX)});
+          T.push_back({dj, (uint32_t)j | 0x80000000u, rv, gshift | ((((uint64_t)loc << 1) | 1) & MASK_NONE_IDX)});
+        }
+      }
+      if (ch > 0) {
+#pragma omp critical(lmi_extra)
+        extras.push_back(Extra{gi, (int)ch, unit, std::move(rl)}); }
     }
   }
-  // genomes.bin + map
-  { GenomeWriter gw(batch_dir(out, 0) + "/genomes.bin", 0); std::vector<std::pair<std::string, uint64_t>> gm;
-    for (size_t gi = 0; gi < n_genomes; gi++) { gw.write(recs[gi]); gm.push_back({recs[gi].id, (uint64_t)gi}); recs[gi].twobit.clear(); recs[gi].twobit.shrink_to_fit(); }
-    gw.close(); write_genome_map(out + "/genomes.map.bin", gm); FileW gc(out + "/genomes.chunks.bin"); gc.close(); }
+  // final unit numbering: kept input genomes in input order, then the extra chunks in (genome, chunk) order
+  std::sort(extras.begin(), extras.end(), [](const Extra& a, const Extra& b) { return a.gi != b.gi ? a.gi < b.gi : a.chunk < b.chunk; });
+  std::vector<uint32_t> unit_of(next_prov, 0xFFFFFFFFu); std::vector<GenomeRec*> units; for (size_t gi = 0; gi < n_genomes; gi++) if (!dropped[gi]) { unit_of[gi] = (uint32_t)units.size(); units.push_back(&recs[gi]); }
+  for (Extra& e : extras) { unit_of[e.prov] = (uint32_t)units.size(); units.push_back(&e.rec); }
+  if (units.empty()) die("no genomes left to index");
+  const size_t NU = units.size(); const size_t bsz = o.batch_size > 0 ? (size_t)o.batch_size : NU; if (bsz > (1u << BITS_GENOME_IDX)) die("more than 131072 genomes per batch: use --batch-size"); const size_t nb = (NU + bsz - 1) / bsz; if (nb > (1u << BITS_BATCH_IDX)) die("too many genome batches");
+  auto bgi_of = [&](uint32_t unit) { return ((uint64_t)(unit / bsz) << BITS_GENOME_IDX) | (uint64_t)(unit % bsz); };
+  { bool ident = extras.empty() && nb == 1; for (size_t gi = 0; gi < n_genomes && ident; gi++) if (dropped[gi]) ident = false;
+    if (!ident) {
+#pragma omp parallel for schedule(static) num_threads(nt)
+      for (int t = 0; t < nt; t++) for (Tuple& x : tl[t]) x.value = (bgi_of(unit_of[x.value >> BITS_NONE_IDX]) << BITS_NONE_IDX) | (x.value & MASK_NONE_IDX); } }
+  // genomes.bin per batch + map + chunk lists
+  { std::vector<std::pair<std::string, uint64_t>> gm;
+    for (size_t b = 0; b < nb; b++) { mkdir_p(batch_dir(out, (int)b)); GenomeWriter gw(batch_dir(out, (int)b) + "/genomes.bin", (int)b);
+      for (size_t u = b * bsz; u < std::min(NU, (b + 1) * bsz); u++) { gw.write(*units[u]); gm.push_back({units[u]->id, bgi_of((uint32_t)u)}); units[u]->twobit.clear(); units[u]->twobit.shrink_to_fit(); } gw.close(); }
+    write_genome_map(out + "/genomes.map.bin", gm);
+    FileW gc(out + "/genomes.chunks.bin");   // per split genome: #chunks, then the batch+genome index of every chunk (big endian u64s, :1795-1812)
+    for (size_t x = 0; x < extras.size();) { size_t y = x; while (y < extras.size() && extras[y].gi == extras[x].gi) y++; gc.be((uint64_t)(y - x + 1), 8); gc.be(bgi_of(unit_of[extras[x].gi]), 8); for (size_t z = x; z < y; z++) gc.be(bgi_of(unit_of[extras[z].prov]), 8); x = y; }
+    gc.close(); }
+  const size_t n_units = NU, n_batches = nb; size_t n_input = 0; for (size_t gi = 0; gi < n_genomes; gi++) if (!dropped[gi]) n_input++;
   // seeds
   std::vector<Tuple> all; { size_t tot = 0; for (auto& v : tl) tot += v.size(); all.reserve(tot); for (auto& v : tl) { all.insert(all.end(), v.begin(), v.end()); std::vector<Tuple>().swap(v); } }
   __gnu_parallel::sort(all.begin(), all.end(), tuple_less);
@@ -265,7 +302,7 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
   for (int c = 0; c < o.chunks; c++) {
     int begin = c * chunk_size, end = std::min(begin + chunk_size, o.masks); if (begin >= end) continue;
-    KvWriter w(chunk_file(out, c), k, begin, end - begin, mask_prefix, anchor_prefix, true /* nbatches(1) <= 512 */);
+    KvWriter w(chunk_file(out, c), k, begin, end - begin, mask_prefix, anchor_prefix, n_batches <= 512 /* 7-byte values, kv-data.go:126-137 */);
     std::vector<KvEntry> ent;
     for (int j = begin; j < end; j++) {
       ent.clear();
@@ -275,9 +312,9 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
     w.close();
   }
   IndexInfo info; info.k = k; info.masks = o.masks; info.rand_seed = o.seed; info.max_desert = o.fill_deserts ? o.max_desert : 0; info.seed_dist_in_desert = o.fill_deserts ? o.seed_dist : 0; info.chunks = o.chunks; info.partitions = o.partitions;
-  info.input_genomes = (int)n_genomes; info.input_bases = total_bases; info.genomes = (int)n_genomes; info.genome_batch_size = (int)n_genomes; info.contig_interval = o.contig_interval;
+  info.input_genomes = (int)n_input; info.input_bases = total_bases; info.genomes = (int)n_units; info.genome_batch_size = (int)bsz; info.genome_batches = (int)n_batches; info.contig_interval = o.contig_interval;
   write_info(out + "/info.toml", info);
-  fprintf(stderr, "[lmi-build] %zu genomes, %lld bases, %zu seed values (%lld from desert filling), %d masks -> %s\n", n_genomes, (long long)total_bases, all.size(), 2 * n_extra, o.masks, out.c_str());
+  fprintf(stderr, "[lmi-build] %zu genomes (%zu units in %zu batches), %lld bases, %zu seed values (%lld from desert filling), %d masks -> %s\n", n_input, n_units, n_batches, (long long)total_bases, all.size(), 2 * n_extra, o.masks, out.c_str());
 }
 
 // ------------------------------------------------------------------ synthetic queries from an index's genomes
@@ -311,7 +348,8 @@ int main(int argc, char** argv) {
     std::string cmd = argv[1];
     BuildOpts o; o.masks = atoi(arg(argc, argv, "--masks", "20000")); o.chunks = atoi(arg(argc, argv, "--chunks", "16")); o.partitions = atoi(arg(argc, argv, "--partitions", "4096"));
     o.seed = atoll(arg(argc, argv, "--rand-seed", "1")); o.threads = atoi(arg(argc, argv, "--threads", "0")); o.contig_interval = atoi(arg(argc, argv, "--contig-interval", "1000"));
-    for (int i = 2; i < argc; i++) if (!strcmp(argv[i], "--fill-deserts")) o.fill_deserts = true;
+    for (int i = 2; i < argc; i++) { if (!strcmp(argv[i], "--fill-deserts")) o.fill_deserts = true; if (!strcmp(argv[i], "--no-fill-deserts")) o.fill_deserts = false; }
+    o.max_genome = atoll(arg(argc, argv, "--max-genome", "15000000")); o.batch_size = atoi(arg(argc, argv, "--batch-size", "0"));
     o.max_desert = atoi(arg(argc, argv, "--seed-max-desert", "100")); o.seed_dist = atoi(arg(argc, argv, "--seed-in-desert-dist", "50"));
     if (o.fill_deserts && (o.seed_dist * 2 > o.max_desert || o.seed_dist < 2)) die("value of --seed-in-desert-dist should be smaller than 0.5 * --seed-max-desert");   // index.go:213
     if (cmd == "index") {

@@ -302,6 +302,15 @@ inline std::vector<std::pair<std::string, uint64_t>> read_genome_map(const std::
   return m;
 }
 
+// genomes.chunks.bin (lib-index-build.go:1795-1812, readGenomeChunksLists :2193-2246): per split genome a big-endian u64 count followed by
+// that many batch+genome indexes. A missing or empty file means no genome was split.
+inline std::vector<std::vector<uint64_t>> read_genome_chunks(const std::string& file) {
+  std::vector<std::vector<uint64_t>> out; FILE* f = fopen(file.c_str(), "rb"); if (!f) return out; fclose(f);
+  std::vector<uint8_t> d = read_file(file); size_t p = 0;
+  while (p + 8 <= d.size()) { uint64_t n = get_be(&d[p], 8); p += 8; if (p + 8 * n > d.size()) die("broken genome chunk file"); std::vector<uint64_t> l; for (uint64_t i = 0; i < n; i++, p += 8) l.push_back(get_be(&d[p], 8)); out.push_back(std::move(l)); }
+  return out;
+}
+
 inline std::string chunk_file(const std::string& dir, int i) { char b[64]; snprintf(b, sizeof b, "/seeds/chunk_%03d.bin", i); return dir + b; }
 inline std::string batch_dir(const std::string& dir, int b) { char s[64]; snprintf(s, sizeof s, "/genomes/batch_%04d", b); return dir + s; }
 

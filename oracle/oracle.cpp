@@ -18,7 +18,7 @@ typedef struct lmo_chain { uint64_t genome; uint32_t query; float score; int32_t
 
 namespace {
 
-struct SD { bool rc; double sim; int nseeds; int seq_idx, nseqs, seqlen; std::string seqid; std::vector<Chain2> chains; };
+struct SD { bool rc; double sim; int nseeds; int seq_idx, nseqs, seqlen; std::string seqid; std::vector<Chain2> chains; uint32_t chunk_idx = 0, n_chunks = 1; };
 struct GenomeRes { uint64_t bgi; std::vector<Sub> subs; std::vector<std::vector<int32_t>> chains; float score = 0; std::vector<SD> sds; double af = 0; };
 
 struct StageSink { std::vector<lmo_anchor>* anchors = nullptr; std::vector<lmo_chain>* chains = nullptr; };
@@ -74,7 +74,7 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
   // ---- (4)+(5) pseudo-alignment and alignment :1834-2763
   QueryTable T = build_query_table((const uint8_t*)s.data(), qlen, 31);  // SeqComparatorOptions.K = 31 search.go:361
   Chain2Opts c2{P.align_max_gap, (int)((double)P.align_min_len * P.min_pident / 100), P.align_min_len, P.align_band / 2, P.align_band, 15};
-  const int extLen = P.ext_len, contigInterval = ix.contig_interval;
+  const int extLen = P.ext_len, contigInterval = ix.contig_interval; const bool has_chunks = !ix.genome_chunks.empty();
   for (GenomeRes* rp : rs) {
     GenomeRes& r = *rp; int refBatch = (int)(r.bgi >> 17), refID = (int)(r.bgi & 131071); const GenomeBatchFile& gb = ix.batches[refBatch]; GenomeMeta gm = genome_meta(gb, refID);
     std::stable_sort(r.chains.begin(), r.chains.end(), [&](const std::vector<int32_t>& a, const std::vector<int32_t>& b) { return r.subs[a[0]].t < r.subs[b[0]].t; });  // :1967-1974
@@ -117,7 +117,9 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
               if (o == 'D') o = 'I'; else if (o == 'I') o = 'D'; c.cigar += std::to_string(n); c.cigar.push_back(o); } }
           double sim = (double)c.bitscore * c.pident; if (sim > maxSim) maxSim = sim; hasResult = true;
         }
-        if (hasResult) { SD sd; sd.rc = rc; sd.nseeds = nSeeds; sd.sim = maxSim; sd.seq_idx = iSeqUse; sd.nseqs = (int)gm.seq_ids.size(); sd.seqlen = gm.seq_sizes[iSeqUse]; sd.seqid = gm.seq_ids[iSeqUse]; sd.chains = chains2; r.sds.push_back(std::move(sd)); }
+        if (hasResult) { SD sd; sd.rc = rc; sd.nseeds = nSeeds; sd.sim = maxSim; sd.seq_idx = iSeqUse; sd.nseqs = (int)gm.seq_ids.size(); sd.seqlen = gm.seq_sizes[iSeqUse]; sd.seqid = gm.seq_ids[iSeqUse]; sd.chains = chains2;
+          { auto ci = ix.genome_chunks.find(r.bgi); if (ci != ix.genome_chunks.end()) { sd.n_chunks = ci->second.n; sd.chunk_idx = ci->second.i; } }   // :2375-2385 / :2643-2654
+          r.sds.push_back(std::move(sd)); }
       };
       auto convert = [&](Chain2& c, int qb_, int qe_, int tb_, int te_, int tPosOffsetBegin, int iS) {  // :2167-2200 / :2423-2454
         c.qb = qb_; c.qe = qe_; c.t_pos_offset_begin = tPosOffsetBegin;
@@ -150,9 +152,22 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
       if (iSeq >= 0 && !cur.empty()) flush(cur, false, iSeq);
     }
     if (r.sds.empty()) continue;
+    if (has_chunks) continue;   // :2701 "if hasGenomeChunks, do not filter results now"
     std::vector<std::array<int, 2>> regions; for (SD& sd : r.sds) for (Chain2& c : sd.chains) if (!c.dead) regions.push_back({c.qb, c.qe});
     r.af = (double)coverage_len(regions) / (double)qlen * 100; if (r.af > 100) r.af = 100; if (r.af < P.min_qcov_genome) { r.sds.clear(); continue; }
     std::stable_sort(r.sds.begin(), r.sds.end(), [](const SD& a, const SD& b) { return a.sim > b.sim; });  // :2745-2747
+  }
+  // ---- (5b) merge the results of the chunks of a split genome :2797-2913. The reference merges into whichever chunk's result arrived first
+  // (goroutine order); made deterministic here: into the chunk that comes first in `rs` (genome-index order), the others appended in that order.
+  if (has_chunks) {
+    std::map<uint32_t, GenomeRes*> first;
+    for (GenomeRes* rp : rs) { if (rp->sds.empty()) continue; auto ci = ix.genome_chunks.find(rp->bgi); if (ci == ix.genome_chunks.end()) continue;
+      auto f = first.find(ci->second.group); if (f == first.end()) { first[ci->second.group] = rp; continue; }
+      for (SD& sd : rp->sds) f->second->sds.push_back(std::move(sd)); rp->sds.clear(); }
+    for (GenomeRes* rp : rs) { GenomeRes& r = *rp; if (r.sds.empty()) continue;   // recompute the query coverage per genome, filter, sort :2856-2897
+      std::vector<std::array<int, 2>> regions; for (SD& sd : r.sds) for (Chain2& c : sd.chains) if (!c.dead) regions.push_back({c.qb, c.qe});
+      r.af = (double)coverage_len(regions) / (double)qlen * 100; if (r.af > 100) r.af = 100; if (r.af < P.min_qcov_genome) { r.sds.clear(); continue; }
+      std::stable_sort(r.sds.begin(), r.sds.end(), [](const SD& a, const SD& b) { return a.sim > b.sim; }); }
   }
   // ---- (6) finish :2919-2932
   std::vector<GenomeRes*> rs2; for (GenomeRes* r : rs) if (!r->sds.empty()) rs2.push_back(r);
@@ -174,7 +189,7 @@ static Params to_params(const lmo_params* p) { Params P; if (!p) return P; P.min
 
 static void rows_of(uint32_t q, const std::vector<GenomeRes>& res, Rows& R) {  // printResult search.go:437-533
   for (const GenomeRes& r : res) { int cls = 1, j = 1;
-    for (const SD& sd : r.sds) { for (const Chain2& c : sd.chains) { if (c.dead) continue; lmo_hsp h; memset(&h, 0, sizeof h); h.query = q; h.hits = (uint32_t)res.size(); h.genome = r.bgi; h.seq_idx = sd.seq_idx; h.n_seqs = sd.nseqs; h.chunk_idx = 0; h.n_chunks = 1; h.seq_len = sd.seqlen;
+    for (const SD& sd : r.sds) { for (const Chain2& c : sd.chains) { if (c.dead) continue; lmo_hsp h; memset(&h, 0, sizeof h); h.query = q; h.hits = (uint32_t)res.size(); h.genome = r.bgi; h.seq_idx = sd.seq_idx; h.n_seqs = sd.nseqs; h.chunk_idx = sd.chunk_idx; h.n_chunks = sd.n_chunks; h.seq_len = sd.seqlen;
         h.cls = cls; h.hsp = j; h.qb = c.qb; h.qe = c.qe; h.tb = c.tb; h.te = c.te; h.rc = sd.rc; h.alen = c.aligned_len; h.matches = c.matched; h.gaps = c.gaps; h.score = c.score; h.bitscore = c.bitscore; h.evalue = c.evalue;
         h.qcov_hsp = c.af; h.pident = c.pident; h.qcov_gnm = r.af; h.cigar_off = R.pool.size(); h.cigar_len = (uint32_t)c.cigar.size(); R.pool += c.cigar; R.pool += c.qseq; R.pool += c.tseq; R.pool += c.align; /* pool entry: cigar | qseq | sseq | align (alen bytes each) */ R.rows.push_back(h); R.seqids.push_back(sd.seqid); j++; } cls++; } }
 }

@@ -89,6 +89,8 @@ struct Index {
   int k = 31, n_masks = 0, contig_interval = 1000, mask_prefix = 7, anchor_prefix = 6; int64_t total_bases = 0;
   std::vector<uint64_t> masks; std::vector<KvChunkFile> chunks; std::vector<GenomeBatchFile> batches;
   std::map<uint64_t, std::string> id2name;
+  // split genomes (genomes.chunks.bin, lib-index-build.go:1787-1812 / readGenomeChunksLists :2193-2246): batch+genome index -> {#chunks, chunk index, group}
+  struct ChunkInfo { uint32_t n, i, group; }; std::map<uint64_t, ChunkInfo> genome_chunks;
 
   static std::map<std::string, std::string> toml(const std::string& file) {
     std::map<std::string, std::string> kv; FILE* f = fopen(file.c_str(), "r"); if (!f) throw std::runtime_error("oracle: cannot open " + file);
@@ -119,6 +121,8 @@ struct Index {
     batches.resize(nbatches);
     for (int b = 0; b < nbatches; b++) { char s[64]; snprintf(s, sizeof s, "/genomes/batch_%04d/genomes.bin", b); batches[b].data = slurp(dir + s); std::vector<uint8_t> x = slurp(dir + s + ".idx");
       uint32_t n = (uint32_t)rd_be(&x[20], 4); for (uint32_t i = 0; i < n; i++) { batches[b].rec_off.push_back(rd_be(&x[24 + 12 * i], 8)); batches[b].nbases.push_back((uint32_t)rd_be(&x[32 + 12 * i], 4)); } }
+    { FILE* f = fopen((dir + "/genomes.chunks.bin").c_str(), "rb"); if (f) { fclose(f); std::vector<uint8_t> d = slurp(dir + "/genomes.chunks.bin"); size_t p = 0; uint32_t grp = 0;
+        while (p + 8 <= d.size()) { uint64_t n = rd_be(&d[p], 8); p += 8; if (p + 8 * n > d.size()) throw std::runtime_error("oracle: broken genome chunk file"); for (uint64_t i = 0; i < n; i++, p += 8) genome_chunks[rd_be(&d[p], 8)] = {(uint32_t)n, (uint32_t)i, grp}; grp++; } } }
     { std::vector<uint8_t> d = slurp(dir + "/genomes.map.bin"); size_t p = 0; while (p + 2 <= d.size()) { size_t l = rd_be(&d[p], 2); p += 2; std::string id((const char*)&d[p], l); p += l; id2name[rd_be(&d[p], 8)] = id; p += 8; } }
   }
 };

@@ -8,11 +8,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, _tools, make_index
+from conftest import GOLD, ROOT, _tools, make_index, read_chunk_groups, read_tsv, tsv_key
 from oracle_binding import Oracle, read_fasta, format_tsv
 
-GOLD = os.path.join(ROOT, "tests", "golden")
-DEMO_REFS = "/root/reference/demo/refs"
 
 
 # ------------------------------------------------------------------ reference KAT: kv/kv-data_test.go:30-283
@@ -128,73 +126,70 @@ def test_genome_subseq_roundtrip(tmp_path):
 
 
 # ------------------------------------------------------------------ golden demo outputs of the reference (v0.10.0)
-@pytest.mark.skipif(not os.path.isdir(DEMO_REFS), reason="reference demo genomes not available on this box")
-def test_oracle_reproduces_reference_demo_rows(tmp_path):
-    """End-to-end pin of stages 1-5 incl. the two absent Go modules (lexichash, wfa): rows of demo/q.gene.fasta.lexicmap.tsv.
-    Our index of demo/refs uses our own masks and no desert filling, so a few low-identity rows may be missing, but every row we
-    do produce must equal the golden row in alenHSP/pident/gaps/coordinates/strand/slen/evalue/bitscore, and CIGARs must match."""
-    lst = tmp_path / "refs.list"
-    lst.write_text("\n".join(os.path.join(DEMO_REFS, f) for f in sorted(os.listdir(DEMO_REFS))) + "\n")
-    idx = str(tmp_path / "demo.lmi")
-    subprocess.check_call([_tools(), "index", "--in-list", str(lst), "--out", idx], stderr=subprocess.DEVNULL)
-    o = Oracle(idx)
-    ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.gene.fasta"))
-    rows, sid, cig = o.search(seqs, o.default_params(output_seq=1), threads=8)
-    mine = format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name, cig, o.last_align_text)
+# The demo index (tests/data/demo.lmi) is written by this repo's writer with the reference's default options (20,000 masks, seed-desert
+# filling) from the reference's 15 demo genomes. Masks differ from the reference's (Go math/rand stream), so a few low-identity rows of the
+# reference may be missing and `hits` may differ; every row found by both must agree in columns 9-20 (alenHSP ... bitscore) and qcovGnm.
+def _demo_rows(o, fasta, **kw):
+    ids, seqs = read_fasta(os.path.join(GOLD, fasta))
+    rows, sid, cig = o.search(seqs, o.default_params(**kw), threads=8)
+    lines = format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name, cig if kw.get("output_seq") else None, o.last_align_text if kw.get("output_seq") else None)
+    return {tsv_key(l.split("\t")): l.split("\t") for l in lines}
 
-    def key(f):
-        return (f[0], f[3], f[4], f[12], f[13], f[14], f[15], f[16])
-    gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLD, "demo_q.gene.fasta.lexicmap.tsv"))][1:]
-    gm = {key(f): f for f in gold}
-    mm = {key(l.split("\t")): l.split("\t") for l in mine}
+
+def test_oracle_reproduces_reference_demo_rows(demo_index):
+    """End-to-end pin of stages 1-5 incl. the two absent Go modules (lexichash, wfa): rows of demo/q.gene.fasta.lexicmap.tsv and the
+    CIGAR / qseq / sseq / align columns of demo/q.gene.fasta.lexicmap_top-2-genomes_all.tsv."""
+    o = Oracle(demo_index)
+    mm = _demo_rows(o, "demo_q.gene.fasta", output_seq=1)
+    gold = read_tsv(os.path.join(GOLD, "demo_q.gene.fasta.lexicmap.tsv"))
+    gm = {tsv_key(f): f for f in gold}
     common = set(gm) & set(mm)
     assert len(gold) == 84 and len(common) >= 80, (len(gold), len(common))
     assert not (set(mm) - set(gm)), "rows not in the reference output"
     for kx in common:
         assert gm[kx][8:20] == mm[kx][8:20], (gm[kx], mm[kx])
-    gold_a = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLD, "demo_q.gene.top2_all.tsv"))][1:]
     n = 0
-    for f in gold_a:
-        if key(f) in mm:
-            assert mm[key(f)][20] == f[20], "CIGAR differs"
-            assert mm[key(f)][21:24] == f[21:24], "qseq / sseq / align text differs"   # cigar.AlignmentText of the absent wfa module, pinned by the golden -a rows
+    for f in read_tsv(os.path.join(GOLD, "demo_q.gene.top2_all.tsv")):
+        if tsv_key(f) in mm:
+            assert mm[tsv_key(f)][20] == f[20], "CIGAR differs"
+            assert mm[tsv_key(f)][21:24] == f[21:24], "qseq / sseq / align text differs"   # cigar.AlignmentText of the absent wfa module, pinned by the golden -a rows
             n += 1
     assert n == 14
 
 
-@pytest.mark.skipif(not os.path.isdir(DEMO_REFS), reason="reference demo genomes not available on this box")
-def test_oracle_reproduces_reference_prophage_rows_with_desert_filling(tmp_path):
-    """Long-query pin: demo/q.prophage.fasta (33.6 kb) against demo/refs. The reference's index fills seed deserts (lib-index-build.go:1086-1413);
-    with the writer's restatement of that step (`--fill-deserts`) the oracle reproduces the reference's long HSPs exactly — alignments of
-    9,371 / 6,942 / 5,941 / 2,983 / 820 columns incl. gap columns, coordinates, pident, bit score, e-value and the genome coverage — which pins
-    chaining over many seeds, windows >= 10 kb (minimum prefix 13) and WFA-adaptive on long alignments. (Without desert filling the 9.4-kb and
-    6.9-kb HSPs come out fragmented.) Rows that depend on seeds of two low-identity genomes differ (other masks than the reference's)."""
-    lst = tmp_path / "refs.list"
-    lst.write_text("\n".join(os.path.join(DEMO_REFS, f) for f in sorted(os.listdir(DEMO_REFS))) + "\n")
-    idx = str(tmp_path / "demo_desert.lmi")
-    subprocess.check_call([_tools(), "index", "--in-list", str(lst), "--out", idx, "--fill-deserts"], stderr=subprocess.DEVNULL)
-    o = Oracle(idx)
-
-    def key(f):
-        return (f[0], f[3], f[4], f[12], f[13], f[14], f[15], f[16])
-    ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.prophage.fasta"))
-    rows, sid, cig = o.search(seqs, o.default_params(), threads=8)
-    mm = {key(l.split("\t")): l.split("\t") for l in format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name)}
-    gold = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLD, "demo_q.prophage.fasta.lexicmap.tsv"))][1:]
-    gm = {key(f): f for f in gold}
+def test_oracle_reproduces_reference_prophage_rows(demo_index):
+    """Long-query pin: demo/q.prophage.fasta (33.6 kb). With the writer's restatement of seed-desert filling (lib-index-build.go:1086-1413,
+    the reference's default) the oracle reproduces the reference's long HSPs exactly — alignments of 9,371 / 6,942 / 5,941 / 2,983 / 820
+    columns incl. gap columns, coordinates, pident, bit score, e-value and the genome coverage — which pins chaining over many seeds,
+    windows >= 10 kb (minimum prefix 13) and WFA-adaptive on long alignments. Rows that depend on seeds of two low-identity genomes differ
+    (other masks than the reference's)."""
+    o = Oracle(demo_index)
+    mm = _demo_rows(o, "demo_q.prophage.fasta")
+    gold = read_tsv(os.path.join(GOLD, "demo_q.prophage.fasta.lexicmap.tsv"))
+    gm = {tsv_key(f): f for f in gold}
     common = set(gm) & set(mm)
     assert len(gold) == 9 and len(common) >= 5
     for kx in common:
         assert gm[kx][8:20] == mm[kx][8:20] and gm[kx][5] == mm[kx][5], (gm[kx], mm[kx])     # columns 9-20 and qcovGnm
     assert {int(gm[kx][9]) for kx in common} >= {9371, 6942, 5941, 2983, 820}
-    # the gene queries on the same index: no row outside the reference's output, at least as many reproduced as without desert filling
-    ids, seqs = read_fasta(os.path.join(GOLD, "demo_q.gene.fasta"))
-    rows, sid, cig = o.search(seqs, o.default_params(), threads=8)
-    mm = {key(l.split("\t")): l.split("\t") for l in format_tsv(rows, sid, ids, [len(s) for s in seqs], o.genome_name)}
-    gm = {key(f): f for f in (l.rstrip("\n").split("\t") for l in list(open(os.path.join(GOLD, "demo_q.gene.fasta.lexicmap.tsv")))[1:])}
-    assert not (set(mm) - set(gm)) and len(set(mm) & set(gm)) >= 80
-    for kx in set(mm) & set(gm):
-        assert gm[kx][8:20] == mm[kx][8:20]
+
+
+LONG_READ_FLAGS = dict(min_qcov_hsp=70.0, top_n_genomes=5, top_n_chains=1)   # demo/README.md:365-368
+
+
+def test_oracle_reproduces_reference_long_read_rows(demo_index):
+    """BASELINE.json configs[3] pin: the ten rows the reference prints for demo/q.long-reads.fasta.gz (demo/README.md:410-419; simulated
+    ONT reads of 2-20 kb, alignments of 2,101-20,481 columns with up to 307 gap columns) are reproduced in every column but `hits`
+    (other masks find further low-identity genomes). Pins WFA-adaptive and the backtrace tie-breaking on noisy long alignments."""
+    o = Oracle(demo_index)
+    mm = _demo_rows(o, "demo_long_reads_sample.fasta.gz", **LONG_READ_FLAGS)
+    gold = read_tsv(os.path.join(GOLD, "demo_long_reads_readme_rows.tsv"))
+    assert len(gold) == 10
+    for f in gold:
+        assert tsv_key(f) in mm, f
+        g = mm[tsv_key(f)]
+        assert g[:2] == f[:2] and g[3:20] == f[3:20], (f, g)
+    assert len(mm) > 150
 
 
 # ------------------------------------------------------------------ regression pin on a deterministic synthetic fixture
@@ -224,6 +219,51 @@ def test_oracle_small_fixture_regression(oracle_small, small_queries):
     if os.environ.get("LMG_REGEN_GOLDEN"):
         open(gold, "w").write("\n".join(mine) + "\n")
     assert mine == open(gold).read().splitlines()
+
+
+def check_split_index_rows(index_dir, rows, sid, ids, seqs, genome_name):
+    """properties of a search against an index with split genomes and several genome batches (lib-index-search.go:2797-2913): the chunks of a
+    genome are merged into one result (one name per query, `hits` = distinct names), qcovGnm is the union coverage over all of the genome's
+    HSPs, cls/hsp count through the merged genome, chunk fields agree with genomes.chunks.bin."""
+    groups = read_chunk_groups(index_dir)
+    assert len(groups) >= 3 and all(len(g) >= 2 for g in groups)
+    assert any((b >> 17) > 0 for g in groups for b in g), "some chunks live in genome batches > 0"
+    merged = 0
+    for q in np.unique(rows["query"]):
+        r = rows[rows["query"] == q]
+        names = [genome_name(g) for g in r["genome"]]
+        order = list(dict.fromkeys(names))
+        assert [k for k, _ in __import__("itertools").groupby(names)] == order, "a genome's rows are contiguous: chunks were merged"
+        assert np.all(r["hits"] == len(order))
+        for nm in order:
+            rr = r[[n_ == nm for n_ in names]]
+            cov = np.zeros(len(seqs[q]), bool)
+            for a, b in zip(rr["qb"], rr["qe"]):
+                cov[a:b + 1] = True
+            assert abs(min(100.0, cov.sum() / len(seqs[q]) * 100) - rr["qcov_gnm"][0]) < 1e-9 and np.all(rr["qcov_gnm"] == rr["qcov_gnm"][0])
+            assert list(rr["hsp"]) == list(range(1, len(rr) + 1)) and rr["cls"][0] == 1 and np.all(np.diff(rr["cls"]) >= 0)
+            if len(set(zip(rr["chunk_idx"], rr["n_chunks"]))) > 1:
+                merged += 1
+            assert np.all(rr["chunk_idx"] < rr["n_chunks"])
+    assert merged > 0, "at least one query hits two chunks of the same genome"
+
+
+def test_split_genomes_and_batches(split_index, small_index, split_queries):
+    ids, seqs = split_queries
+    o = Oracle(split_index)
+    info = open(os.path.join(split_index, "info.toml")).read()
+    assert int(re.search(r"genome-batches\s*=\s*(\d+)", info).group(1)) >= 4 and int(re.search(r"\ngenomes\s*=\s*(\d+)", info).group(1)) > 16
+    rows, sid, cig = o.search(seqs, o.default_params(output_seq=1))
+    check_split_index_rows(split_index, rows, sid, ids, seqs, o.genome_name)
+    # same genomes unsplit: every query that is found there is found here too
+    o2 = Oracle(small_index)
+    rows2, _, _ = o2.search(seqs, o2.default_params())
+    assert set(np.unique(rows2["query"])) <= set(np.unique(rows["query"]))
+    # -Q is applied to the merged coverage
+    rq, _, _ = o.search(seqs, o.default_params(min_qcov_genome=90.0))
+    assert len(rq) < len(rows) and np.all(rq["qcov_gnm"] >= 90.0)
+    chim = [i for i, x in enumerate(ids) if x.startswith("chimera")]
+    assert set(chim) <= set(np.unique(rq["query"]).tolist()), "each half covers 50 % of a chimera: it passes -Q 90 only through the merged coverage"
 
 
 def test_mask_fast_equals_bruteforce_definition(oracle_small, small_queries):
@@ -286,7 +326,7 @@ def test_all_columns_pool_layout_and_formatters(oracle_small, small_queries):
 
 
 def test_desert_filling_closes_seed_gaps(tmp_path):
-    """index writer, `--fill-deserts` (lib-index-build.go:1086-1413): first-round seeds leave gaps of >= 100 bases between consecutive seed
+    """index writer, seed-desert filling (on by default; lib-index-build.go:1086-1413): first-round seeds leave gaps of >= 100 bases between consecutive seed
     positions; after filling, gaps above max_desert + seed_dist survive only next to contig-interval regions, the first-round seeds are
     all still there, and every extra seed also has its base-reversed copy (reverse flag 1)."""
     import glob
@@ -306,8 +346,8 @@ def test_desert_filling_closes_seed_gaps(tmp_path):
     a = str(tmp_path / "plain.lmi")
     b = str(tmp_path / "filled.lmi")
     # 2,048 masks over 200-kb genomes: ~100 bases between first-round seeds on average, so deserts are common (20,000 masks would leave none here)
-    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", a, "--chunks", "4", "--masks", "2048"], stderr=subprocess.DEVNULL)
-    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", b, "--chunks", "4", "--masks", "2048", "--fill-deserts"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", a, "--chunks", "4", "--masks", "2048", "--no-fill-deserts"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([tools, "index", "--synth", "2,2,200000,5,3", "--out", b, "--chunks", "4", "--masks", "2048"], stderr=subprocess.DEVNULL)
     (fa, ra), (fb, rb) = seed_positions(a), seed_positions(b)
     assert set(fa) == set(fb)
     for g in fa:
