@@ -105,6 +105,24 @@ void lmg_results_free(lmg_results* r);
  * lmg_anchor_batch (issued, with anchor, search steps, entries scanned, hit records, anchors) [6]=query bases [7]=queries
  * [8]=probe slots [15]=kernels launched by this library so far */
 int  lmg_last_timing(const lmg_index* idx, double* ms16, uint64_t* counters16);
+/* byte-model sums of the last lmg_anchor_batch: [0] sum over probes of ceil(log2(n_a+1)), n_a = entries of the probe's anchor run
+ * [1] sum of 32-byte sectors of matched entries [2] sum of matched values (anchors before the query-location product) [3] reserved */
+int  lmg_probe_model(const lmg_index* idx, uint64_t* sums4);
+
+/* e-values use the index's total bases (lib-index-search.go:1918). A search over genome shards (one index per shard, results merged as
+ * `lexicmap utils merge-search-results` does, merge-search-results.go:143-153) sets the total of ALL shards here so that every shard reports
+ * the e-values of the whole collection. */
+int  lmg_index_set_total_bases(lmg_index* idx, int64_t total_bases);
+/* wall-clock milliseconds of lmg_index_open: [0] genomes [1] seed chunks: upload + counting pass [2] seed chunks: fill pass + anchors [3] total */
+int  lmg_index_load_times(const lmg_index* idx, double* ms4);
+
+/* ---- seed-lookup microbenchmark (BASELINE.json configs[4]): a synthetic seeds-only image of `masks` buckets x `per_mask` sorted k-mers held for the
+ * mask range [mask_lo, mask_hi) (range partitioning across GPUs), and a run of the index-lookup kernel over n_queries synthetic 31-mers (one prefix and one
+ * suffix probe each; only probes of the held mask range are issued). out16: [0] probes issued [1] probes with an anchor (kernel work items) [2] mean kernel ms
+ * [3] hit records [4] sum ceil(log2(n_a+1)) [5] sum of 32-B sectors of matched entries [6] sum of matched values [7] search steps taken [8] entries scanned
+ * [9] generator ms [10] best kernel ms. Search entry points refuse such an index. */
+int  lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed, int32_t mask_lo, int32_t mask_hi, int32_t with_values, lmg_index** out);
+int  lmg_probe_bench(lmg_index* idx, uint64_t n_queries, uint64_t seed, int32_t min_prefix, int32_t iters, double* out16);
 
 /* ---- stage-wise entry points (parity tests; mirror a1-a7 of SURVEY.md §8a) ---- */
 /* lexichash mask + DUST filter + suffix re-masking (lib-index-search.go:1212-1350): kmers[n*m], nlocs[n*m], minloc[n*m];

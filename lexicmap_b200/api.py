@@ -74,6 +74,11 @@ def load_library():
     L.lmg_chain_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_wfa_batch.argtypes = [C.c_int, vp, vp, C.c_int32, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_free.argtypes = [vp]
+    L.lmg_index_set_total_bases.argtypes = [vp, C.c_int64]
+    L.lmg_index_load_times.argtypes = [vp, vp]
+    L.lmg_probe_model.argtypes = [vp, vp]
+    L.lmg_index_synth.argtypes = [C.c_int, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.lmg_probe_bench.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
     _lib = L
     return L
 
@@ -98,6 +103,40 @@ class Index:
         self.h = h
         self.info = Info()
         self.lib.lmg_index_info(self.h, C.byref(self.info))
+
+    @classmethod
+    def synthetic(cls, masks=20000, per_mask=100000, seed=1, mask_lo=0, mask_hi=None, device=0, with_values=False):
+        """seeds-only synthetic image for the seed-lookup microbenchmark (BASELINE.json configs[4]); only probe_bench() runs on it"""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        h = C.c_void_p()
+        if self.lib.lmg_index_synth(device, masks, per_mask, seed, mask_lo, masks if mask_hi is None else mask_hi, int(with_values), C.byref(h)) != 0:
+            raise RuntimeError(self.lib.lmg_last_error().decode())
+        self.h = h
+        self.info = Info()
+        self.lib.lmg_index_info(self.h, C.byref(self.info))
+        return self
+
+    def probe_bench(self, n_queries, seed=20260926, min_prefix=15, iters=5):
+        out = np.zeros(16, np.float64)
+        if self.lib.lmg_probe_bench(self.h, n_queries, seed, min_prefix, iters, out.ctypes.data) != 0:
+            self._err()
+        keys = ["issued", "survivors", "kernel_ms", "hits", "sum_log2", "sum_hit_sectors", "sum_values", "steps", "entries", "gen_ms", "kernel_ms_best"]
+        return dict(zip(keys, out.tolist()))
+
+    def set_total_bases(self, n):
+        if self.lib.lmg_index_set_total_bases(self.h, int(n)) != 0:
+            self._err()
+
+    def load_times(self):
+        ms = np.zeros(4, np.float64)
+        self.lib.lmg_index_load_times(self.h, ms.ctypes.data)
+        return dict(zip(["genomes_ms", "seed_count_ms", "seed_fill_ms", "total_ms"], ms.tolist()))
+
+    def probe_model(self):
+        s = np.zeros(4, np.uint64)
+        self.lib.lmg_probe_model(self.h, s.ctypes.data)
+        return [int(x) for x in s]
 
     def close(self):
         if getattr(self, "h", None):
@@ -126,15 +165,16 @@ class Index:
         return (s.value or b"").decode()
 
     # ---- Index.Search, batched (lib-index-search.go:1191)
-    def search(self, seqs, params=None, packed=None):
-        """returns (rows: HSP_DTYPE array, seqids, cigars). `packed` = (uint8 buf, uint64 off) to skip re-packing."""
+    def search(self, seqs, params=None, packed=None, rows_only=False):
+        """returns (rows: HSP_DTYPE array, seqids, cigars). `packed` = (uint8 buf, uint64 off) to skip re-packing.
+        rows_only: (rows, None, None) without the per-row Python work (benchmarks)."""
         p = params or self.default_params()
         buf, off = packed if packed is not None else pack_queries(seqs)
         n = len(off) - 1
         r = C.c_void_p()
         if self.lib.lmg_search_batch(self.h, C.byref(p), buf.ctypes.data, off.ctypes.data, n, C.byref(r)) != 0:
             self._err()
-        return self._collect(r)
+        return self._collect(r, rows_only)
 
     def stage(self, seqs=None, packed=None):
         """copy a query batch to HBM ahead of time; returns an opaque handle for search_staged()"""
@@ -150,7 +190,7 @@ class Index:
         if self.lib.lmg_search_staged(self.h, C.byref(p), q, C.byref(r)) != 0:
             self._err()
         if collect:
-            return self._collect(r)
+            return self._collect(r, rows_only=(collect == "rows"))
         nr = self._nrows(r)
         self.lib.lmg_results_free(r)
         return nr
@@ -174,10 +214,13 @@ class Index:
         self.lib.lmg_results_free(r)
         return nr
 
-    def _collect(self, r):
+    def _collect(self, r, rows_only=False):
         rows_p, pool_p, nr, npool = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
         self.lib.lmg_results_rows(r, C.byref(rows_p), C.byref(nr), C.byref(pool_p), C.byref(npool))
         rows = np.frombuffer(C.string_at(rows_p, nr.value * HSP_DTYPE.itemsize), dtype=HSP_DTYPE).copy() if nr.value else np.zeros(0, HSP_DTYPE)
+        if rows_only:
+            self.lib.lmg_results_free(r)
+            return rows, None, None
         pool = C.string_at(pool_p, npool.value) if npool.value else b""
         seqids = []
         s = C.c_char_p()

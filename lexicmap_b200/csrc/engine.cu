@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 // =====================================================================================================
 // K2: seed probe (kv.Searcher.Search / Search2, kv/kv-searcher.go:190-1088) + anchors (lib-index-search.go:1357-1569)
 // =====================================================================================================
-struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 pad; };  // mask_dir = mask<<1 | dir ; [lo,lo+n) = query table rows (locs)
-struct ProbeParams { const u64 *bucket_off, *keys, *val_off, *vals; const u32 *anchor_start, *anchor_bits; int m, k, NA, mask_prefix, anchor_prefix, p; };
+struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 bucket; };  // mask_dir = capturing mask<<1 | dir ; [lo,lo+n) = query table rows (locs); bucket = mask bucket searched; [e0, e0+ne) = matched index entries
+struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_start, *anchor_bits; int m, k, NA, mask_prefix, anchor_prefix, p; };
 
 // Probe semantics (kv.Searcher.Search / Search2): dir 0 = captured k-mer against its own mask bucket, values must have reverse flag 0;
 // dir 1 = base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
@@ -185,20 +185,51 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
   if (stats) { for (int of = 16; of; of >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, of); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
 }
 
+// K2 phase B, the roofline kernel: one thread per surviving probe. Anchor start (one random 32-byte sector), galloping + binary lower bound
+// over the bucket's 16-byte entries (two per sector), then the range walk over the same records: the entry that ends the search already
+// holds the first-value flag and the value count, so no second or third array is touched (round 1 read keys, val_off and vals[v0]).
+// STATS additionally counts, per probe, the size n_a of its anchor's run of entries (for the SURVEY.md §8d byte model) — untimed passes only.
+template <bool STATS>
 __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0;
-  if (t < ns) { Surv sv = surv[t]; int dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; int bucket = (int)(aslot / (u32)P.NA); u64 kmer = sv.kmer;
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0, lg = 0, hsec = 0, nout = 0;
+  if (t < ns) { Surv sv = surv[t]; const u32 dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; const u32 bucket = aslot / (u32)P.NA; u64 kmer = sv.kmer;
     int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; u32 as = P.anchor_start[aslot];
-    u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; u64 lo = b0 + as, hi = b1;
-    u64 step = 1, l = lo; while (l + step < hi && P.keys[l + step] < left) { l += step; step <<= 1; steps++; }
-    u64 r = min(hi, l + step); if (P.keys[l] >= left) r = l; else l = l + 1;
-    while (l < r) { u64 mid = (l + r) >> 1; if (P.keys[mid] < left) l = mid + 1; else r = mid; steps++; }
+    const u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; const SeedEntry* __restrict__ E = P.entries; u64 lo = b0 + as, hi = b1;
+    u64 step = 1, l = lo; while (l + step < hi && E[l + step].key < left) { l += step; step <<= 1; steps++; }
+    u64 r = min(hi, l + step); if (E[l].key >= left) r = l; else l = l + 1;
+    while (l < r) { u64 mid = (l + r) >> 1; if (E[mid].key < left) l = mid + 1; else r = mid; steps++; }
     u64 e0 = l; u32 na = 0;
-    while (e0 + ne < hi && P.keys[e0 + ne] <= right) { u64 v0 = P.val_off[e0 + ne], v1 = P.val_off[e0 + ne + 1]; if (v1 > v0 && (int)(P.vals[v0] & 1) == dir) na += (u32)(v1 - v0); ne++; }
-    if (na) { u32 cl = sv.lo, cn = sv.n; have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = cl; h.n = cn; h.kmer = kmer; h.nanch = na * cn; h.pad = 0; } }
+    while (e0 + ne < hi) { const ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(E + e0 + ne); if (raw.x > right) break; const u32 nf = (u32)(raw.y >> 32); if ((nf >> 31) == dir) na += nf & 0x7FFFFFFFu; ne++; }
+    if (na) { have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = sv.lo; h.n = sv.n; h.kmer = kmer; h.nanch = na * sv.n; h.bucket = bucket; }
+    if (STATS) { const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1; const u64 an = E[lo].key >> ash; u32 n_a = 0; while (lo + n_a < hi && (E[lo + n_a].key >> ash) == an) n_a++; lg = 32 - __clz(n_a); hsec = (16 * ne + 31) / 32; nout = na; }   // ceil(log2(n_a + 1)) = bit length of n_a
+  }
   int lane = threadIdx.x & 31; u32 bal = __ballot_sync(FULLMASK, have);
   if (bal) { u32 base = 0; if (lane == __ffs(bal) - 1) base = atomicAdd(nhits, __popc(bal)); base = __shfl_sync(FULLMASK, base, __ffs(bal) - 1); if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_hits) hits[w] = h; } }
-  if (stats) { for (int o = 16; o; o >>= 1) { steps += __shfl_xor_sync(FULLMASK, steps, o); ne += __shfl_xor_sync(FULLMASK, ne, o); } if (lane == 0) { atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); } }
+  if (STATS && stats) { for (int o = 16; o; o >>= 1) { steps += __shfl_xor_sync(FULLMASK, steps, o); ne += __shfl_xor_sync(FULLMASK, ne, o); lg += __shfl_xor_sync(FULLMASK, lg, o); hsec += __shfl_xor_sync(FULLMASK, hsec, o); nout += __shfl_xor_sync(FULLMASK, nout, o); }
+    if (lane == 0) { atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); atomicAdd((unsigned long long*)&stats[4], (unsigned long long)lg); atomicAdd((unsigned long long*)&stats[5], (unsigned long long)hsec); atomicAdd((unsigned long long*)&stats[6], (unsigned long long)nout); } }
+}
+
+// ---- seed-lookup microbenchmark (BASELINE.json configs[4]; SURVEY.md §8d "C5"): query 31-mers -> one prefix probe and one suffix probe each,
+// exactly the records k_capture2 emits for real queries. Half of the queries are stored keys of a random bucket with their last 0-16 bases
+// randomised (LCP with the stored key in [15, 31]); half are uniform random k-mers (bucket = the mask that would capture them).
+// Only probes whose bucket lies in [mask_lo, mask_hi) are kept: with the index range-partitioned by mask every GPU keeps its own share.
+__global__ void __launch_bounds__(256) k_c5_gen(ProbeParams P, const u64* __restrict__ masks, const u32* __restrict__ mask_pstart, int mask_pbits, u64 per, u64 iseed, u64 qseed, u64 nq, int mask_lo, int mask_hi,
+                                                 Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap, u64* __restrict__ stats) {
+  const u64 q = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool s0 = false, s1 = false; Surv a, b; u32 issued = 0; const int k = P.k; const int lane = threadIdx.x & 31;
+  if (q < nq) { u64 r = mix64(qseed ^ (q * 0x9E3779B97F4A7C15ull)); u64 key; u32 bucket; const int msh = 2 * k - mask_pbits;
+    auto argmin_mask = [&](u64 x) { u32 mp = (u32)(x >> msh); u32 lo = mask_pstart[mp], hi = mask_pstart[mp + 1]; if (lo == hi) { lo = 0; hi = (u32)P.m; } xor_argmin_range(masks, lo, hi, x); return lo; };
+    if (r & 1) { bucket = (u32)((r >> 1) % (u64)P.m); const u64 j = mix64(r) % per; key = synth_key(masks[bucket], P.mask_prefix, k, per, j, iseed, bucket); const u64 r2 = mix64(r ^ 0x5bd1e995ull); const int t = (int)(r2 % 17); if (t) key ^= (r2 >> 8) & ((1ull << (2 * t)) - 1); }
+    else { key = r >> 2; bucket = argmin_mask(key); }
+    const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1;
+    if ((int)bucket >= mask_lo && (int)bucket < mask_hi) { issued++; const u64 left = key & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)bucket * P.NA + an;
+      if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = key; a.qi = (u32)q; a.aslot_dir = (u32)aslot; a.lo = 0; a.n = 1; } }
+    const u64 rv = kmer_reverse62(key, k); const u32 b2 = argmin_mask(rv);
+    if ((int)b2 >= mask_lo && (int)b2 < mask_hi) { issued++; const u64 left = rv & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)b2 * P.NA + an;
+      if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)q; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = 0; b.n = 1; } } }
+  const u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1), tot = __popc(b0) + __popc(b1);
+  if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
+    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap) surv[w] = b; } }
+  for (int o = 16; o; o >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, o); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued);
 }
 
 __global__ void k_hit_counts(const ProbeHit* __restrict__ h, u32 n, u64* __restrict__ c) { u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t <= n) c[t] = (t < n) ? h[t].nanch : 0; }
@@ -210,11 +241,11 @@ __device__ __forceinline__ u64 pack_hi(u32 q, u32 g) { return ((u64)q << 36) | (
 // one thread per hit: (matched key) x (query locations) x (values) -> anchors (lib-index-search.go:1398-1557)
 __global__ void k_probe_emit(ProbeParams P, const ProbeHit* __restrict__ hits, const u64* __restrict__ hoff, u32 nh, const u32* __restrict__ qvals, const u64* __restrict__ koff,
                              const u32* __restrict__ batch_base, u64* __restrict__ a_hi, u64* __restrict__ a_lo) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= nh) return; ProbeHit h = hits[t]; u64 w = hoff[t]; const int K = P.k, want = h.mask_dir & 1; const u32* locs = qvals + koff[h.q] + h.lo;
-  for (u32 e = 0; e < h.ne; e++) { u64 key = P.keys[h.e0 + e]; u64 v0 = P.val_off[h.e0 + e], v1 = P.val_off[h.e0 + e + 1]; if (v1 == v0 || (int)(P.vals[v0] & 1) != want) continue;
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= nh) return; ProbeHit h = hits[t]; u64 w = hoff[t]; const int K = P.k; const u32 want = h.mask_dir & 1; const u32* locs = qvals + koff[h.q] + h.lo; const u64* V = P.vals + P.bucket_voff[h.bucket];
+  for (u32 e = 0; e < h.ne; e++) { const SeedEntry se = P.entries[h.e0 + e]; const u32 nv = se.nflag & 0x7FFFFFFFu; if (nv == 0 || (se.nflag >> 31) != want) continue; const u64 key = se.key;
     int len = (__clzll(h.kmer ^ key) >> 1) + K - 32; if (h.kmer == key) len = K;   // Len = LZ(q^kmer)/2 + k - 32 (kv-searcher.go:480)
     for (u32 li = 0; li < h.n; li++) { u32 loc = locs[li] & 0x7fffffffu; u32 rcQ = loc & 1; i32 posQ = (i32)(loc >> 1);
-      for (u64 vi = v0; vi < v1; vi++) { u64 rp = P.vals[vi]; u64 bgi = rp >> 30; u32 g = batch_base[bgi >> 17] + (u32)(bgi & 0x1ffff); i32 posT = (i32)((rp << 34) >> 36); u32 rv = rp & 1, rcT = (rp >> 1) & 1; i32 bq, bt;
+      for (u32 vi = 0; vi < nv; vi++) { u64 rp = V[se.vrel + vi]; u64 bgi = rp >> 30; u32 g = batch_base[bgi >> 17] + (u32)(bgi & 0x1ffff); i32 posT = (i32)((rp << 34) >> 36); u32 rv = rp & 1, rcT = (rp >> 1) & 1; i32 bq, bt;
         if (!rv) { bq = rcQ ? posQ + K - len : posQ; bt = rcT ? posT + K - len : posT; } else { bq = rcQ ? posQ : posQ + K - len; bt = rcT ? posT : posT + K - len; }
         a_hi[w] = pack_hi(h.q, g); a_lo[w] = pack_lo(bq, (u32)len, bt, rcQ, rcT); w++; } } }
 }
@@ -247,7 +278,7 @@ struct HostPool {
 // sub-batches whose host phases (window geometry, contig mapping, scoring) overlap the other sub-batch's kernels.
 struct lmg_index {
   Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
-  double ms[16] = {0}; u64 counters[16] = {0}; std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
+  double ms[16] = {0}; u64 counters[16] = {0}; u64 pstat[4] = {0, 0, 0, 0};   /* last statistics pass of the seed lookup: sum ceil(log2(n_a+1)), sum of 32-byte sectors of matched entries, sum of values of matched entries */ std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
   // workers per lane: half of this process's cores over the active lanes. LMG_HOST_CORES (or OMP_NUM_THREADS, which launchers such as torchrun
   // set per rank) tells how many cores the process may use when several ranks share a node.
   int host_threads() const { static const int hc = [] { int v = 0; if (const char* e = getenv("LMG_HOST_CORES")) v = atoi(e); if (v <= 0) if (const char* e = getenv("OMP_NUM_THREADS")) v = atoi(e); if (v <= 0) v = (int)std::thread::hardware_concurrency(); return v > 0 ? v : 8; }();
@@ -295,7 +326,7 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
-static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.keys = I.d_keys; P.val_off = I.d_val_off; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
+static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
@@ -338,12 +369,12 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivor
   cudaStream_t st = ix->st; const Image& I = ix->img; ProbeParams P = probe_params(I, prm->min_prefix); DBuf<u32> nh(1, st); DBuf<u64> dstats(8, st); dstats.zero(); const u32 ns = SV.n; DBuf<Surv>& surv = SV.d;
   // phase B: index lookup on the survivors
   DBuf<ProbeHit> hits; u64 capH = std::max<u64>(1u << 18, (u64)ns / 2 + 1024); u32 nhit = 0;
-  for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) { u64 z[2] = {0, 0}; CUDA_CHECK(cudaMemcpyAsync(dstats.p + 2, z, 16, cudaMemcpyHostToDevice, st)); }
-    cudaEventRecord(ix->kev[1], st); k_probe_find2<<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), stats ? dstats.p : nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
+  for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) CUDA_CHECK(cudaMemsetAsync(dstats.p + 2, 0, 40, st));
+    cudaEventRecord(ix->kev[1], st); if (stats) k_probe_find2<true><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), dstats.p); else k_probe_find2<false><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
     nhit = nh.to_host()[0]; if (nhit <= capH) break; capH = (u64)ns + 1024; }
   if (!hits.p) hits.alloc(16, st);
   { float fb = 0; if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] += fb; ix->counters[13] = (u64)(fb * 1000); }
-  { auto sdt = dstats.to_host(); if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; } ix->counters[4] = nhit; }
+  { auto sdt = dstats.to_host(); if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; ix->pstat[0] = sdt[4]; ix->pstat[1] = sdt[5]; ix->pstat[2] = sdt[6]; } ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
   DBuf<u64> hoff(nhit + 1, st);
   { DBuf<u64> cnt(nhit + 1, st); k_hit_counts<<<cdiv(nhit + 1, 256), 256, 0, st>>>(hits.p, nhit, cnt.p); KERNEL_CHECK();
@@ -1414,6 +1445,7 @@ static void search_range(lmg_index* lx, const lmg_params* p, const u8* seqs, con
 
 static void search_lanes(lmg_index* ix, const lmg_params* p, const u8* seqs, const u64* off, int nq, lmg_results& R, lmg_queries* staged) {
   auto w0 = std::chrono::steady_clock::now(); const int dev = ix->img.device; CUDA_CHECK(cudaSetDevice(dev));
+  if (ix->img.synth_per) throw std::runtime_error("this index is a synthetic seeds-only image (lmg_index_synth): only lmg_probe_bench runs on it");
   if (ix->img.n_shards > 1 && p->top_n_genomes > 0) throw std::runtime_error("--top-n-genomes cannot be applied inside one genome shard (the top N are chosen over all genomes): search the shards without it and select after merging");
   std::vector<int> cut = staged ? staged->cut : lane_cuts(off, nq, pick_lanes(p, nq, off[nq] - off[0])); const int L = (int)cut.size() - 1;
   if (L == 1) { ix->active_lanes = 1; search_range(ix, p, seqs, off, nq, R, staged ? &staged->parts[0] : nullptr); }
@@ -1453,6 +1485,26 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
     wfa_run_all(st, pr.multiProcessorCount, dj, de, ex, (u32)n, dq.p, dqm.p, dqo.p, dt.p, dto.p, 1, adaptive, hw, ops, counters, dms, pr.totalGlobalMem); std::string out;
     for (int i = 0; i < n; i++) { for (i64 x = (i64)hw[i].ops_n - 1; x >= 0; x--) { u64 op = ops[hw[i].ops_off + x]; out += std::to_string((u32)(op & 0xffffffffu)); out.push_back((char)(op >> 32)); } out.push_back('\n'); }
     char* c = (char*)malloc(out.size() + 1); memcpy(c, out.data(), out.size() + 1); *cigars = c; *cigars_len = out.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
+
+int lmg_index_set_total_bases(lmg_index* ix, int64_t tb) { if (!ix || tb <= 0) { g_err = "lmg_index_set_total_bases: total_bases must be positive"; return -1; } std::lock_guard<std::mutex> lk(ix->mu); ix->imgp->total_bases = tb; return 0; }
+int lmg_index_load_times(const lmg_index* ix, double* ms4) { for (int i = 0; i < 4; i++) ms4[i] = ix->img.load_ms[i]; return 0; }
+int lmg_probe_model(const lmg_index* ix, uint64_t* s4) { for (int i = 0; i < 4; i++) s4[i] = ix->pstat[i]; return 0; }
+int lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed, int32_t mask_lo, int32_t mask_hi, int32_t with_values, lmg_index** out) {
+  try { int ndev = 0; CUDA_CHECK(cudaGetDeviceCount(&ndev)); if (ndev == 0) throw std::runtime_error("no CUDA device: the LexicMap GPU path has no CPU fallback"); if (masks < 64 || per_mask == 0 || per_mask >= (1ull << 31) || mask_lo < 0 || mask_hi > masks || mask_lo >= mask_hi) throw std::runtime_error("lmg_index_synth: bad arguments");
+    Image* im = new Image; lmg_index* ix = nullptr; try { im->synth(device, masks, per_mask, seed, mask_lo, mask_hi, with_values != 0); im->info.chunks = 0; im->info.partitions = im->NA; im->info.genome_batches = 0; im->synth_per = per_mask; im->synth_seed = seed; ix = make_ctx(im, true, device); } catch (...) { if (!ix) { im->release(); delete im; } throw; }
+    *out = ix; return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
+int lmg_probe_bench(lmg_index* ix, uint64_t n_queries, uint64_t seed, int32_t min_prefix, int32_t iters, double* out16) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); const Image& I = ix->img; if (!I.synth_per) throw std::runtime_error("lmg_probe_bench needs an index made by lmg_index_synth"); CUDA_CHECK(cudaSetDevice(I.device)); cudaStream_t st = ix->st;
+    if (n_queries == 0 || n_queries >= (1ull << 31)) throw std::runtime_error("lmg_probe_bench: 1 <= n_queries < 2^31"); ProbeParams P = probe_params(I, min_prefix); for (int i = 0; i < 16; i++) out16[i] = 0;
+    DBuf<Surv> surv(2 * n_queries + 64, st); DBuf<u32> nsv(1, st), nh(1, st); DBuf<u64> dstats(8, st); nsv.zero(); dstats.zero(); cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st); k_c5_gen<<<cdiv((i64)n_queries, 256), 256, 0, st>>>(P, I.d_masks, I.d_mask_pstart, I.mask_pbits, I.synth_per, I.synth_seed, seed, n_queries, I.mask_lo, I.mask_hi, surv.p, nsv.p, (u32)(2 * n_queries), dstats.p); KERNEL_CHECK(); cudaEventRecord(e1, st);
+    const u32 ns = nsv.to_host()[0]; float fg = 0; cudaEventElapsedTime(&fg, e0, e1); out16[0] = (double)dstats.to_host()[0]; out16[1] = (double)ns; out16[9] = fg; DBuf<ProbeHit> hits((u64)ns + 64, st); double tsum = 0, tmin = 1e30;
+    for (int it = -1; it < iters && ns; it++) { nh.zero(); cudaEventRecord(e0, st); k_probe_find2<false><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, ns, nullptr); KERNEL_CHECK(); cudaEventRecord(e1, st); CUDA_CHECK(cudaEventSynchronize(e1)); float f = 0; cudaEventElapsedTime(&f, e0, e1); if (it >= 0) { tsum += f; tmin = std::min(tmin, (double)f); } }
+    out16[2] = iters > 0 ? tsum / iters : 0; out16[10] = tmin < 1e29 ? tmin : 0; out16[3] = (double)nh.to_host()[0];
+    if (ns) { nh.zero(); dstats.zero(); k_probe_find2<true><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, ns, dstats.p); KERNEL_CHECK(); auto sd = dstats.to_host(); out16[4] = (double)sd[4]; out16[5] = (double)sd[5]; out16[6] = (double)sd[6]; out16[7] = (double)sd[2]; out16[8] = (double)sd[3]; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); CUDA_CHECK(cudaStreamSynchronize(st)); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 
 int lmg_queries_upload(lmg_index* ix, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_queries** out) {

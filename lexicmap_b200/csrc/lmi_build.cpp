@@ -357,7 +357,9 @@ int main(int argc, char** argv) {
       std::string synth = arg(argc, argv, "--synth", ""), list = arg(argc, argv, "--in-list", "");
       if (!synth.empty()) {  // F,S,G,seed[,max_contigs]
         int F, S, G, mc = 20; unsigned long long sd; int n = sscanf(synth.c_str(), "%d,%d,%d,%llu,%d", &F, &S, &G, &sd, &mc); if (n < 4) die("--synth F,S,G,seed[,max_contigs]");
-        build_index(out, (size_t)F * S, [&](size_t gi) { return synth_genome((int)(gi / S), (int)(gi % S), S, G, sd, mc); }, o);
+        // --synth-range lo,hi: only genomes [lo, hi) of the collection (one shard of a genome-sharded collection; same masks, same genomes as the full build)
+        long long lo = 0, hi = (long long)F * S; std::string rg = arg(argc, argv, "--synth-range", ""); if (!rg.empty() && (sscanf(rg.c_str(), "%lld,%lld", &lo, &hi) != 2 || lo < 0 || hi > (long long)F * S || lo >= hi)) die("--synth-range lo,hi within [0, F*S)");
+        build_index(out, (size_t)(hi - lo), [&](size_t gi) { size_t g = gi + (size_t)lo; return synth_genome((int)(g / S), (int)(g % S), S, G, sd, mc); }, o);
       } else if (!list.empty()) {  // text file: one FASTA(.gz) path per line; genome id = file name up to first ".fa"/".fna"/".fasta"
         std::vector<std::string> files; { FILE* f = fopen(list.c_str(), "r"); if (!f) die("cannot open " + list); char l[4096]; while (fgets(l, sizeof l, f)) { std::string s(l); while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); if (!s.empty()) files.push_back(s); } fclose(f); }
         build_index(out, files.size(), [&](size_t gi) {

@@ -44,7 +44,8 @@ int main(int argc, char** argv) {
     else if (a == "-j" || a == "--threads" || a == "-J" || a == "--max-query-conc" || a == "--max-open-files" || a == "--gc-interval" || a == "-S" || a == "--max-seed-matching-conc") need(i);   // accepted, meaningless on the GPU path
     else if (a == "-T" || a == "--taxdump" || a == "-G" || a == "--genome2taxid" || a == "-t" || a == "--taxids" || a == "--taxid-file" || a == "-k" || a == "--keep-genomes-without-taxid")
       die("taxonomy filtering (" + a + ") is not part of the GPU search path; filter the TSV by sgenome afterwards");   // search.go:236-330, out of scope
-    else if (a == "-w" || a == "--load-whole-seeds" || a == "--debug") {} else if (a == "-h" || a == "--help") { usage(); return 0; }
+    else if (a == "-w" || a == "--load-whole-seeds") die("-w/--load-whole-seeds selects the reference's in-memory searcher, which tests the reversed flag of every seed value (kv-searcher2.go:302) where the default on-disk searcher tests the first value of a k-mer (kv-searcher.go:466-488); the GPU image always holds all seeds in memory and implements the default semantics only: run without -w");
+    else if (a == "--debug") { if (!o.quiet) fprintf(stderr, "[INFO] --debug has no effect on the GPU path (LMG_DEBUG_TIMING=1 prints the host-side stage times)\n"); } else if (a == "-h" || a == "--help") { usage(); return 0; }
     else if (a[0] == '-' && a.size() > 1) die("unknown flag: " + a); else o.files.push_back(a); }
   // option checks, search.go:163-230
   if (o.index.empty()) die("flag -d/--index needed");
@@ -75,13 +76,16 @@ int main(int argc, char** argv) {
       fprintf(out, "\n"); }
     lmg_results_free(r); total += ids.size(); ids.clear(); seqs.clear(); off.assign(1, 0); fflush(out);
   };
-  for (const std::string& f : o.files) { gzFile g = (f == "-") ? gzdopen(0, "rb") : gzopen(f.c_str(), "rb"); if (!g) die("cannot open " + f); static char buf[1 << 16]; std::string id, seq; bool have = false, fastq = false; int fqline = 0;
+  // whole lines of any length (a FASTQ record of an ONT read is one line of > 64 kb): gzgets chunks are joined until the newline
+  auto read_line = [](gzFile g, std::string& line) -> bool { static char chunk[1 << 16]; line.clear(); bool any = false; while (gzgets(g, chunk, sizeof chunk)) { any = true; size_t l = strlen(chunk); line.append(chunk, l); if (l && chunk[l - 1] == '\n') break; }
+    while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back(); return any; };
+  for (const std::string& f : o.files) { gzFile g = (f == "-") ? gzdopen(0, "rb") : gzopen(f.c_str(), "rb"); if (!g) die("cannot open " + f); gzbuffer(g, 1 << 20); std::string id, seq, line; bool have = false, fastq = false; int fqline = 0;
     auto push = [&]() { if (!have) return; if (seq.size() >= 31) { ids.push_back(id); seqs += seq; off.push_back(seqs.size()); } else total++;   // queries shorter than k are skipped, search.go:571-575
       have = false; seq.clear(); if ((long)seqs.size() >= o.batch_bases || (int)ids.size() >= o.batch_queries) flush(); };
-    while (gzgets(g, buf, sizeof buf)) { size_t l = strlen(buf); while (l && (buf[l - 1] == '\n' || buf[l - 1] == '\r')) buf[--l] = 0;
-      if (fastq) { fqline++; if (fqline == 1) seq += buf; else if (fqline == 3) { fastq = false; push(); } continue; }
-      if (buf[0] == '>' || buf[0] == '@') { push(); have = true; const char* e = buf + 1; while (*e && *e != ' ' && *e != '\t') e++; id.assign((const char*)buf + 1, e); if (buf[0] == '@') { fastq = true; fqline = 0; } }
-      else if (have) seq += buf; }
+    while (read_line(g, line)) { const char* buf = line.c_str();
+      if (fastq) { fqline++; if (fqline == 1) seq += line; else if (fqline == 3) { fastq = false; push(); } continue; }
+      if (buf[0] == '>' || buf[0] == '@') { push(); have = true; const char* e = buf + 1; while (*e && *e != ' ' && *e != '\t') e++; id.assign(buf + 1, e); if (buf[0] == '@') { fastq = true; fqline = 0; } }
+      else if (have) seq += line; }
     push(); gzclose(g); }
   flush();
   if (!o.quiet) { double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(); fprintf(stderr, "[INFO] processed queries: %llu, speed: %.3f queries per minute\n[INFO] %.4f%% (%llu/%llu) queries matched\n", total, total / s * 60, total ? 100.0 * matched / total : 0.0, matched, total); }

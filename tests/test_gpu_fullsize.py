@@ -16,7 +16,7 @@ def full_case():
     from oracle_binding import read_fasta
     import lexicmap_b200
     os.makedirs(WORK, exist_ok=True)
-    idx = make_index(WORK, "c2_50x20x1000000", "50,20,1000000,20260924,20", chunks=16)   # same directory and arguments as bench.py::ensure_workload
+    idx = make_index(WORK, "c2d_50x20x1000000", "50,20,1000000,20260924,20", chunks=16)   # same directory and arguments as bench.py::ensure_c2 (desert-filled, the writer's default)
     ids, seqs = read_fasta(make_queries(WORK, idx, "c2_fullsize_q", 10000, 1000, seed=20260925))
     return idx, lexicmap_b200.Index(idx, device=0), seqs
 
@@ -52,14 +52,17 @@ def test_full_size_lanes_idempotence_and_bounds(full_case):
     assert np.all(r["cls"][first] == 1) and np.all(r["hsp"][first] == 1)
 
 
-def test_full_size_sample_matches_oracle(full_case):
+def test_full_size_batch_matches_oracle(full_case):
+    """all 10,000 queries of the benchmark batch, every column of every row, CIGARs and sequence ids included, against the CPU oracle"""
     idx, g, seqs = full_case
     from oracle_binding import Oracle
     o = Oracle(idx)
-    rng = np.random.default_rng(7)
-    pick = sorted(rng.choice(len(seqs), size=192, replace=False).tolist())
-    sub = [seqs[i] for i in pick]
-    gr, gs, gc = g.search(sub, g.default_params(output_seq=1, lanes=3))   # forced lanes on a small batch
-    orr, os_, oc = o.search(sub, o.default_params(output_seq=1), threads=os.cpu_count() or 8)
-    assert len(orr) > 1000
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    orr, os_, oc = o.search(seqs, o.default_params(output_seq=1), threads=threads)
+    gr, gs, gc = g.search(seqs, g.default_params(output_seq=1))
+    assert len(orr) > 100000
     _same((gr, gs, gc), (orr, os_, oc))
+    rng = np.random.default_rng(7)
+    pick = sorted(rng.choice(len(seqs), size=96, replace=False).tolist())
+    sub = [seqs[i] for i in pick]
+    _same(g.search(sub, g.default_params(output_seq=1, lanes=3)), o.search(sub, o.default_params(output_seq=1), threads=threads))   # forced lanes on a small batch
