@@ -302,14 +302,8 @@ def run_search(a, rank, world, local):
 
     def hits_allreduce(rows):
         """genome-sharded search: per-query genome counts of this shard -> NCCL sum over the shards (merge-search-results.go:143-153)"""
-        h = np.zeros(nq, np.int32)
-        if len(rows):
-            first = np.r_[True, rows["query"][1:] != rows["query"][:-1]]
-            h[rows["query"][first]] = rows["hits"][first]
-        t = torch.from_numpy(h).cuda()
-        if dist:
-            dist.all_reduce(t)
-        return t
+        from lexicmap_b200.dist import shard_hit_counts, allreduce_hits
+        return allreduce_hits(shard_hit_counts(rows, nq), device=torch.device("cuda", local))
 
     collect = cfgname == "c3"
     # ---- value leg: staged inputs

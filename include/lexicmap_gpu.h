@@ -77,6 +77,11 @@ typedef struct lmg_chain {        /* one lexichash chain: first/last anchor (all
   int32_t q0, t0, len0, q1, t1, len1; int32_t rc;
 } lmg_chain;
 
+typedef struct lmg_pa {           /* one Chain2Result of SeqComparator.Compare (lib-seq_compare.go:335-522, lib-chaining2.go:106-135) in window coordinates */
+  uint64_t genome; uint32_t query; int32_t t_begin, t_end, rc;   /* the chain's target window [t_begin, t_end] on the concatenated genome, rc = minus strand (lib-index-search.go:1987-2051) */
+  int32_t qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors;
+} lmg_pa;
+
 typedef struct lmg_index lmg_index;
 typedef struct lmg_results lmg_results;
 
@@ -133,6 +138,8 @@ int  lmg_mask_batch(lmg_index* idx, const uint8_t* seqs, const uint64_t* seq_off
 int  lmg_anchor_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, const uint64_t* seq_off, int32_t n, lmg_anchor** out, uint64_t* n_out);
 /* ClearSubstrPairs + Chainer.Chain (lib-index-search.go:864-990, lib-chaining.go:122-633) */
 int  lmg_chain_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, const uint64_t* seq_off, int32_t n, lmg_chain** out, uint64_t* n_out);
+/* window geometry + SeqComparator.Index/Compare + Chainer2 (a9-a12: lib-index-search.go:1987-2051, lib-seq_compare.go:115-159,:335-522, lib-chaining2.go) */
+int  lmg_pseudoalign_batch(lmg_index* idx, const lmg_params* p, const uint8_t* seqs, const uint64_t* seq_off, int32_t n, lmg_pa** out, uint64_t* n_out);
 /* WFA batch (wfa.Aligner.Align): pairs of ASCII sequences -> CIGAR strings in wfa convention, '\n' separated */
 int  lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off /*2n+1*/, int32_t n, int32_t adaptive, char** cigars, uint64_t* cigars_len);
 void lmg_free(void* p);

@@ -31,6 +31,10 @@ ANCHOR_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("qbegin", "<i4"),
 CHAIN_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("score", "<f4"), ("n_seeds", "<i4"), ("q0", "<i4"), ("t0", "<i4"), ("len0", "<i4"),
                         ("q1", "<i4"), ("t1", "<i4"), ("len1", "<i4"), ("rc", "<i4")])
 
+PA_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("t_begin", "<i4"), ("t_end", "<i4"), ("rc", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("tb", "<i4"), ("te", "<i4"),
+                     ("aligned_q", "<i4"), ("aligned_t", "<i4"), ("matched", "<i4"), ("n_anchors", "<i4")])
+
+
 def split_align_text(rows, pool):
     """with output_seq the pool entry of a row is cigar | qseq | sseq | align (alen bytes each); returns [(qseq, sseq, align)] or None"""
     if not len(rows) or len(pool) < int(rows["cigar_off"][-1]) + int(rows["cigar_len"][-1]) + 3 * int(rows["alen"][-1]) or not int(rows["cigar_len"].max()):
@@ -72,6 +76,7 @@ def load_library():
     L.lmg_mask_batch.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, u64p]
     L.lmg_anchor_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_chain_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
+    L.lmg_pseudoalign_batch.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_wfa_batch.argtypes = [C.c_int, vp, vp, C.c_int32, C.c_int32, C.POINTER(vp), u64p]
     L.lmg_free.argtypes = [vp]
     L.lmg_index_set_total_bases.argtypes = [vp, C.c_int64]
@@ -279,6 +284,10 @@ class Index:
 
     def chains(self, seqs, params=None):
         return self._stage(self.lib.lmg_chain_batch, CHAIN_DTYPE, seqs, params)
+
+    def pseudoalign(self, seqs, params=None):
+        """window geometry + pseudo-alignment + Chainer2: one record per Chain2Result, window coordinates (a9-a12)"""
+        return self._stage(self.lib.lmg_pseudoalign_batch, PA_DTYPE, seqs, params)
 
 
 def wfa_batch(pairs, device=0, adaptive=1):

@@ -26,6 +26,7 @@
 #include <set>
 #include <array>
 #include <memory>
+#include <sched.h>
 
 // =====================================================================================================
 // small device utilities
@@ -119,7 +120,10 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 // K2: seed probe (kv.Searcher.Search / Search2, kv/kv-searcher.go:190-1088) + anchors (lib-index-search.go:1357-1569)
 // =====================================================================================================
 struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 bucket; };  // mask_dir = capturing mask<<1 | dir ; [lo,lo+n) = query table rows (locs); bucket = mask bucket searched; [e0, e0+ne) = matched index entries
-struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_start, *anchor_bits; int m, k, NA, mask_prefix, anchor_prefix, p; };
+struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_start, *anchor_bits, *pbloom; u32 pbmask; int m, k, NA, mask_prefix, anchor_prefix, p; };
+// a probe survives when its anchor exists in the bucket's anchor table (the reference's own test) AND some key of the bucket starts with the probe's first maskPrefix+anchorPrefix bases (prefix Bloom filter, image.cuh)
+__device__ __forceinline__ bool probe_may_hit(const ProbeParams& P, u32 bucket, u64 left, int ash) { const u32 pre = (u32)(left >> ash); const u64 aslot = (u64)bucket * P.NA + (pre & (u32)(P.NA - 1)); if (!((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1)) return false;
+  const u32 hb = pb_hash(bucket, pre) & P.pbmask; return (P.pbloom[hb >> 5] >> (hb & 31)) & 1; }
 
 // Probe semantics (kv.Searcher.Search / Search2): dir 0 = captured k-mer against its own mask bucket, values must have reverse flag 0;
 // dir 1 = base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
@@ -133,9 +137,9 @@ __global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap,
   u64 qi = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool s0 = false, s1 = false; Surv a, b; u32 issued = 0;
   if (qi < nslot) { u64 kmer = cap.kmer[qi];
     if (kmer != 0) { u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); const int s2 = (P.k - P.p) << 1; const u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1;
-      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; a.lo = cap.lo[qi]; a.n = cap.n[qi]; } }
+      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if (probe_may_hit(P, (u32)i, left, ash)) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; a.lo = cap.lo[qi]; a.n = cap.n[qi]; } }
       u32 lo = cap.lo[qi]; if (owner[koff[q] + lo] == (u32)i) { u64 rv = kmer_reverse62(kmer, P.k); u32 sm = cap.smask[qi]; u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)sm * P.NA + an; issued++;
-        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = lo; b.n = cap.n[qi]; } } } }
+        if (probe_may_hit(P, sm, left, ash)) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = lo; b.n = cap.n[qi]; } } } }
   int lane = threadIdx.x & 31; u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1); u32 tot = __popc(b0) + __popc(b1);
   if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
     if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = b; } }
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
     if (i < m) { u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
       u64 km = tab[lo]; bool lc = (lcb[lo >> 5] >> (lo & 31)) & 1;   // km==0 is DUST-low-complexity too, as in the reference
       if (!lc) { atomicMin(&own[lo], (u32)i); u64 left = km & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++;
-        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot; r.lo = lo; r.n = hi - lo; } }
+        if (probe_may_hit(P, (u32)i, left, ash)) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot; r.lo = lo; r.n = hi - lo; } }
       if (DUMP) { u64 w = (u64)q * m + i; cap.kmer[w] = lc ? 0 : km; cap.lo[w] = lo; cap.n[w] = hi - lo; cap.smask[w] = 0; } }
     emit(s0, r); }
   __syncthreads();
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
       if (i != 0xFFFFFFFFu) { u64 km = tab[rr]; u32 c = 1; while (rr + c < n && tab[rr + c] == km) c++;
         u64 rv = kmer_reverse62(km, k); u32 mp = (u32)(rv >> msh); u32 a = mask_pstart[mp], b = mask_pstart[mp + 1]; if (a == b) { a = 0; b = (u32)m; } xor_argmin_range(masks, a, b, rv);
         u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)a * P.NA + an; issued++;
-        if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; r.kmer = rv; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot | 0x80000000u; r.lo = rr; r.n = c; }
+        if (probe_may_hit(P, a, left, ash)) { s1 = true; r.kmer = rv; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot | 0x80000000u; r.lo = rr; r.n = c; }
         if (DUMP) { cap.smask[(u64)q * m + i] = a; owner_g[o + rr] = i; } } }
     emit(s1, r); }
   if (stats) { for (int of = 16; of; of >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, of); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
@@ -222,10 +226,10 @@ __global__ void __launch_bounds__(256) k_c5_gen(ProbeParams P, const u64* __rest
     else { key = r >> 2; bucket = argmin_mask(key); }
     const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1;
     if ((int)bucket >= mask_lo && (int)bucket < mask_hi) { issued++; const u64 left = key & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)bucket * P.NA + an;
-      if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s0 = true; a.kmer = key; a.qi = (u32)q; a.aslot_dir = (u32)aslot; a.lo = 0; a.n = 1; } }
+      if (probe_may_hit(P, bucket, left, ash)) { s0 = true; a.kmer = key; a.qi = (u32)q; a.aslot_dir = (u32)aslot; a.lo = 0; a.n = 1; } }
     const u64 rv = kmer_reverse62(key, k); const u32 b2 = argmin_mask(rv);
     if ((int)b2 >= mask_lo && (int)b2 < mask_hi) { issued++; const u64 left = rv & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)b2 * P.NA + an;
-      if ((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1) { s1 = true; b.kmer = rv; b.qi = (u32)q; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = 0; b.n = 1; } } }
+      if (probe_may_hit(P, b2, left, ash)) { s1 = true; b.kmer = rv; b.qi = (u32)q; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = 0; b.n = 1; } } }
   const u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1), tot = __popc(b0) + __popc(b1);
   if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
     if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap) surv[w] = b; } }
@@ -279,10 +283,14 @@ struct HostPool {
 struct lmg_index {
   Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
   double ms[16] = {0}; u64 counters[16] = {0}; u64 pstat[4] = {0, 0, 0, 0};   /* last statistics pass of the seed lookup: sum ceil(log2(n_a+1)), sum of 32-byte sectors of matched entries, sum of values of matched entries */ std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
-  // workers per lane: half of this process's cores over the active lanes. LMG_HOST_CORES (or OMP_NUM_THREADS, which launchers such as torchrun
-  // set per rank) tells how many cores the process may use when several ranks share a node.
-  int host_threads() const { static const int hc = [] { int v = 0; if (const char* e = getenv("LMG_HOST_CORES")) v = atoi(e); if (v <= 0) if (const char* e = getenv("OMP_NUM_THREADS")) v = atoi(e); if (v <= 0) v = (int)std::thread::hardware_concurrency(); return v > 0 ? v : 8; }();
-    return std::max(1, std::min(32, hc / (2 * std::max(1, active_lanes)))); }
+  // workers per lane: this process's usable cores over the active lanes. LMG_HOST_CORES (or OMP_NUM_THREADS, which launchers such as torchrun set per
+  // rank) tells how many cores the process may use when several ranks share a node; otherwise the affinity mask capped by the cgroup CPU quota
+  // (a GPU lease of a big box shows all its cores in hardware_concurrency() but schedules only the quota: oversubscribed pools stall every lane).
+  static int usable_cores() { int v = 0; cpu_set_t cs; CPU_ZERO(&cs); if (sched_getaffinity(0, sizeof cs, &cs) == 0) v = CPU_COUNT(&cs); if (v <= 0) v = (int)std::thread::hardware_concurrency();
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) { char a[64]; double per = 0; if (fscanf(f, "%63s %lf", a, &per) == 2 && strcmp(a, "max") != 0 && per > 0) { int q = (int)(atof(a) / per + 0.5); if (q > 0) v = std::min(v, q); } fclose(f); }
+    return v > 0 ? v : 8; }
+  int host_threads() const { static const int hc = [] { int v = 0; if (const char* e = getenv("LMG_HOST_CORES")) v = atoi(e); if (v <= 0) if (const char* e = getenv("OMP_NUM_THREADS")) v = atoi(e); if (v <= 0) v = usable_cores(); return v > 0 ? v : 8; }();
+    return std::max(1, std::min(32, hc / std::max(1, active_lanes))); }
   lmg_index(Image* p, bool own) : imgp(p), img(*p), owner(own) {}
 };
 
@@ -326,7 +334,7 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
-static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
+static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.pbloom = I.d_pbloom; P.pbmask = I.pbmask; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
@@ -999,6 +1007,9 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
 #define WF_OPSMAX 4096
 #define WF_WARPS 8
 #define WF_SEQW 144
+#define X2_LV 2
+#define OE2_LV 4
+#define E2_LV 1
 #define WF_SMEM_BYTES ((size_t)WF_WARPS * (WF_SEQW * 8 + 9 * WFS * 2 + WFS * 2))
 struct WfaSeg { u64 qw, tw; };   // word offsets of the job's packed query / target (query: 2 streams: bases at qw, ambiguity at qw + nqw)
 
@@ -1011,14 +1022,14 @@ __global__ void k_wfa_prep(const HspJob* __restrict__ jobs, const ExtOut* __rest
 }
 __device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos) { u32 i = (u32)pos >> 5, sh = ((u32)pos & 31) * 2; u64 a = W[i]; if (sh == 0) return a; return (a << sh) | (W[i + 1] >> (64 - sh)); }
 
-__global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, u32 job0, u32 njobs, u32* __restrict__ next_job,
+__global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, const u32* __restrict__ job_ids, u32 job0, u32 njobs, u32* __restrict__ next_job,
                                                           u16* __restrict__ slabs, WfaOut* __restrict__ outs, int adaptive, int lmax) {
   extern __shared__ __align__(16) u8 wf_smem[];   // per warp: packed sequences | ring of 9 wavefronts (0-4: M levels L%5, 5-6: I L%2, 7-8: D L%2) | distances of the current M wavefront
   const int X2 = 2, OE2 = 4, E2 = 1;        // penalties 4 / 8 / 2 in units of levels (score = 2*level)
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wf_smem + (size_t)wib * WF_SEQW; u16 (*R)[WFS] = (u16 (*)[WFS])(wf_smem + (size_t)WF_WARPS * WF_SEQW * 8) + (size_t)wib * 9;
   u16* Dst = (u16*)(wf_smem + (size_t)WF_WARPS * WF_SEQW * 8 + (size_t)WF_WARPS * 9 * WFS * 2) + (size_t)wib * WFS;
   for (;;) {
-    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job0 + jr; u16* slab = slabs + (u64)jr * lmax * 3 * WFS;   // one slab per alignment of the round
+    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job_ids ? job_ids[job0 + jr] : job0 + jr; u16* slab = slabs + (u64)jr * lmax * 3 * WFS;   // one slab per alignment of the round
     ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
     const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
     { // stage the packed sequences in shared memory when they fit (alignments of up to ~3 kb each side): the extension loop is a chain of dependent word fetches
@@ -1085,8 +1096,8 @@ __global__ void __launch_bounds__(WF_WARPS * 32) k_wfa_fast(const ExtOut* __rest
 }
 // Backtrace of the fast path, ONE THREAD per alignment: the walk is a chain of dependent HBM reads (~1 us each), so 32 of them per warp
 // (instead of lane 0 only) hide the latency. Same decision rule as k_wfa: mismatch(9) > D ext(6) > D open(5) > I ext(2) > I open(1).
-__global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, u32 job0, u32 njobs, const u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int lmax) {
-  const int X2 = 2, OE2 = 4, E2 = 1; u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
+__global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 job0, u32 njobs, const u16* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int lmax) {
+  const int X2 = 2, OE2 = 4, E2 = 1; u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job_ids ? job_ids[job0 + t] : job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
   ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u16* slab = slabs + (u64)t * lmax * 3 * WFS; u64* ops = ops_scratch + (u64)t * WF_OPSMAX;
   i32 L = Rr.wscore / 2; i32 k = kend, off = tlen, lv = L; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0; (void)plen;
   auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
@@ -1114,6 +1125,100 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
   outs[jb] = Rr;
 }
 
+// ---------------- WFA register path: one diagonal per lane, wavefronts in registers
+// After WFA-adaptive reduction (MaxDistDiff 50) the live band of an alignment at <= ~15 % divergence is 10-20 diagonals wide, so the whole
+// wavefront of a level fits the 32 lanes of a warp with one FIXED diagonal per lane (k = kb + lane, kb chosen so that diagonals 0 and
+// kend = tlen - plen sit inside the window). The M offsets of the last four levels and the I / D offsets of the last level then live in
+// registers, neighbours (k-1, k+1) come from warp shuffles, and a level costs ~200 warp instructions instead of the ~850 of the
+// shared-memory-ring kernel (k_wfa_fast: range loops over a padded band, ring index arithmetic, three HBM stores per cell).
+// Backtrace data: ONE u32 per (level, lane) — the backtrace decision taken with exactly the values the backtrace of k_wfa_fast would
+// load: pre-extension offset (15 bits) | source of the M cell (4 bits: 9 mismatch, 6 D-ext, 5 D-open, 2 I-ext, 1 I-open) | "I came from
+// I-ext" | "D came from D-ext" — 128 B per level (k_wfa_fast: 1,632 B), written as one coalesced line; the backtrace reads one word per step.
+// A level whose range leaves the window (wide bands: high divergence, long gaps) reports status 1 and the alignment is redone by k_wfa_fast /
+// k_wfa: results are identical whichever kernel runs (same recurrences, same reduction rule, same tie-breaking).
+#define WR_WARPS 8
+#define WR_SEQW 144
+#define WR_SMEM_BYTES ((size_t)WR_WARPS * WR_SEQW * 8)
+__device__ __forceinline__ i32 wr_window_base(i32 kend) { return (kend >= 0 ? kend / 2 : -((-kend + 1) / 2)) - 16; }   // window [kb, kb+31] centred between diagonal 0 and kend
+__global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, u32 job0, u32 njobs, u32* __restrict__ next_job,
+                                                         u32* __restrict__ slabs, WfaOut* __restrict__ outs, int adaptive, int lmax) {
+  extern __shared__ __align__(16) u8 wr_smem[];
+  const int X2 = 2, OE2 = 4, E2 = 1; const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wr_smem + (size_t)wib * WR_SEQW;
+  for (;;) {
+    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job0 + jr; u32* slab = slabs + (u64)jr * lmax * 32;
+    ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
+    const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
+    { const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
+      if (nqw + nA + ntw <= WR_SEQW) { u64* sq = seqb; for (u32 i = lane; i < nqw + nA; i += 32) sq[i] = Q[i]; for (u32 i = lane; i < ntw; i += 32) sq[nqw + nA + i] = T[i]; __syncwarp(); Q = sq; A = sq + nqw; T = sq + nqw + nA; } }
+    WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
+    const i32 kb = wr_window_base(kend), k = kb + lane;
+    if (plen >= 32000 || tlen >= 32000 || plen <= 0 || tlen <= 0 || 0 < kb + 2 || 0 > kb + 29 || kend < kb + 2 || kend > kb + 29) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    auto extend = [&](i32 kk, i32 h) { i32 v = h - kk; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
+    i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
+    i32 m1 = -1, m2 = -1, m3 = -1, m4 = -1, i1 = -1, d1 = -1;   // M of levels L-1..L-4, I and D of level L-1 on this lane's diagonal; -1 = null
+    if (k == 0) m1 = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = 0;
+    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = __shfl_sync(FULLMASK, m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }
+    while (!done) {
+      L++; if (L >= lmax) { overflow = true; break; }
+      const bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
+      i32 lo = INT32_MAX, hi = INT32_MIN; const bool allnull = nx && no && ni && nd;
+      if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
+      if (!allnull && (lo < kb + 1 || hi > kb + 30)) { overflow = true; break; }   // lanes 0 and 31 stay null: every k-1 / k+1 neighbour of a live cell is inside the window
+      // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab)
+      i32 m4l = __shfl_up_sync(FULLMASK, m4, 1), i1l = __shfl_up_sync(FULLMASK, i1, 1), m4r = __shfl_down_sync(FULLMASK, m4, 1), d1r = __shfl_down_sync(FULLMASK, d1, 1);
+      if (lane == 0) { m4l = -1; i1l = -1; } if (lane == 31) { m4r = -1; d1r = -1; }
+      i32 om = -1, oi = -1, od = -1, dv = INT32_MAX; u32 cell = 0;
+      if (!allnull && k >= lo && k <= hi) {
+        i32 ins = max(m4l, i1l); ins = (ins < 0) ? -1 : ins + 1; i32 del = max(m4r, d1r); i32 mis = (m2 < 0) ? -1 : m2 + 1;
+        const i32 hmax = min(tlen, plen + k); if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
+        i32 mm = max(mis, max(ins, del)); if (mm >= 0) { om = extend(k, mm); dv = max(plen - (om - k), tlen - om); } oi = ins; od = del;
+        // backtrace decisions, from the unfiltered values: offset first, then mismatch(9) > D-ext(6) > D-open(5) > I-ext(2) > I-open(1)
+        i32 best = -1; if (m2 >= 0) best = ((m2 + 1) << 4) | 9; if (m4l >= 0) best = max(best, ((m4l + 1) << 4) | 1); if (i1l >= 0) best = max(best, ((i1l + 1) << 4) | 2); if (m4r >= 0) best = max(best, (m4r << 4) | 5); if (d1r >= 0) best = max(best, (d1r << 4) | 6);
+        if (best >= 0) cell = (u32)(best >> 4) | ((u32)(best & 15) << 15);
+        if (i1l >= 0 && i1l >= m4l) cell |= 1u << 19; if (d1r >= 0 && d1r >= m4r) cell |= 1u << 20; if (m4l < 0 && i1l < 0) cell |= 1u << 21; if (m4r < 0 && d1r < 0) cell |= 1u << 22;   // bits 21/22: no source for the I / D state (backtrace error as in k_wfa_bt)
+      }
+      bool anyM = __any_sync(FULLMASK, om >= 0), anyI = __any_sync(FULLMASK, oi >= 0), anyD = __any_sync(FULLMASK, od >= 0);
+      if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa / k_wfa_fast / the oracle
+        i32 mind = dv; for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50; const bool ok = (om >= 0) && dv <= thr;   // distances of null cells are +inf
+        const i32 top_limit = min(kend, hi); i32 nlo = lo; { u32 bal = __ballot_sync(FULLMASK, ok && k >= lo && k < top_limit); if (bal) nlo = kb + __ffs(bal) - 1; else if (top_limit > lo) nlo = top_limit; }
+        const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; { u32 bal = __ballot_sync(FULLMASK, ok && k <= hi && k > bottom_limit); if (bal) nhi = kb + 31 - __clz(bal); else if (hi > bottom_limit) nhi = bottom_limit; }
+        if (nlo != lo || nhi != hi) { if (k < nlo || k > nhi) { om = -1; oi = -1; od = -1; } anyM = __any_sync(FULLMASK, om >= 0); anyI = __any_sync(FULLMASK, oi >= 0); anyD = __any_sync(FULLMASK, od >= 0); lo = nlo; hi = nhi; }
+      }
+      slab[(u64)L * 32 + lane] = cell;
+      m4 = m3; m3 = m2; m2 = m1; m1 = om; i1 = oi; d1 = od;
+      for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
+      hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
+      if (!allnull && kend >= lo && kend <= hi) { const i32 v = __shfl_sync(FULLMASK, m1, kend - kb); done = (v >= tlen); }
+    }
+    if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = 2 * L; outs[jb] = Rz; }
+    __syncwarp();
+  }
+}
+// backtrace of the register path, one thread per alignment: one word per step
+__global__ void __launch_bounds__(128) k_wfa_bt2(const ExtOut* __restrict__ ext, u32 job0, u32 njobs, const u32* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int lmax) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
+  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen, kb = wr_window_base(kend); const u32* slab = slabs + (u64)t * lmax * 32; u64* ops = ops_scratch + (u64)t * WF_OPSMAX;
+  i32 k = kend, off = tlen, lv = Rr.wscore / 2; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
+  auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
+  auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
+    if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
+    else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
+  while (vv > 0 && h > 0 && lv > 0) {
+    const u32 cell = slab[(u64)lv * 32 + (u32)(k - kb)]; int type;
+    if (mat == 0) { type = (int)((cell >> 15) & 15); if (type == 0) { Rr.status = 2; break; } const i32 mo = (i32)(cell & 0x7FFF); put('M', off - mo, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
+    else if (mat == 1) { if ((cell >> 21) & 1) { Rr.status = 2; break; } type = ((cell >> 19) & 1) ? 2 : 1; }
+    else { if ((cell >> 22) & 1) { Rr.status = 2; break; } type = ((cell >> 20) & 1) ? 6 : 5; }
+    switch (type) { case 9: lv -= X2_LV; mat = 0; put('X', 1, off - k, off); off--; break;
+      case 1: lv -= OE2_LV; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: lv -= E2_LV; mat = 1; put('I', 1, off - k, off); k--; off--; break;
+      case 5: lv -= OE2_LV; mat = 0; put('D', 1, off - k, off); k++; break; case 6: lv -= E2_LV; mat = 2; put('D', 1, off - k, off); k++; break; default: Rr.status = 2; break; }
+    if (Rr.status) break; vv = off - k; h = off;
+  }
+  if (Rr.status == 0) { if (lv == 0) put('M', off, off - k, off); else { if (vv > 0) put('D', vv, vv, h); if (h > 0) put('I', h, 0, h); } }
+  flush();
+  if (want_ops && Rr.status == 0) { if (ops_over) Rr.status = 1; else { u64 o = atomicAdd((unsigned long long*)ops_cursor, (unsigned long long)nops); if (o + nops <= ops_cap) { for (u32 i = 0; i < nops; i++) ops_pool[o + i] = ops[i]; Rr.ops_off = o; Rr.ops_n = nops; } else Rr.status = 3; } }
+  (void)plen; outs[jb] = Rr;
+}
+
 // the dynamic shared-memory ceiling of a kernel is a per-device attribute: raise it once on every device this process runs alignments on
 static void wfa_raise_smem_limit() { static std::mutex mu; static std::set<int> done; int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); std::lock_guard<std::mutex> lk(mu); if (done.count(dev)) return;
   CUDA_CHECK(cudaFuncSetAttribute(k_wfa_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM_BYTES)); done.insert(dev); }
@@ -1126,20 +1231,36 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
       DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st); DBuf<u32> hasamb(nj + 1, st);
       if (g_lap) (*g_lap)("wfa host prep"); { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p, hasamb.p); KERNEL_CHECK(); }
-      // rounds: a fixed HBM budget of per-alignment slabs; forward pass by persistent warps, backtrace by one thread per alignment.
       // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
       i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
-      const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64)); const u64 slab_bytes = (u64)lmax * 3 * WFS * 2;
-      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30) / (u64)std::max(1, active_lanes); const u32 nwarps = (u32)sm_count * 4 * WF_WARPS;
-      u32 per_round = (u32)std::min<u64>(nj, std::max<u64>(nwarps, budgetF / slab_bytes)); if (per_round > nwarps) per_round = per_round / nwarps * nwarps; if (g_arena == nullptr) per_round = std::min<u32>(per_round, 2048);
-      if (g_lap) (*g_lap)("wfa prep kernel"); DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
-      { KTimer kt(st, &ms[11]);
-        for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (n + WF_WARPS - 1) / WF_WARPS);
-          k_wfa_fast<<<blocks, WF_WARPS * 32, WF_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
-          k_wfa_bt<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
-      counters[14] = per_round; counters[15] = (u64)lmax; if (g_lap) (*g_lap)("wfa rounds");
-      std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; }
-      counters[9] = nj; counters[10] = ids.size(); if (g_lap) (*g_lap)("wfa d2h"); }
+      const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64));
+      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30) / (u64)std::max(1, active_lanes);
+      if (g_lap) (*g_lap)("wfa prep kernel");
+      // pass 1, every job: the register kernel (one diagonal per lane, 128 B of backtrace words per level). Rounds only when the slabs of all jobs exceed the budget.
+      std::vector<u32> rest;   // jobs whose band left the 32-lane window (or too deep / too long): pass 2
+      static const bool use_reg = getenv("LMG_NO_WFA_REG") == nullptr;
+      if (use_reg) { const u64 per_job = (u64)lmax * 32 * 4 + (want_ops ? (u64)WF_OPSMAX * 8 : 0); const u32 nwarpsR = (u32)sm_count * 8 * WR_WARPS;
+        u32 per_round = (u32)std::min<u64>(nj, std::max<u64>(nwarpsR, budgetF / per_job)); if (g_arena == nullptr) per_round = std::min<u32>(per_round, 8192);
+        DBuf<u32> rslabs((u64)per_round * lmax * 32, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
+        { KTimer kt(st, &ms[11]);
+          for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 8, (n + WR_WARPS - 1) / WR_WARPS);
+            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, rslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
+            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, rslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
+        std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) rest.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
+        counters[14] = per_round; if (g_lap) (*g_lap)("wfa register pass"); }
+      else { rest.resize(nj); std::iota(rest.begin(), rest.end(), 0u); }
+      counters[9] = nj; counters[10] = rest.size(); counters[15] = (u64)lmax;
+      // pass 2, the jobs left: shared-memory-ring kernel (bands up to 256 diagonals), per-alignment slabs of 3 x u16 per cell in rounds bounded by the HBM budget
+      if (!rest.empty()) { const u32 nr = (u32)rest.size(); DBuf<u32> d_rest(nr, st); d_rest.from_host(rest.data(), nr); const u64 slab_bytes = (u64)lmax * 3 * WFS * 2; const u32 nwarps = (u32)sm_count * 4 * WF_WARPS;
+        u32 per_round = (u32)std::min<u64>(nr, std::max<u64>(nwarps, budgetF / slab_bytes)); if (per_round > nwarps) per_round = per_round / nwarps * nwarps; if (g_arena == nullptr) per_round = std::min<u32>(per_round, 2048);
+        DBuf<u16> fslabs((u64)per_round * lmax * 3 * WFS, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
+        { KTimer kt(st, &ms[11]);
+          for (u32 j0 = 0; j0 < nr; j0 += per_round) { u32 n = std::min(per_round, nr - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 4, (n + WF_WARPS - 1) / WF_WARPS);
+            k_wfa_fast<<<blocks, WF_WARPS * 32, WF_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, d_rest.p, j0, n, next.p, fslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
+            k_wfa_bt<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, d_rest.p, j0, n, fslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
+        if (!use_reg) counters[14] = per_round; if (g_lap) (*g_lap)("wfa rounds");
+        std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j : rest) { if (o[j].status == 1) ids.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (fast kernel)"); else hw[j] = o[j]; } }
+      if (g_lap) (*g_lap)("wfa d2h"); }
     u64 budget = 0; if (!ids.empty()) { size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); budget = (u64)(freeb * 0.6); }
     u64 slab_words = 1ull << 20;  // 4 MB per warp to start
     for (int round = 0; round < 6 && !ids.empty(); round++) {
@@ -1174,7 +1295,7 @@ struct HostCluster { u32 seg; u32 item; bool rc, variantA; int nseeds, iseq; std
 
 struct lmg_results { std::vector<lmg_hsp> rows; std::string pool; std::vector<u32> row_genome; std::shared_ptr<const std::vector<std::vector<std::string>>> seq_ids; };   // sseqid of row i = (*seq_ids)[row_genome[i]][rows[i].seq_idx]; the host-side id table is shared with the index and outlives lmg_index_close
 
-static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged) {
+static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs, const u64* off, int nq, lmg_results& R, QBatch* staged, std::vector<lmg_pa>* pa_sink = nullptr) {
   cudaStream_t st = ix->st; const Image& I = ix->img; StageTimer T(st); T.mark();
   LapTimer lap; lap.lane = ix->lane_id; const bool dbgt = lap.on; struct LapScope { LapTimer* prev; LapScope(LapTimer* l) : prev(g_lap) { g_lap = l; } ~LapScope() { g_lap = prev; } } lapscope(&lap);
   QBatch Blocal; if (!staged) upload_queries(ix, seqs, off, nq, Blocal); QBatch& B = staged ? *staged : Blocal; nq = B.nq; T.mark();   // [0] h2d (zero when the queries were staged beforehand)
@@ -1251,6 +1372,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     lap("pa_chain+d2h"); bucket_sort(c2, nit, [](const C2Rec& a) { return a.item; }, [](const C2Rec& a, const C2Rec& b) { if (a.qb != b.qb) return a.qb < b.qb; return a.ord < b.ord; });   // lib-seq_compare.go:501-508
   }
   lap("c2 bucket sort"); tkeys.free(); tvals.free(); T.mark();                                                                  // [4] pseudo-align
+  if (pa_sink) { for (const C2Rec& r : c2) { const WinItem& w = items[r.item]; lmg_pa o; o.genome = I.genome_bgi[w.g]; o.query = w.q; o.t_begin = w.tBegin; o.t_end = w.tEnd; o.rc = (i32)w.rc; o.qb = r.qb; o.qe = r.qe; o.tb = r.tb; o.te = r.te; o.aligned_q = r.aligned_q; o.aligned_t = r.aligned_t; o.matched = r.matched; o.n_anchors = r.n_anchors; pa_sink->push_back(o); } T.mark(); finish_times(5); return; }
   if (c2.empty()) { T.mark(); finish_times(5); return; }
   // ---- contig mapping, clusters, jobs (lib-index-search.go:2083-2469) — host, sequential per (query, genome)
   std::vector<HostCluster> clusters; std::vector<HspJob> jobs; const int contigInterval = I.contig_interval;
@@ -1426,6 +1548,11 @@ int lmg_chain_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, con
     for (u32 i = 0; i < C.n; i++) { const ChainRec& r = C.h[i]; lmg_chain& c = o[i]; u64 key = S.h_key[r.seg]; c.query = (u32)(key >> 36); c.genome = ix->img.genome_bgi[(u32)((key >> 2) & 0x3FFFFFFFFull)]; c.score = r.score; c.n_seeds = r.nseeds;
       c.q0 = r.q0; c.t0 = r.t0; c.len0 = r.len0; c.q1 = r.q1; c.t1 = r.t1; c.len1 = r.len1; bool qrc = (r.flags1 >> 1) & 1, trc = r.flags1 & 1; c.rc = (r.nseeds == 1) ? (qrc != trc) : (r.t0 > r.t1); }
     *out = o; *n_out = C.n; return 0; } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int lmg_pseudoalign_batch(lmg_index* ix, const lmg_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, lmg_pa** out, uint64_t* n_out) {
+  try { std::lock_guard<std::mutex> lk(ix->mu); CUDA_CHECK(cudaSetDevice(ix->img.device)); if (ix->img.synth_per) throw std::runtime_error("synthetic seeds-only index"); std::vector<lmg_pa> v; if (n > 0) { ArenaReset ar_(ix); ix->active_lanes = 1; lmg_results R; search_pipeline(ix, p, seqs, off, n, R, nullptr, &v); }
+    lmg_pa* o = (lmg_pa*)malloc(sizeof(lmg_pa) * (v.size() + 1)); if (!v.empty()) memcpy(o, v.data(), sizeof(lmg_pa) * v.size()); *out = o; *n_out = v.size(); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 
 struct lmg_queries { std::vector<QBatch> parts; std::vector<int> cut; };

@@ -25,6 +25,12 @@
 struct SeedEntry { u64 key; u32 vrel; u32 nflag; };   // nflag = number of values | (reversed flag of the key's FIRST value in the whole index) << 31
 static_assert(sizeof(SeedEntry) == 16, "SeedEntry must be 16 bytes");
 
+// Prefix Bloom filter of the seed index: one bit per hashed (mask bucket, leading maskPrefix+anchorPrefix bases of a stored k-mer). A probe can only
+// match keys that share its first p >= maskPrefix+anchorPrefix bases (kv-searcher.go:202,282-304), so "no key of the bucket starts like the probe" is
+// an exact reason to drop it before the index lookup; the anchor table alone (which ignores the mask prefix, kv-data.go:319-325) lets ~30 % of the
+// (query, mask) slots through, most of them with nothing to find.
+__host__ __device__ __forceinline__ u32 pb_hash(u32 bucket, u32 prefix) { u32 h = prefix * 0x9E3779B1u ^ (bucket * 0x85EBCA6Bu); h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13; return h; }
+
 __device__ __forceinline__ u64 ld_be(const u8* __restrict__ p, int n) { u64 v = 0; for (int i = 0; i < n; i++) v = (v << 8) | p[i]; return v; }
 
 struct KvWalk {   // cursor over one mask's record stream
@@ -47,10 +53,10 @@ __global__ void k_kv_count(const u8* __restrict__ d, const u8* __restrict__ x, c
 }
 // fill pass: entries + values of every mask of the chunk
 __global__ void k_kv_fill(const u8* __restrict__ d, const u8* __restrict__ x, const u64* __restrict__ xoff, const u32* __restrict__ xn, int nmasks, int vb, ShardSel S, const u64* __restrict__ bucket_off, const u64* __restrict__ bucket_voff,
-                          SeedEntry* __restrict__ entries, u64* __restrict__ vals) {
+                          SeedEntry* __restrict__ entries, u64* __restrict__ vals, u32* __restrict__ pbloom, u32 pbmask, int ash, int mask0) {
   int m = blockIdx.x * blockDim.x + threadIdx.x; if (m >= nmasks || xn[m] == 0) return;
   const u64 rec0 = ld_be(x + xoff[m] + 8, 8) >> 1; const u64 nk = ld_be(d + rec0 - 8, 8); KvWalk w{d, rec0, 0, nk, vb}; SeedEntry* E = entries + bucket_off[m]; u64* V = vals + bucket_voff[m]; u64 e = 0, v = 0;
-  auto put = [&](u64 key, u64 v0, u64 n) { SeedEntry t; t.key = key; t.vrel = (u32)v; u32 cnt = 0, flag = 0; for (u64 i = 0; i < n; i++) { const u64 val = ld_be(d + v0 + i * vb, vb); if (i == 0) flag = (u32)(val & 1); if (S.keep(val)) { V[v++] = val; cnt++; } } t.nflag = cnt | (flag << 31); E[e++] = t; };
+  auto put = [&](u64 key, u64 v0, u64 n) { SeedEntry t; t.key = key; t.vrel = (u32)v; u32 cnt = 0, flag = 0; for (u64 i = 0; i < n; i++) { const u64 val = ld_be(d + v0 + i * vb, vb); if (i == 0) flag = (u32)(val & 1); if (S.keep(val)) { V[v++] = val; cnt++; } } t.nflag = cnt | (flag << 31); E[e++] = t; const u32 hb = pb_hash((u32)(mask0 + m), (u32)(key >> ash)) & pbmask; atomicOr(&pbloom[hb >> 5], 1u << (hb & 31)); };
   while (w.left) { u64 k1, k2, n1, n2; bool h2; const u64 v0 = w.next(k1, k2, n1, n2, h2); put(k1, v0, n1); if (h2) put(k2, v0 + n1 * (u64)vb, n2); }
 }
 // anchor records of the .idx block -> bucket-relative entry index (the recorded k-mer is the key the scan starts at). One warp per mask.
@@ -65,9 +71,10 @@ __global__ void k_anchor_bits(const u32* __restrict__ anchor_start, u64 n, u32* 
 // by construction), one random value each (reversed flag = bit 0 of a hash)
 __host__ __device__ inline u64 mix64(u64 z) { z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
 __host__ __device__ inline u64 synth_key(u64 mask, int mask_prefix, int k, u64 per, u64 j, u64 seed, u32 bucket) { const int lowbits = 2 * (k - mask_prefix); const u64 span = 1ull << lowbits, stride = span / per; const u64 r = j * stride + mix64(seed ^ ((u64)bucket << 32) ^ j) % stride; return ((mask >> lowbits) << lowbits) | r; }
-__global__ void k_synth_fill(const u64* __restrict__ masks, int m0, int nm, int mask_prefix, int k, u64 per, u64 seed, SeedEntry* __restrict__ entries, u64* __restrict__ vals) {
+__global__ void k_synth_fill(const u64* __restrict__ masks, int m0, int nm, int mask_prefix, int k, u64 per, u64 seed, SeedEntry* __restrict__ entries, u64* __restrict__ vals, u32* __restrict__ pbloom, u32 pbmask, int ash) {
   u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (t >= (u64)nm * per) return; const u32 b = (u32)(t / per); const u64 j = t % per; SeedEntry e; e.key = synth_key(masks[m0 + b], mask_prefix, k, per, j, seed, m0 + b); e.vrel = (u32)j;
-  const u64 v = mix64(seed * 31 + t + ((u64)m0 << 40)); e.nflag = 1u | ((u32)(v & 1) << 31); entries[t] = e; if (vals) vals[t] = v & ~(0x1FFFFull << 47);   // batch bits cleared: genome = bits 30..46 only
+  { const u32 hb = pb_hash((u32)(m0 + b), (u32)(e.key >> ash)) & pbmask; atomicOr(&pbloom[hb >> 5], 1u << (hb & 31)); }
+  const u64 v = mix64(seed * 31 + ((u64)(m0 + b) * per + j)); e.nflag = 1u | ((u32)(v & 1) << 31); entries[t] = e; if (vals) vals[t] = v & ~(0x1FFFFull << 47);   // batch bits cleared: genome = bits 30..46 only
 }
 __global__ void k_synth_anchor(const u64* __restrict__ bucket_off, const SeedEntry* __restrict__ entries, int nm, int sh, u32 NA, u32* __restrict__ anchor_start) {   // thread per (mask, anchor): first entry with that anchor
   u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (t >= (u64)nm * NA) return; const u32 b = (u32)(t / NA), a = (u32)(t % NA); const SeedEntry* E = entries + bucket_off[b]; const u32 n = (u32)(bucket_off[b + 1] - bucket_off[b]); if (!n) { anchor_start[t] = 0xFFFFFFFFu; return; }
@@ -83,6 +90,7 @@ struct Image {
   int mask_lo = 0, mask_hi = 0;   // masks whose buckets this image holds ([0, m) except for mask-range-partitioned synthetic images)
   // device arrays
   u64 *d_masks = nullptr, *d_bucket_off = nullptr, *d_bucket_voff = nullptr, *d_vals = nullptr; SeedEntry* d_entries = nullptr; u32* d_anchor_start = nullptr;
+  u32* d_pbloom = nullptr; u32 pbmask = 0;   // prefix Bloom filter (pb_hash): pbmask + 1 bits, a power of two >= 8 bits per stored k-mer (<= 2^32)
   u32* d_anchor_bits = nullptr;   // m * NA/32 words: bit a of mask i set iff anchor_start[i][a] is present (10 MB, L2-resident filter in front of the 328 MB table)
   u32* d_mask_pstart = nullptr; int mask_pbits = 14;   // masks bucketed by their mask_prefix leading bases: [pstart[p], pstart[p+1])
   u8* d_g2bit = nullptr; u64* d_g_off = nullptr; u32 *d_g_nbases = nullptr, *d_g_seq_off = nullptr, *d_seq_sizes = nullptr; u32* d_batch_base = nullptr;
@@ -98,6 +106,7 @@ struct Image {
   template <class T> T* dalloc(size_t n) { T* d = nullptr; size_t b = std::max<size_t>(n, 1) * sizeof(T) + 64; CUDA_CHECK(cudaMalloc((void**)&d, b)); bytes += b; return d; }
   template <class T> T* up(const std::vector<T>& h) { T* d = dalloc<T>(h.size()); if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); return d; }
 
+  void alloc_pbloom() { u64 bits = 1ull << 20; while (bits < 8 * E && bits < (1ull << 32)) bits <<= 1; pbmask = (u32)(bits - 1); d_pbloom = dalloc<u32>(bits / 32); CUDA_CHECK(cudaMemset(d_pbloom, 0, bits / 8)); }
   void finish_masks() { mask_pbits = 2 * mask_prefix; std::vector<u32> ps(((size_t)1 << mask_pbits) + 1, 0); for (u64 mk : h_masks) ps[(mk >> (2 * k - mask_pbits)) + 1]++; for (size_t i = 0; i + 1 < ps.size(); i++) ps[i + 1] += ps[i]; d_mask_pstart = up(ps); d_masks = up(h_masks); }
   void make_anchor_bits() { const u64 n = (u64)m * NA; d_anchor_bits = dalloc<u32>(n / 32 + 1); k_anchor_bits<<<(unsigned)((n / 32 + 256) / 256), 256>>>(d_anchor_start, n, d_anchor_bits); CUDA_CHECK(cudaGetLastError()); CUDA_CHECK(cudaDeviceSynchronize()); }
 
@@ -152,9 +161,10 @@ struct Image {
     for (int j = 0; j < m; j++) { bucket_off[j + 1] = bucket_off[j] + nk[j]; bucket_voff[j + 1] = bucket_voff[j] + nv[j]; if (nk[j] >= (1ull << 32) || nv[j] >= (1ull << 31)) lmi::die("a mask bucket holds more than 2^32 k-mers or 2^31 values"); }
     E = bucket_off[m]; V = bucket_voff[m]; load_ms[1] = ms_since(t0); t0 = std::chrono::steady_clock::now();
     d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V); d_anchor_start = dalloc<u32>((size_t)m * NA); CUDA_CHECK(cudaMemset(d_anchor_start, 0xff, (size_t)m * NA * 4));
+    alloc_pbloom();
     u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); const int sh = 2 * (k - mask_prefix - anchor_prefix);
     for (int c = 0; c < info.chunks; c++) { ChunkDev cd = keep_raw ? kept[c] : upload_chunk(c); if (cd.nm) {
-        k_kv_fill<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_bucket_off + cd.mask0, d_bucket_voff + cd.mask0, d_entries, d_vals); CUDA_CHECK(cudaGetLastError());
+        k_kv_fill<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_bucket_off + cd.mask0, d_bucket_voff + cd.mask0, d_entries, d_vals, d_pbloom, pbmask, sh, cd.mask0); CUDA_CHECK(cudaGetLastError());
         k_kv_anchor<<<(cd.nm * 32 + 127) / 128, 128>>>(cd.x, cd.xoff, cd.xn, cd.nm, cd.mask0, d_bucket_off, d_entries, sh, (u32)NA, d_anchor_start, d_bad); CUDA_CHECK(cudaGetLastError()); }
       CUDA_CHECK(cudaDeviceSynchronize()); free_chunk(cd); }
     u32 bad = 0; CUDA_CHECK(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad); if (bad) lmi::die("kv-index: " + std::to_string(bad) + " anchor records do not name a stored k-mer");
@@ -170,9 +180,9 @@ struct Image {
     std::sort(h_masks.begin(), h_masks.end()); for (int i = 1; i < m; i++) if (h_masks[i] == h_masks[i - 1]) lmi::die("synthetic masks collide");
     std::vector<u64> bucket_off(m + 1, 0), bucket_voff(m + 1, 0); for (int j = 0; j < m; j++) { const u64 n = (j >= lo && j < hi) ? per : 0; bucket_off[j + 1] = bucket_off[j] + n; bucket_voff[j + 1] = bucket_voff[j] + (with_values ? n : 0); }
     E = bucket_off[m]; V = bucket_voff[m]; finish_masks(); d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V); d_anchor_start = dalloc<u32>((size_t)m * NA); CUDA_CHECK(cudaMemset(d_anchor_start, 0xff, (size_t)m * NA * 4));
-    const int nm = hi - lo; if (nm > 0 && per) { const u64 tot = (u64)nm * per; k_synth_fill<<<(unsigned)((tot + 255) / 256), 256>>>(d_masks, lo, nm, mask_prefix, k, per, seed, d_entries, with_values ? d_vals : nullptr); CUDA_CHECK(cudaGetLastError());
-      const int sh = 2 * (k - mask_prefix - anchor_prefix); const u64 ta = (u64)nm * NA; k_synth_anchor<<<(unsigned)((ta + 255) / 256), 256>>>(d_bucket_off + lo, d_entries, nm, sh, (u32)NA, d_anchor_start + (size_t)lo * NA); CUDA_CHECK(cudaGetLastError()); }
+    alloc_pbloom(); const int sh = 2 * (k - mask_prefix - anchor_prefix);
+    const int nm = hi - lo; if (nm > 0 && per) { const u64 tot = (u64)nm * per; k_synth_fill<<<(unsigned)((tot + 255) / 256), 256>>>(d_masks, lo, nm, mask_prefix, k, per, seed, d_entries, with_values ? d_vals : nullptr, d_pbloom, pbmask, sh); CUDA_CHECK(cudaGetLastError()); const u64 ta = (u64)nm * NA; k_synth_anchor<<<(unsigned)((ta + 255) / 256), 256>>>(d_bucket_off + lo, d_entries, nm, sh, (u32)NA, d_anchor_start + (size_t)lo * NA); CUDA_CHECK(cudaGetLastError()); }
     make_anchor_bits(); batch_base.assign(2, 0); d_batch_base = up(batch_base); std::vector<u64> one(2, 0); d_g_off = up(one); d_g2bit = dalloc<u8>(64);
   }
-  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_start, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits}) if (p) cudaFree(p); }
+  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_start, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits, (void*)d_pbloom}) if (p) cudaFree(p); }
 };

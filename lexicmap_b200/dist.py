@@ -26,6 +26,39 @@ def reduce_counters(rows, bases, step_ms, device=None):
     return float(t[0]), float(t[1]), float(m[0])
 
 
+def shard_hit_counts(rows, n_queries):
+    """per-query number of genomes in ONE shard's rows (the `hits` column is constant over a query's rows): int32[n_queries]"""
+    import numpy as np
+    h = np.zeros(n_queries, np.int32)
+    if len(rows):
+        first = np.r_[True, rows["query"][1:] != rows["query"][:-1]]
+        h[rows["query"][first]] = rows["hits"][first]
+    return h
+
+
+def allreduce_hits(counts, device=None):
+    """the exchange step of a genome-sharded search: SUM over the shards of the per-query genome counts (what `lexicmap utils
+    merge-search-results` computes offline, merge-search-results.go:143-153). NCCL all-reduce of int32[n_queries] when `device` is a CUDA
+    device, gloo in the CPU tests; identity when no process group is initialised. Returns a torch tensor on `device`."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(counts)
+    if device is not None:
+        t = t.to(device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def apply_global_hits(rows, hits):
+    """write the all-reduced genome counts into a shard's rows (TSV column 3)"""
+    import numpy as np
+    h = hits.cpu().numpy() if hasattr(hits, "cpu") else np.asarray(hits)
+    if len(rows):
+        rows["hits"] = h[rows["query"]]
+    return rows
+
+
 def merge_genome_shards(parts):
     """Merge the results of the same query batch searched against the genome shards of one index (`lmg_index_open(..., shard, n_shards)`:
     every shard holds all masks but only the seed values / genomes with dense_id % n_shards == shard; SURVEY.md §8e option 2, the offline

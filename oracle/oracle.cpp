@@ -10,6 +10,7 @@ using namespace lmo;
 extern "C" {
 typedef struct lmo_params { int32_t min_prefix, min_single_prefix, top_n_genomes, top_n_chains; float max_gap, max_distance; int32_t ext_len, ext_len2; double min_qcov_genome, max_evalue;
   int32_t align_max_gap, align_min_len, align_band, output_seq; double min_pident, min_qcov_hsp; int32_t wfa_adaptive, reserved; } lmo_params;
+typedef struct lmo_pa { uint64_t genome; uint32_t query; int32_t t_begin, t_end, rc; int32_t qb, qe, tb, te, aligned_q, aligned_t, matched, n_anchors; } lmo_pa;   // one Chain2Result of SeqComparator.Compare in window coordinates (lib-seq_compare.go:335-522)
 typedef struct lmo_hsp { uint32_t query, hits; uint64_t genome; uint32_t seq_idx, n_seqs, chunk_idx, n_chunks; int32_t seq_len, cls, hsp, qb, qe, tb, te, rc, alen, matches, gaps, score, bitscore, pad0;
   double evalue, qcov_hsp, pident, qcov_gnm; uint64_t cigar_off; uint32_t cigar_len, pad; } lmo_hsp;
 typedef struct lmo_anchor { uint64_t genome; uint32_t query; int32_t qbegin, tbegin; uint8_t len, qrc, trc, pad; } lmo_anchor;
@@ -21,7 +22,7 @@ namespace {
 struct SD { bool rc; double sim; int nseeds; int seq_idx, nseqs, seqlen; std::string seqid; std::vector<Chain2> chains; uint32_t chunk_idx = 0, n_chunks = 1; };
 struct GenomeRes { uint64_t bgi; std::vector<Sub> subs; std::vector<std::vector<int32_t>> chains; float score = 0; std::vector<SD> sds; double af = 0; };
 
-struct StageSink { std::vector<lmo_anchor>* anchors = nullptr; std::vector<lmo_chain>* chains = nullptr; };
+struct StageSink { std::vector<lmo_anchor>* anchors = nullptr; std::vector<lmo_chain>* chains = nullptr; std::vector<lmo_pa>* pas = nullptr; };
 
 // genome.Reader.SubSeq3 genome/genome.go:931-1143 (+ meta parse)
 static GenomeMeta genome_meta(const GenomeBatchFile& b, int idx) {
@@ -89,6 +90,7 @@ static void search_one(const Index& ix, const Params& P, const std::string& qseq
       std::string tseq = subseq3(gb, refID, gm, tBegin, tEnd); if ((int)tseq.size() < tEnd - tBegin + 1) tEnd -= tEnd - tBegin + 1 - (int)tseq.size();
       if (rc) rc_inplace(tseq);
       std::vector<Chain2> crChains = compare(T, (uint32_t)qBegin, (uint32_t)qEnd, tseq, c2, 11); if (crChains.empty()) continue;
+      if (sink && sink->pas) for (const Chain2& c : crChains) sink->pas->push_back({r.bgi, qidx, tBegin, tEnd, (int32_t)rc, c.qb, c.qe, c.tb, c.te, c.aligned_q, c.aligned_t, c.matched, c.n_anchors});
       iSeqPre = -1; std::vector<Chain2> cur; const int tlenSeq = (int)tseq.size();
       auto flush = [&](std::vector<Chain2>& chains2, bool variantA, int iSeqUse) {
         bool hasResult = false; double maxSim = 0;
@@ -232,9 +234,10 @@ int lmo_mask_batch(void* hh, const uint8_t* seqs, const uint64_t* off, int32_t n
   *n_suf = ns_; return 0;
 }
 static void* stage(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, int which, uint64_t* n_out) {
-  Handle* h = (Handle*)hh; Params P = to_params(p); auto* A = new std::vector<lmo_anchor>; auto* C = new std::vector<lmo_chain>; StageSink sk; sk.anchors = A; sk.chains = C; std::vector<GenomeRes> res;
+  Handle* h = (Handle*)hh; Params P = to_params(p); auto* A = new std::vector<lmo_anchor>; auto* C = new std::vector<lmo_chain>; std::vector<lmo_pa> PA; StageSink sk; sk.anchors = A; sk.chains = C; if (which == 2) sk.pas = &PA; std::vector<GenomeRes> res;
   // for the chain stage the downstream stages are irrelevant but harmless
   for (int q = 0; q < n; q++) search_one(h->ix, P, std::string((const char*)seqs + off[q], off[q + 1] - off[q]), q, res, &sk);
+  if (which == 2) { *n_out = PA.size(); void* out = malloc(PA.size() * sizeof(lmo_pa) + 1); memcpy(out, PA.data(), PA.size() * sizeof(lmo_pa)); delete A; delete C; return out; }
   if (which == 0) { std::sort(A->begin(), A->end(), [](const lmo_anchor& a, const lmo_anchor& b) { if (a.query != b.query) return a.query < b.query; if (a.genome != b.genome) return a.genome < b.genome; if (a.qbegin != b.qbegin) return a.qbegin < b.qbegin;
       if (a.len != b.len) return a.len > b.len; if (a.tbegin != b.tbegin) return a.tbegin < b.tbegin; if (a.qrc != b.qrc) return a.qrc < b.qrc; return a.trc < b.trc; });
     *n_out = A->size(); void* out = malloc(A->size() * sizeof(lmo_anchor) + 1); memcpy(out, A->data(), A->size() * sizeof(lmo_anchor)); delete A; delete C; return out; }
@@ -243,6 +246,7 @@ static void* stage(void* hh, const lmo_params* p, const uint8_t* seqs, const uin
 }
 void* lmo_anchor_batch(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* n_out) { try { return stage(hh, p, seqs, off, n, 0, n_out); } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
 void* lmo_chain_batch(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* n_out) { try { return stage(hh, p, seqs, off, n, 1, n_out); } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
+void* lmo_pseudoalign_batch(void* hh, const lmo_params* p, const uint8_t* seqs, const uint64_t* off, int32_t n, uint64_t* n_out) { try { return stage(hh, p, seqs, off, n, 2, n_out); } catch (std::exception& e) { g_err = e.what(); return nullptr; } }
 // WFA on pairs: off[2n+1]; returns '\n'-joined CIGARs in wfa convention (not swapped), untrimmed
 char* lmo_wfa_batch(const uint8_t* seqs, const uint64_t* off, int32_t n, int32_t adaptive, uint64_t* out_len) {
   std::string o; for (int i = 0; i < n; i++) { WfaResult w = wfa_align((const char*)seqs + off[2 * i], (int)(off[2 * i + 1] - off[2 * i]), (const char*)seqs + off[2 * i + 1], (int)(off[2 * i + 2] - off[2 * i + 1]), adaptive);

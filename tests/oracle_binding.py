@@ -27,6 +27,9 @@ HSP_DTYPE = np.dtype([("query", "<u4"), ("hits", "<u4"), ("genome", "<u8"), ("se
 ANCHOR_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("qbegin", "<i4"), ("tbegin", "<i4"), ("len", "u1"), ("qrc", "u1"), ("trc", "u1"), ("pad", "u1")])
 CHAIN_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("score", "<f4"), ("n_seeds", "<i4"), ("q0", "<i4"), ("t0", "<i4"), ("len0", "<i4"),
                         ("q1", "<i4"), ("t1", "<i4"), ("len1", "<i4"), ("rc", "<i4")])
+PA_DTYPE = np.dtype([("genome", "<u8"), ("query", "<u4"), ("t_begin", "<i4"), ("t_end", "<i4"), ("rc", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("tb", "<i4"), ("te", "<i4"),
+                     ("aligned_q", "<i4"), ("aligned_t", "<i4"), ("matched", "<i4"), ("n_anchors", "<i4")])
+assert PA_DTYPE.itemsize == 56
 assert HSP_DTYPE.itemsize == 136 and ANCHOR_DTYPE.itemsize == 24 and CHAIN_DTYPE.itemsize == 48
 
 
@@ -79,7 +82,7 @@ class Oracle:
         L.lmo_row_seqid.argtypes = [C.c_void_p, C.c_uint64]
         L.lmo_rows_free.argtypes = [C.c_void_p]
         L.lmo_mask_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
-        for f in (L.lmo_anchor_batch, L.lmo_chain_batch):
+        for f in (L.lmo_anchor_batch, L.lmo_chain_batch, L.lmo_pseudoalign_batch):
             f.restype = C.c_void_p
             f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
         L.lmo_wfa_batch.restype = C.c_void_p
@@ -162,6 +165,9 @@ class Oracle:
 
     def chains(self, seqs, params=None):
         return self._stage(self.lib.lmo_chain_batch, CHAIN_DTYPE, seqs, params)
+
+    def pseudoalign(self, seqs, params=None):
+        return self._stage(self.lib.lmo_pseudoalign_batch, PA_DTYPE, seqs, params)
 
     def wfa(self, pairs, adaptive=1):
         flat = []

@@ -52,6 +52,15 @@ def test_chains_top_n(gpu_small, oracle_small, small_queries):
     assert gc.tobytes() == oc.tobytes()
 
 
+def test_pseudoalignment_matches_oracle(gpu_small, oracle_small, small_queries):
+    """a9-a12 stage-wise: target windows of the chains, SeqComparator.Compare anchors, ClearSubstrPairs / TrimSubStrPairs, Chainer2 regions"""
+    ids, seqs = small_queries
+    for kw in (dict(), dict(top_n_chains=1, align_min_len=80, align_max_gap=10)):
+        ga = np.sort(gpu_small.pseudoalign(seqs, gpu_small.default_params(**kw)), order=["query", "genome", "t_begin", "t_end", "rc", "qb", "qe", "tb", "te", "aligned_q", "aligned_t", "matched", "n_anchors"])
+        oa = np.sort(oracle_small.pseudoalign(seqs, oracle_small.default_params(**kw)), order=["query", "genome", "t_begin", "t_end", "rc", "qb", "qe", "tb", "te", "aligned_q", "aligned_t", "matched", "n_anchors"])
+        assert len(oa) > 50 and ga.tobytes() == oa.tobytes()
+
+
 def _rows_equal(gr, orr, gs, os_, gc=None, oc=None):
     assert len(gr) == len(orr), "row count differs: gpu %d oracle %d" % (len(gr), len(orr))
     for f in gr.dtype.names:
