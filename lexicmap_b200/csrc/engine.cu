@@ -654,13 +654,14 @@ __device__ __forceinline__ void pa3_emit(const u64* sk, const u32* sv, u32 e, u6
 template <int NT>   // threads per CTA: 256, or 1024 when the table leaves room for a single CTA per SM anyway (5-kb queries)
 __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
                                                      const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn) {
-  __shared__ u32 s_base; __shared__ u32 bloom[1024]; __shared__ u32 pdir[257];   // bloom: 32768 bits over hashed 11-base prefixes; pdir: first table row of every 4-base prefix
+  constexpr int BW = NT >= 1024 ? 4096 : 1024, BSH = NT >= 1024 ? 15 : 17;   // Bloom filter over hashed 11-base prefixes: 32 kbit for tables of up to ~4,000 rows, 128 kbit for the big-table variant (a 10,000-row table filled 26 % of 32 kbit)
+  __shared__ u32 s_base; __shared__ u32 bloom[BW]; __shared__ u32 pdir[257];   // pdir: first table row of every 4-base prefix
   extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
   const u32 q = qlist[blockIdx.x]; const u32 t0q = toff[q], tn = toff[q + 1] - t0q; const int K = 31;
-  for (u32 i = threadIdx.x; i < 1024; i += NT) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += NT) pdir[i] = tn;
+  for (u32 i = threadIdx.x; i < (u32)BW; i += NT) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += NT) pdir[i] = tn;
   for (u32 i = threadIdx.x; i < tn; i += NT) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
   __syncthreads();
-  for (u32 i = threadIdx.x; i < tn; i += NT) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> 17; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
+  for (u32 i = threadIdx.x; i < tn; i += NT) { u64 kk = sk[i]; u32 h = ((u32)(kk >> 40) * 2654435761u) >> BSH; atomicOr(&bloom[h >> 5], 1u << (h & 31)); u32 b = (u32)(kk >> 54); if (i == 0 || (u32)(sk[i - 1] >> 54) != b) pdir[b] = i; }
   __syncthreads();
   if (threadIdx.x == 0) { u32 nxt = tn; for (int b = 255; b >= 0; b--) { if (pdir[b] == tn) pdir[b] = nxt; else nxt = pdir[b]; } pdir[256] = tn; }   // empty buckets -> start of the next one
   const u64 ccc = 0x1555555555555555ull, ggg = 0x2AAAAAAAAAAAAAAAull, ttt = 0x3FFFFFFFFFFFFFFFull; const int lane = threadIdx.x & 31;
@@ -680,8 +681,8 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
       if (more) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
         if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
           if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
-            u32 hb = ((u32)(km >> 40) * 2654435761u) >> 17; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
-            hb = ((u32)(kr >> 40) * 2654435761u) >> 17; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
+            u32 hb = ((u32)(km >> 40) * 2654435761u) >> BSH; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
+            hb = ((u32)(kr >> 40) * 2654435761u) >> BSH; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
         pa3_push(qfast, &nfast, c1, (u32)idx << 1, lane); pa3_push(qfast, &nfast, c2, ((u32)idx << 1) | 1u, lane); }
       // drain: full chunks of 256 candidates while scanning, everything at the end. Every thread reads the counters between two barriers.
       for (;;) {
@@ -1139,75 +1140,95 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
 #define WR_WARPS 8
 #define WR_SEQW 144
 #define WR_SMEM_BYTES ((size_t)WR_WARPS * WR_SEQW * 8)
-__device__ __forceinline__ i32 wr_window_base(i32 kend) { return (kend >= 0 ? kend / 2 : -((-kend + 1) / 2)) - 16; }   // window [kb, kb+31] centred between diagonal 0 and kend
-__global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, u32 job0, u32 njobs, u32* __restrict__ next_job,
-                                                         u32* __restrict__ slabs, WfaOut* __restrict__ outs, int adaptive, int lmax) {
+#define WR_MAXLEN (1 << 20)      // offsets are stored in 20 bits of the backtrace word
+#define WR_W 64                  // diagonals in the window: two per lane (lane l holds kb + l and kb + 32 + l)
+// The 64-diagonal window follows the band: kb moves (registers shifted by warp shuffles) whenever the range of the new level or of one of the four
+// levels it reads from would touch the window's edge diagonals; the alignment falls back to k_wfa_fast / k_wfa only when that span itself exceeds
+// 62 diagonals. Bands of up to 30 diagonals (<= ~12 % divergence) live in the first slot only and the second slot's work is skipped (warp-uniform
+// branch). Diagonal kb never holds a live cell: its slab word stores kb of the level for the backtrace. This is what lets long, indel-rich
+// alignments (ONT reads: |tlen - plen| of hundreds, tens of thousands of levels) stay on the register path.
+struct WrCell { i32 om, oi, od, dv; u32 word; };
+__global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, const u32* __restrict__ job_ids, u32 job0, u32 njobs, u32* __restrict__ next_job,
+                                                         u32* __restrict__ slabs, const u64* __restrict__ slab_off, WfaOut* __restrict__ outs, int adaptive) {
   extern __shared__ __align__(16) u8 wr_smem[];
-  const int X2 = 2, OE2 = 4, E2 = 1; const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wr_smem + (size_t)wib * WR_SEQW;
+  const int X2 = 2, OE2 = 4, E2 = 1; const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wr_smem + (size_t)wib * WR_SEQW; const int lm1 = (lane + 31) & 31, lp1 = (lane + 1) & 31;
   for (;;) {
-    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job0 + jr; u32* slab = slabs + (u64)jr * lmax * 32;
+    u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job_ids ? job_ids[job0 + jr] : job0 + jr;
+    u32* slab = slabs + slab_off[jr] * WR_W; const i32 lmax = (i32)(slab_off[jr + 1] - slab_off[jr]);   // levels this alignment may use
     ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
     const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
     { const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
       if (nqw + nA + ntw <= WR_SEQW) { u64* sq = seqb; for (u32 i = lane; i < nqw + nA; i += 32) sq[i] = Q[i]; for (u32 i = lane; i < ntw; i += 32) sq[nqw + nA + i] = T[i]; __syncwarp(); Q = sq; A = sq + nqw; T = sq + nqw + nA; } }
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
-    const i32 kb = wr_window_base(kend), k = kb + lane;
-    if (plen >= 32000 || tlen >= 32000 || plen <= 0 || tlen <= 0 || 0 < kb + 2 || 0 > kb + 29 || kend < kb + 2 || kend > kb + 29) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    if (plen >= WR_MAXLEN || tlen >= WR_MAXLEN || plen <= 0 || tlen <= 0 || lmax < 2) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
     auto extend = [&](i32 kk, i32 h) { i32 v = h - kk; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
+    // one cell: recurrences + extension + the backtrace word (decisions from the unfiltered neighbour values: offset first, then mismatch(9) > D-ext(6) > D-open(5) > I-ext(2) > I-open(1))
+    auto cell = [&](i32 k, bool live, i32 c_m2, i32 m4l, i32 i1l, i32 m4r, i32 d1r) { WrCell c; c.om = -1; c.oi = -1; c.od = -1; c.dv = INT32_MAX; c.word = 0;
+      if (live) { i32 ins = max(m4l, i1l); ins = (ins < 0) ? -1 : ins + 1; i32 del = max(m4r, d1r); i32 mis = (c_m2 < 0) ? -1 : c_m2 + 1;
+        const i32 hmax = min(tlen, plen + k); if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
+        i32 mm = max(mis, max(ins, del)); if (mm >= 0) { c.om = extend(k, mm); c.dv = max(plen - (c.om - k), tlen - c.om); } c.oi = ins; c.od = del;
+        i32 best = -1; if (c_m2 >= 0) best = ((c_m2 + 1) << 4) | 9; if (m4l >= 0) best = max(best, ((m4l + 1) << 4) | 1); if (i1l >= 0) best = max(best, ((i1l + 1) << 4) | 2); if (m4r >= 0) best = max(best, (m4r << 4) | 5); if (d1r >= 0) best = max(best, (d1r << 4) | 6);
+        if (best >= 0) c.word = (u32)(best >> 4) | ((u32)(best & 15) << 20);
+        if (i1l >= 0 && i1l >= m4l) c.word |= 1u << 24; if (d1r >= 0 && d1r >= m4r) c.word |= 1u << 25; if (m4l < 0 && i1l < 0) c.word |= 1u << 26; if (m4r < 0 && d1r < 0) c.word |= 1u << 27; }   // bits 26/27: no source for the I / D state (backtrace error as in k_wfa_bt)
+      return c; };
     i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
-    i32 m1 = -1, m2 = -1, m3 = -1, m4 = -1, i1 = -1, d1 = -1;   // M of levels L-1..L-4, I and D of level L-1 on this lane's diagonal; -1 = null
-    if (k == 0) m1 = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = 0;
-    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = __shfl_sync(FULLMASK, m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }
+    i32 kb = -16;   // diagonal 0 on lane 16 of slot 0
+    i32 m1a = -1, m2a = -1, m3a = -1, m4a = -1, i1a = -1, d1a = -1, m1b = -1, m2b = -1, m3b = -1, m4b = -1, i1b = -1, d1b = -1;   // slot a: diagonal kb + lane, slot b: kb + 32 + lane; M of levels L-1..L-4, I / D of level L-1; -1 = null
+    if (kb + lane == 0) m1a = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = lane == 0 ? (u32)kb : 0u;
+    auto at = [&](i32 va, i32 vb, i32 j) { const i32 x = __shfl_sync(FULLMASK, va, j & 31), y = __shfl_sync(FULLMASK, vb, j & 31); return (j >> 5) ? y : x; };   // value on window position j (0..63), warp-uniform j
+    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = at(m1a, m1b, 0 - kb); done = (kend == 0 && v0 >= tlen); }
     while (!done) {
       L++; if (L >= lmax) { overflow = true; break; }
       const bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; const bool allnull = nx && no && ni && nd;
       if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
-      if (!allnull && (lo < kb + 1 || hi > kb + 30)) { overflow = true; break; }   // lanes 0 and 31 stay null: every k-1 / k+1 neighbour of a live cell is inside the window
-      // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab)
-      i32 m4l = __shfl_up_sync(FULLMASK, m4, 1), i1l = __shfl_up_sync(FULLMASK, i1, 1), m4r = __shfl_down_sync(FULLMASK, m4, 1), d1r = __shfl_down_sync(FULLMASK, d1, 1);
-      if (lane == 0) { m4l = -1; i1l = -1; } if (lane == 31) { m4r = -1; d1r = -1; }
-      i32 om = -1, oi = -1, od = -1, dv = INT32_MAX; u32 cell = 0;
-      if (!allnull && k >= lo && k <= hi) {
-        i32 ins = max(m4l, i1l); ins = (ins < 0) ? -1 : ins + 1; i32 del = max(m4r, d1r); i32 mis = (m2 < 0) ? -1 : m2 + 1;
-        const i32 hmax = min(tlen, plen + k); if (ins > hmax) ins = -1; if (del > hmax || del - k < 0) del = -1; if (mis > hmax) mis = -1;
-        i32 mm = max(mis, max(ins, del)); if (mm >= 0) { om = extend(k, mm); dv = max(plen - (om - k), tlen - om); } oi = ins; od = del;
-        // backtrace decisions, from the unfiltered values: offset first, then mismatch(9) > D-ext(6) > D-open(5) > I-ext(2) > I-open(1)
-        i32 best = -1; if (m2 >= 0) best = ((m2 + 1) << 4) | 9; if (m4l >= 0) best = max(best, ((m4l + 1) << 4) | 1); if (i1l >= 0) best = max(best, ((i1l + 1) << 4) | 2); if (m4r >= 0) best = max(best, (m4r << 4) | 5); if (d1r >= 0) best = max(best, (d1r << 4) | 6);
-        if (best >= 0) cell = (u32)(best >> 4) | ((u32)(best & 15) << 15);
-        if (i1l >= 0 && i1l >= m4l) cell |= 1u << 19; if (d1r >= 0 && d1r >= m4r) cell |= 1u << 20; if (m4l < 0 && i1l < 0) cell |= 1u << 21; if (m4r < 0 && d1r < 0) cell |= 1u << 22;   // bits 21/22: no source for the I / D state (backtrace error as in k_wfa_bt)
-      }
-      bool anyM = __any_sync(FULLMASK, om >= 0), anyI = __any_sync(FULLMASK, oi >= 0), anyD = __any_sync(FULLMASK, od >= 0);
+      { // the window must hold this level's range and the ranges of the levels still in registers on positions 1..62 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
+        i32 slo = allnull ? INT32_MAX : lo, shi = allnull ? INT32_MIN : hi; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { slo = min(slo, hlo[i]); shi = max(shi, hhi[i]); }
+        const i32 span = shi - slo + 1;
+        if (slo <= shi && (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30))) { if (span > WR_W - 2) { overflow = true; break; }
+          const i32 nkb = (span <= 30) ? slo - 1 - (30 - span) / 2 : slo - 1 - (WR_W - 2 - span) / 2, dlt = nkb - kb;   // narrow bands are centred in slot a, so that slot b stays idle
+          auto shift = [&](i32& va, i32& vb) { const i32 ja = lane + dlt, jb2 = lane + 32 + dlt; const i32 xa = __shfl_sync(FULLMASK, va, ja & 31), ya = __shfl_sync(FULLMASK, vb, ja & 31), xb = __shfl_sync(FULLMASK, va, jb2 & 31), yb = __shfl_sync(FULLMASK, vb, jb2 & 31);
+            va = (ja < 0 || ja > 63) ? -1 : ((ja >> 5) ? ya : xa); vb = (jb2 < 0 || jb2 > 63) ? -1 : ((jb2 >> 5) ? yb : xb); };
+          shift(m1a, m1b); shift(m2a, m2b); shift(m3a, m3b); shift(m4a, m4b); shift(i1a, i1b); shift(d1a, d1b); kb = nkb; } }
+      const i32 ka = kb + lane, kbb = kb + 32 + lane; const bool useB = !allnull && hi >= kb + 32, useA = !allnull && lo <= kb + 31;
+      WrCell ca, cb; ca.om = ca.oi = ca.od = -1; ca.dv = INT32_MAX; ca.word = 0; cb = ca;
+      if (useA || useB) {   // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab); position 31 | 32 is the seam between the slots
+        const i32 r0 = __shfl_sync(FULLMASK, m4a, lm1), r1 = __shfl_sync(FULLMASK, m4b, lm1), s0 = __shfl_sync(FULLMASK, i1a, lm1), s1 = __shfl_sync(FULLMASK, i1b, lm1);
+        const i32 t0 = __shfl_sync(FULLMASK, m4a, lp1), t1 = __shfl_sync(FULLMASK, m4b, lp1), u0 = __shfl_sync(FULLMASK, d1a, lp1), u1 = __shfl_sync(FULLMASK, d1b, lp1);
+        if (useA) ca = cell(ka, ka >= lo && ka <= hi, m2a, lane ? r0 : -1, lane ? s0 : -1, lane < 31 ? t0 : t1, lane < 31 ? u0 : u1);
+        if (useB) cb = cell(kbb, kbb >= lo && kbb <= hi, m2b, lane ? r1 : r0, lane ? s1 : s0, lane < 31 ? t1 : -1, lane < 31 ? u1 : -1); }
+      bool anyM = __any_sync(FULLMASK, ca.om >= 0 || cb.om >= 0), anyI = __any_sync(FULLMASK, ca.oi >= 0 || cb.oi >= 0), anyD = __any_sync(FULLMASK, ca.od >= 0 || cb.od >= 0);
       if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa / k_wfa_fast / the oracle
-        i32 mind = dv; for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50; const bool ok = (om >= 0) && dv <= thr;   // distances of null cells are +inf
-        const i32 top_limit = min(kend, hi); i32 nlo = lo; { u32 bal = __ballot_sync(FULLMASK, ok && k >= lo && k < top_limit); if (bal) nlo = kb + __ffs(bal) - 1; else if (top_limit > lo) nlo = top_limit; }
-        const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; { u32 bal = __ballot_sync(FULLMASK, ok && k <= hi && k > bottom_limit); if (bal) nhi = kb + 31 - __clz(bal); else if (hi > bottom_limit) nhi = bottom_limit; }
-        if (nlo != lo || nhi != hi) { if (k < nlo || k > nhi) { om = -1; oi = -1; od = -1; } anyM = __any_sync(FULLMASK, om >= 0); anyI = __any_sync(FULLMASK, oi >= 0); anyD = __any_sync(FULLMASK, od >= 0); lo = nlo; hi = nhi; }
+        i32 mind = min(ca.dv, cb.dv); for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50; const bool oka = (ca.om >= 0) && ca.dv <= thr, okb = (cb.om >= 0) && cb.dv <= thr;   // distances of null cells are +inf
+        const i32 top_limit = min(kend, hi); i32 nlo = lo; { const u32 ba = __ballot_sync(FULLMASK, oka && ka >= lo && ka < top_limit), bb = __ballot_sync(FULLMASK, okb && kbb >= lo && kbb < top_limit); if (ba) nlo = kb + __ffs(ba) - 1; else if (bb) nlo = kb + 32 + __ffs(bb) - 1; else if (top_limit > lo) nlo = top_limit; }
+        const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; { const u32 ba = __ballot_sync(FULLMASK, oka && ka <= hi && ka > bottom_limit), bb = __ballot_sync(FULLMASK, okb && kbb <= hi && kbb > bottom_limit); if (bb) nhi = kb + 63 - __clz(bb); else if (ba) nhi = kb + 31 - __clz(ba); else if (hi > bottom_limit) nhi = bottom_limit; }
+        if (nlo != lo || nhi != hi) { if (ka < nlo || ka > nhi) { ca.om = -1; ca.oi = -1; ca.od = -1; } if (kbb < nlo || kbb > nhi) { cb.om = -1; cb.oi = -1; cb.od = -1; }
+          anyM = __any_sync(FULLMASK, ca.om >= 0 || cb.om >= 0); anyI = __any_sync(FULLMASK, ca.oi >= 0 || cb.oi >= 0); anyD = __any_sync(FULLMASK, ca.od >= 0 || cb.od >= 0); lo = nlo; hi = nhi; }
       }
-      slab[(u64)L * 32 + lane] = cell;
-      m4 = m3; m3 = m2; m2 = m1; m1 = om; i1 = oi; d1 = od;
+      { u32* row = slab + (u64)L * WR_W; row[lane] = lane == 0 ? (u32)kb : ca.word; if (useB) row[32 + lane] = cb.word; }
+      m4a = m3a; m3a = m2a; m2a = m1a; m1a = ca.om; i1a = ca.oi; d1a = ca.od; m4b = m3b; m3b = m2b; m2b = m1b; m1b = cb.om; i1b = cb.oi; d1b = cb.od;
       for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
-      if (!allnull && kend >= lo && kend <= hi) { const i32 v = __shfl_sync(FULLMASK, m1, kend - kb); done = (v >= tlen); }
+      if (!allnull && kend >= lo && kend <= hi) { const i32 v = at(m1a, m1b, kend - kb); done = (v >= tlen); }
     }
     if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = 2 * L; outs[jb] = Rz; }
     __syncwarp();
   }
 }
-// backtrace of the register path, one thread per alignment: one word per step
-__global__ void __launch_bounds__(128) k_wfa_bt2(const ExtOut* __restrict__ ext, u32 job0, u32 njobs, const u32* __restrict__ slabs, u64* __restrict__ ops_scratch, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int lmax) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
-  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen, kb = wr_window_base(kend); const u32* slab = slabs + (u64)t * lmax * 32; u64* ops = ops_scratch + (u64)t * WF_OPSMAX;
+// backtrace of the register path, one thread per alignment: two words of one 128-byte line per step (the level's window base and the cell)
+__global__ void __launch_bounds__(128) k_wfa_bt2(const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 job0, u32 njobs, const u32* __restrict__ slabs, const u64* __restrict__ slab_off, u64* __restrict__ ops_scratch, const u64* __restrict__ ops_off, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job_ids ? job_ids[job0 + t] : job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
+  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32* slab = slabs + slab_off[t] * WR_W; u64* ops = ops_scratch + (want_ops ? ops_off[t] : 0); const u32 ops_max = want_ops ? (u32)(ops_off[t + 1] - ops_off[t]) : 0;
   i32 k = kend, off = tlen, lv = Rr.wscore / 2; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
-  auto flush = [&]() { if (want_ops && curn) { if (nops < WF_OPSMAX) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
+  auto flush = [&]() { if (want_ops && curn) { if (nops < ops_max) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
   auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
     if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
     else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
   while (vv > 0 && h > 0 && lv > 0) {
-    const u32 cell = slab[(u64)lv * 32 + (u32)(k - kb)]; int type;
-    if (mat == 0) { type = (int)((cell >> 15) & 15); if (type == 0) { Rr.status = 2; break; } const i32 mo = (i32)(cell & 0x7FFF); put('M', off - mo, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
-    else if (mat == 1) { if ((cell >> 21) & 1) { Rr.status = 2; break; } type = ((cell >> 19) & 1) ? 2 : 1; }
-    else { if ((cell >> 22) & 1) { Rr.status = 2; break; } type = ((cell >> 20) & 1) ? 6 : 5; }
+    const u32* row = slab + (u64)lv * WR_W; const i32 kb = (i32)row[0]; const u32 li = (u32)(k - kb); if (li - 1u > (u32)(WR_W - 3)) { Rr.status = 2; break; } const u32 cell = row[li]; int type;
+    if (mat == 0) { type = (int)((cell >> 20) & 15); if (type == 0) { Rr.status = 2; break; } const i32 mo = (i32)(cell & 0xFFFFF); put('M', off - mo, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
+    else if (mat == 1) { if ((cell >> 26) & 1) { Rr.status = 2; break; } type = ((cell >> 24) & 1) ? 2 : 1; }
+    else { if ((cell >> 27) & 1) { Rr.status = 2; break; } type = ((cell >> 25) & 1) ? 6 : 5; }
     switch (type) { case 9: lv -= X2_LV; mat = 0; put('X', 1, off - k, off); off--; break;
       case 1: lv -= OE2_LV; mat = 0; put('I', 1, off - k, off); k--; off--; break; case 2: lv -= E2_LV; mat = 1; put('I', 1, off - k, off); k--; off--; break;
       case 5: lv -= OE2_LV; mat = 0; put('D', 1, off - k, off); k++; break; case 6: lv -= E2_LV; mat = 2; put('D', 1, off - k, off); k++; break; default: Rr.status = 2; break; }
@@ -1239,15 +1260,23 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       // pass 1, every job: the register kernel (one diagonal per lane, 128 B of backtrace words per level). Rounds only when the slabs of all jobs exceed the budget.
       std::vector<u32> rest;   // jobs whose band left the 32-lane window (or too deep / too long): pass 2
       static const bool use_reg = getenv("LMG_NO_WFA_REG") == nullptr;
-      if (use_reg) { const u64 per_job = (u64)lmax * 32 * 4 + (want_ops ? (u64)WF_OPSMAX * 8 : 0); const u32 nwarpsR = (u32)sm_count * 8 * WR_WARPS;
-        u32 per_round = (u32)std::min<u64>(nj, std::max<u64>(nwarpsR, budgetF / per_job)); if (g_arena == nullptr) per_round = std::min<u32>(per_round, 8192);
-        DBuf<u32> rslabs((u64)per_round * lmax * 32, st); DBuf<u64> oscr(want_ops ? (u64)per_round * WF_OPSMAX : 8, st); DBuf<u32> next(1, st);
+      if (use_reg) {   // per-job slabs: levels for ~40 % divergence of THIS alignment (0.8 x its longer side), op runs up to its length; rounds fill the HBM budget
+        auto lv_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return (u64)std::max<i64>(256, ((i64)(0.8 * (double)len) + 63) / 64 * 64); };
+        auto op_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return want_ops ? (u64)std::max<i64>(1024, len + 64) : 0ull; };
+        std::vector<u64> hso, hoo; std::vector<u32> skipped; u32 rounds = 0, round_max = 0;
         { KTimer kt(st, &ms[11]);
-          for (u32 j0 = 0; j0 < nj; j0 += per_round) { u32 n = std::min(per_round, nj - j0); next.zero(); u32 blocks = (u32)std::min<u64>((u64)sm_count * 8, (n + WR_WARPS - 1) / WR_WARPS);
-            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, j0, n, next.p, rslabs.p, d_out.p, adaptive, lmax); KERNEL_CHECK();
-            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, j0, n, rslabs.p, oscr.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, lmax); KERNEL_CHECK(); } }
-        std::vector<WfaOut> o = d_out.to_host(nj); for (u32 j = 0; j < nj; j++) { if (o[j].status == 1) rest.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
-        counters[14] = per_round; if (g_lap) (*g_lap)("wfa register pass"); }
+          for (u32 j0 = 0; j0 < nj;) { hso.assign(1, 0); hoo.assign(1, 0); u64 bytes = 0; u32 n = 0;
+            while (j0 + n < nj) { const u64 lv = lv_cap(j0 + n), oc = op_cap(j0 + n), b = lv * WR_W * 4 + oc * 8; if (n > 0 && (bytes + b > budgetF || (g_arena == nullptr && n >= 8192))) break; if (n == 0 && b > budgetF) { skipped.push_back(j0); j0++; continue; } hso.push_back(hso.back() + lv); hoo.push_back(hoo.back() + oc); bytes += b; n++; }
+            if (n == 0) continue;
+            DBuf<u64> soff(n + 1, st), ooff(n + 1, st); soff.from_host(hso.data(), n + 1); ooff.from_host(hoo.data(), n + 1); DBuf<u32> rslabs(hso.back() * WR_W + 64, st); DBuf<u64> oscr(hoo.back() + 8, st); DBuf<u32> next(1, st); next.zero();
+            const u32 blocks = (u32)std::min<u64>((u64)sm_count * 8, (n + WR_WARPS - 1) / WR_WARPS);
+            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, nullptr, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive); KERNEL_CHECK();
+            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, nullptr, j0, n, rslabs.p, soff.p, oscr.p, ooff.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+            CUDA_CHECK(cudaStreamSynchronize(st));   // the round's buffers go back to the arena
+            j0 += n; rounds++; round_max = std::max(round_max, n); } }
+        std::vector<WfaOut> o = d_out.to_host(nj); std::vector<char> sk(nj, 0); for (u32 j : skipped) sk[j] = 1;
+        for (u32 j = 0; j < nj; j++) { if (sk[j] || o[j].status == 1) rest.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
+        counters[14] = round_max; (void)rounds; if (g_lap) (*g_lap)("wfa register pass"); }
       else { rest.resize(nj); std::iota(rest.begin(), rest.end(), 0u); }
       counters[9] = nj; counters[10] = rest.size(); counters[15] = (u64)lmax;
       // pass 2, the jobs left: shared-memory-ring kernel (bands up to 256 diagonals), per-alignment slabs of 3 x u16 per cell in rounds bounded by the HBM budget
@@ -1323,7 +1352,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<u32> htoff = toff.to_host(B.nq + 1); std::vector<u64> hhoff(B.nq + 1, 0); for (int q = 0; q < B.nq; q++) { u32 n = htoff[q + 1] - htoff[q]; u64 H = 0; if (n) { H = 16; while (H < 2ull * n) H <<= 1; } hhoff[q + 1] = hhoff[q] + H; }
   // queries -> item ranges (items are ordered by (query, genome)); per-query kernel when table + window fit in shared memory
   std::vector<u32> qbeg(B.nq, 0), qend(B.nq, 0), qlist, rest; { u32 i = 0; while (i < nit) { u32 q = items[i].q, j = i; while (j < nit && items[j].q == q) j++; qbeg[q] = i; qend[q] = j; i = j; } }
-  u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 36 * 1024, 190 * 1024);   // dynamic part; the 1,024-thread variant has 33 KB of static queues
+  u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 48 * 1024, 178 * 1024);   // dynamic part; the 1,024-thread variant has 46 KB of static queues + Bloom filter
   for (int q = 0; q < B.nq; q++) if (qend[q] > qbeg[q]) { u32 tn = htoff[q + 1] - htoff[q]; i32 mw = 0; for (u32 i = qbeg[q]; i < qend[q]; i++) mw = std::max(mw, items[i].W); size_t need = (size_t)tn * 12 + ((size_t)(mw + 15) / 16 + 2) * 4 + 64;
       if (need <= smem_cap3) { qlist.push_back(q); max_tn = std::max(max_tn, tn); maxW3 = std::max(maxW3, mw); } else for (u32 i = qbeg[q]; i < qend[q]; i++) rest.push_back(i); }
   if (rest.empty()) std::fill(hhoff.begin(), hhoff.end(), 0);   // the L2-resident hash index is only needed by the fallback kernel
@@ -1332,7 +1361,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>((i64)std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
   size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
   DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
-  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 36 * 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
+  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 48 * 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
   DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
   lap("k4 host prep");
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than W+226: capacities become the exact counts
