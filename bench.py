@@ -443,6 +443,8 @@ def run_c5(a, rank, world, local):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m, per, nq = C5["masks"], C5["per_mask"], C5["n_queries"]
+    from lexicmap_b200.api import gather_bench
+    gb = gather_bench(device=local, gbytes=8.0) if rank == 0 else None   # the device's random 32-byte-sector read rate, measured before the index fills the memory
     lo, hi = m * rank // world, m * (rank + 1) // world
     free_b = torch.cuda.mem_get_info(local)[0]
     need = (hi - lo) * per * 16 + m * 4096 * 4 + 3 * nq * 24 * 2
@@ -464,6 +466,7 @@ def run_c5(a, rank, world, local):
     sampler.start()
     r = idx.probe_bench(nq, iters=max(a.steps, 1) + a.warmup)
     sampler.finish()
+
     t = torch.tensor([r["survivors"], r["issued"], r["hits"], r["sum_log2"], r["sum_hit_sectors"], r["sum_values"], r["kernel_ms"], r["kernel_ms_best"]], device="cuda", dtype=torch.float64)
     if dist:
         tm = t[6:].clone()
@@ -485,7 +488,9 @@ def run_c5(a, rank, world, local):
                       "sharding": "index range-partitioned by mask over %d GPU(s); every probe goes to the GPU that owns its mask; no collective" % world, "seed": C5["seed"], "l2": "index shard (tens of GB) and the probe list (hundreds of MB) exceed the 126 MB L2"},
            "gpu_launches": a.steps + a.warmup + 2, "probes_issued": issued, "probes_with_anchor": surv, "hit_records": hits,
            "roofline": {"bound": "hbm", "kernel": "k_probe_find2", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None, "model": "SURVEY.md §8d per-probe bytes, per GPU (max kernel time over ranks)",
-                        "algorithmic_bytes_per_step": alg, "bytes_per_probe": alg / max(surv, 1), "kernel_ms_per_step": kms, "kernel_ms_best": kbest, "mean_log2_steps": slog / max(surv, 1), "peak_source": peak_src},
+                        "algorithmic_bytes_per_step": alg, "bytes_per_probe": alg / max(surv, 1), "kernel_ms_per_step": kms, "kernel_ms_best": kbest, "mean_log2_steps": slog / max(surv, 1), "peak_source": peak_src,
+                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): a lookup made of dependent random sectors is bound by this (DRAM row activations), not by the streaming peak",
+                                                  "sectors_per_s": gb["sectors_per_s"], "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak}},
            "e2e": {"value": surv / (kms * 1e-3), "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "device-resident microbenchmark: probes are generated on the GPU; the end-to-end numbers are the search configs'"},
            "cpu_baseline": None, "clocks": sampler.summary()}
     if dist:

@@ -129,6 +129,10 @@ int  lmg_index_load_times(const lmg_index* idx, double* ms4);
 int  lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed, int32_t mask_lo, int32_t mask_hi, int32_t with_values, lmg_index** out);
 int  lmg_probe_bench(lmg_index* idx, uint64_t n_queries, uint64_t seed, int32_t min_prefix, int32_t iters, double* out16);
 
+/* random 32-byte-sector read rate of the device (the physical ceiling of the seed lookup, whose accesses are dependent random sectors):
+ * n_threads x per_thread independent random reads of a `bytes`-sized buffer. out4: [0] sectors/s [1] GB/s at 32 B per access [2] best ms [3] mean ms */
+int  lmg_gather_bench(int device, uint64_t bytes, uint64_t n_threads, int32_t per_thread, int32_t iters, double* out4);
+
 /* ---- stage-wise entry points (parity tests; mirror a1-a7 of SURVEY.md §8a) ---- */
 /* lexichash mask + DUST filter + suffix re-masking (lib-index-search.go:1212-1350): kmers[n*m], nlocs[n*m], minloc[n*m];
  * suffix triples (query,new_mask,old_mask,kmer) flattened into suf[4*cap], *n_suf written. */

@@ -83,6 +83,7 @@ def load_library():
     L.lmg_index_load_times.argtypes = [vp, vp]
     L.lmg_probe_model.argtypes = [vp, vp]
     L.lmg_index_synth.argtypes = [C.c_int, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.lmg_gather_bench.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
     L.lmg_probe_bench.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, vp]
     _lib = L
     return L
@@ -288,6 +289,15 @@ class Index:
     def pseudoalign(self, seqs, params=None):
         """window geometry + pseudo-alignment + Chainer2: one record per Chain2Result, window coordinates (a9-a12)"""
         return self._stage(self.lib.lmg_pseudoalign_batch, PA_DTYPE, seqs, params)
+
+
+def gather_bench(device=0, gbytes=8.0, n_threads=1 << 24, per_thread=8, iters=5):
+    """random 32-byte-sector read rate of the device: {"sectors_per_s", "gbs_at_32B", "best_ms", "mean_ms"}"""
+    L = load_library()
+    out = np.zeros(4, np.float64)
+    if L.lmg_gather_bench(device, int(gbytes * (1 << 30)), n_threads, per_thread, iters, out.ctypes.data) != 0:
+        raise RuntimeError(L.lmg_last_error().decode())
+    return dict(zip(["sectors_per_s", "gbs_at_32B", "best_ms", "mean_ms"], out.tolist()))
 
 
 def wfa_batch(pairs, device=0, adaptive=1):

@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
   for (u32 tb = 0; tb < n; tb += blockDim.x) { u32 t = tb + threadIdx.x; bool lc = (t < n) && kmer_low_complexity(tab[t], k); u32 bal = __ballot_sync(FULLMASK, lc); if (lane == 0 && (tb + threadIdx.x) < ((n + 31) & ~31u)) lcb[(tb + threadIdx.x) >> 5] = bal; }
   __syncthreads();
   const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1; const int msh = 2 * k - mask_pbits; u32 issued = 0;
-  auto emit = [&](bool have, const Surv& r) { u32 bal = __ballot_sync(FULLMASK, have); if (!bal) return; u32 base = 0; int ldr = __ffs(bal) - 1; if (lane == ldr) base = atomicAdd(nsurv, __popc(bal)); base = __shfl_sync(FULLMASK, base, ldr);
-    if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; } };
+  // survivors are appended with ONE global atomic per CTA and loop iteration (ballot -> per-warp counts in shared memory -> thread 0), double-buffered by iteration parity:
+  // one atomic per warp and iteration meant ~5 million same-address atomics per batch
+  __shared__ u32 e_cnt[2][32], e_base[2]; int ep = 0; const int wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  auto emit = [&](bool have, const Surv& r) { const u32 bal = __ballot_sync(FULLMASK, have); if (lane == 0) e_cnt[ep][wid] = __popc(bal); __syncthreads();
+    if (threadIdx.x == 0) { u32 tot = 0; for (int i = 0; i < nwarp; i++) { const u32 c = e_cnt[ep][i]; e_cnt[ep][i] = tot; tot += c; } e_base[ep] = tot ? atomicAdd(nsurv, tot) : 0u; } __syncthreads();
+    if (have) { const u32 w = e_base[ep] + e_cnt[ep][wid] + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; } ep ^= 1; };
   // pass 1: masks
   for (int ib = 0; ib < m; ib += blockDim.x) { int i = ib + threadIdx.x; bool s0 = false; Surv r;
     if (i < m) { u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
@@ -207,8 +211,10 @@ __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* 
     if (na) { have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = sv.lo; h.n = sv.n; h.kmer = kmer; h.nanch = na * sv.n; h.bucket = bucket; }
     if (STATS) { const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1; const u64 an = E[lo].key >> ash; u32 n_a = 0; while (lo + n_a < hi && (E[lo + n_a].key >> ash) == an) n_a++; lg = 32 - __clz(n_a); hsec = (16 * ne + 31) / 32; nout = na; }   // ceil(log2(n_a + 1)) = bit length of n_a
   }
-  int lane = threadIdx.x & 31; u32 bal = __ballot_sync(FULLMASK, have);
-  if (bal) { u32 base = 0; if (lane == __ffs(bal) - 1) base = atomicAdd(nhits, __popc(bal)); base = __shfl_sync(FULLMASK, base, __ffs(bal) - 1); if (have) { u32 w = base + __popc(bal & ((1u << lane) - 1)); if (w < cap_hits) hits[w] = h; } }
+  // hit records are appended with ONE global atomic per CTA (warp ballots -> shared-memory warp counts -> thread 0): one atomic per warp put ~400,000 same-address atomics per launch on the critical path
+  __shared__ u32 s_wcnt[8], s_base; const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5; const u32 bal = __ballot_sync(FULLMASK, have); if (lane == 0) s_wcnt[wid] = __popc(bal); __syncthreads();
+  if (threadIdx.x == 0) { u32 tot = 0; for (int i = 0; i < 8; i++) { const u32 c = s_wcnt[i]; s_wcnt[i] = tot; tot += c; } s_base = tot ? atomicAdd(nhits, tot) : 0u; } __syncthreads();
+  if (have) { const u32 w = s_base + s_wcnt[wid] + __popc(bal & ((1u << lane) - 1)); if (w < cap_hits) hits[w] = h; }
   if (STATS && stats) { for (int o = 16; o; o >>= 1) { steps += __shfl_xor_sync(FULLMASK, steps, o); ne += __shfl_xor_sync(FULLMASK, ne, o); lg += __shfl_xor_sync(FULLMASK, lg, o); hsec += __shfl_xor_sync(FULLMASK, hsec, o); nout += __shfl_xor_sync(FULLMASK, nout, o); }
     if (lane == 0) { atomicAdd((unsigned long long*)&stats[2], (unsigned long long)steps); atomicAdd((unsigned long long*)&stats[3], (unsigned long long)ne); atomicAdd((unsigned long long*)&stats[4], (unsigned long long)lg); atomicAdd((unsigned long long*)&stats[5], (unsigned long long)hsec); atomicAdd((unsigned long long*)&stats[6], (unsigned long long)nout); } }
 }
@@ -1141,12 +1147,13 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
 #define WR_SEQW 144
 #define WR_SMEM_BYTES ((size_t)WR_WARPS * WR_SEQW * 8)
 #define WR_MAXLEN (1 << 20)      // offsets are stored in 20 bits of the backtrace word
-#define WR_W 64                  // diagonals in the window: two per lane (lane l holds kb + l and kb + 32 + l)
-// The 64-diagonal window follows the band: kb moves (registers shifted by warp shuffles) whenever the range of the new level or of one of the four
-// levels it reads from would touch the window's edge diagonals; the alignment falls back to k_wfa_fast / k_wfa only when that span itself exceeds
-// 62 diagonals. Bands of up to 30 diagonals (<= ~12 % divergence) live in the first slot only and the second slot's work is skipped (warp-uniform
-// branch). Diagonal kb never holds a live cell: its slab word stores kb of the level for the backtrace. This is what lets long, indel-rich
-// alignments (ONT reads: |tlen - plen| of hundreds, tens of thousands of levels) stay on the register path.
+#define WR_NS 4                  // diagonals per lane ("slots"): lane l holds window positions l, 32 + l, 64 + l, 96 + l
+#define WR_W (32 * WR_NS)        // diagonals in the window
+// The 128-diagonal window follows the band: kb moves (registers shifted by warp shuffles) whenever the range of the new level or of one of the four
+// levels it reads from would touch the window's edge positions; the alignment falls back to k_wfa_fast / k_wfa only when that span itself exceeds
+// 126 diagonals. Only the slots the span touches do any work (warp-uniform branches): bands of up to 30 diagonals (<= ~12 % divergence) are kept in
+// slot 0, ~25 % divergence needs two or three slots. Window position 0 never holds a live cell: its slab word stores kb of the level for the backtrace.
+// This is what lets long, indel-rich alignments (ONT reads: |tlen - plen| of hundreds, tens of thousands of levels) stay on the register path.
 struct WrCell { i32 om, oi, od, dv; u32 word; };
 __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, const u32* __restrict__ job_ids, u32 job0, u32 njobs, u32* __restrict__ next_job,
                                                          u32* __restrict__ slabs, const u64* __restrict__ slab_off, WfaOut* __restrict__ outs, int adaptive) {
@@ -1173,43 +1180,75 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
       return c; };
     i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
     i32 kb = -16;   // diagonal 0 on lane 16 of slot 0
-    i32 m1a = -1, m2a = -1, m3a = -1, m4a = -1, i1a = -1, d1a = -1, m1b = -1, m2b = -1, m3b = -1, m4b = -1, i1b = -1, d1b = -1;   // slot a: diagonal kb + lane, slot b: kb + 32 + lane; M of levels L-1..L-4, I / D of level L-1; -1 = null
-    if (kb + lane == 0) m1a = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = lane == 0 ? (u32)kb : 0u;
-    auto at = [&](i32 va, i32 vb, i32 j) { const i32 x = __shfl_sync(FULLMASK, va, j & 31), y = __shfl_sync(FULLMASK, vb, j & 31); return (j >> 5) ? y : x; };   // value on window position j (0..63), warp-uniform j
-    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = at(m1a, m1b, 0 - kb); done = (kend == 0 && v0 >= tlen); }
+    i32 m1[WR_NS], m2[WR_NS], m3[WR_NS], m4[WR_NS], i1[WR_NS], d1[WR_NS];   // per slot: M of levels L-1..L-4, I / D of level L-1 on this lane's diagonals; -1 = null
+#pragma unroll
+    for (int s_ = 0; s_ < WR_NS; s_++) { m1[s_] = m2[s_] = m3[s_] = m4[s_] = i1[s_] = d1[s_] = -1; }
+    if (kb + lane == 0) m1[0] = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = lane == 0 ? (u32)kb : 0u;
+    auto at = [&](const i32 (&v)[WR_NS], i32 j) { i32 r = -1;   // value on window position j, warp-uniform j
+#pragma unroll
+      for (int t = 0; t < WR_NS; t++) { const i32 x = __shfl_sync(FULLMASK, v[t], j & 31); if ((j >> 5) == t) r = x; } return r; };
+    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = at(m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }
     while (!done) {
       L++; if (L >= lmax) { overflow = true; break; }
       const bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; const bool allnull = nx && no && ni && nd;
       if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
-      { // the window must hold this level's range and the ranges of the levels still in registers on positions 1..62 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
-        i32 slo = allnull ? INT32_MAX : lo, shi = allnull ? INT32_MIN : hi; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { slo = min(slo, hlo[i]); shi = max(shi, hhi[i]); }
-        const i32 span = shi - slo + 1;
-        if (slo <= shi && (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30))) { if (span > WR_W - 2) { overflow = true; break; }
-          const i32 nkb = (span <= 30) ? slo - 1 - (30 - span) / 2 : slo - 1 - (WR_W - 2 - span) / 2, dlt = nkb - kb;   // narrow bands are centred in slot a, so that slot b stays idle
-          auto shift = [&](i32& va, i32& vb) { const i32 ja = lane + dlt, jb2 = lane + 32 + dlt; const i32 xa = __shfl_sync(FULLMASK, va, ja & 31), ya = __shfl_sync(FULLMASK, vb, ja & 31), xb = __shfl_sync(FULLMASK, va, jb2 & 31), yb = __shfl_sync(FULLMASK, vb, jb2 & 31);
-            va = (ja < 0 || ja > 63) ? -1 : ((ja >> 5) ? ya : xa); vb = (jb2 < 0 || jb2 > 63) ? -1 : ((jb2 >> 5) ? yb : xb); };
-          shift(m1a, m1b); shift(m2a, m2b); shift(m3a, m3b); shift(m4a, m4b); shift(i1a, i1b); shift(d1a, d1b); kb = nkb; } }
-      const i32 ka = kb + lane, kbb = kb + 32 + lane; const bool useB = !allnull && hi >= kb + 32, useA = !allnull && lo <= kb + 31;
-      WrCell ca, cb; ca.om = ca.oi = ca.od = -1; ca.dv = INT32_MAX; ca.word = 0; cb = ca;
-      if (useA || useB) {   // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab); position 31 | 32 is the seam between the slots
-        const i32 r0 = __shfl_sync(FULLMASK, m4a, lm1), r1 = __shfl_sync(FULLMASK, m4b, lm1), s0 = __shfl_sync(FULLMASK, i1a, lm1), s1 = __shfl_sync(FULLMASK, i1b, lm1);
-        const i32 t0 = __shfl_sync(FULLMASK, m4a, lp1), t1 = __shfl_sync(FULLMASK, m4b, lp1), u0 = __shfl_sync(FULLMASK, d1a, lp1), u1 = __shfl_sync(FULLMASK, d1b, lp1);
-        if (useA) ca = cell(ka, ka >= lo && ka <= hi, m2a, lane ? r0 : -1, lane ? s0 : -1, lane < 31 ? t0 : t1, lane < 31 ? u0 : u1);
-        if (useB) cb = cell(kbb, kbb >= lo && kbb <= hi, m2b, lane ? r1 : r0, lane ? s1 : s0, lane < 31 ? t1 : -1, lane < 31 ? u1 : -1); }
-      bool anyM = __any_sync(FULLMASK, ca.om >= 0 || cb.om >= 0), anyI = __any_sync(FULLMASK, ca.oi >= 0 || cb.oi >= 0), anyD = __any_sync(FULLMASK, ca.od >= 0 || cb.od >= 0);
+      // the window must hold this level's range and the ranges of the levels still in registers on positions 1..WR_W-2 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
+      i32 slo = allnull ? INT32_MAX : lo, shi = allnull ? INT32_MIN : hi; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { slo = min(slo, hlo[i]); shi = max(shi, hhi[i]); }
+      if (slo <= shi) { const i32 span = shi - slo + 1;
+        if (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30)) { if (span > WR_W - 2) { overflow = true; break; }
+          const i32 room = span <= 30 ? 30 : (span <= 62 ? 62 : (span <= 94 ? 94 : WR_W - 2)); const i32 nkb = slo - 1 - (room - span) / 2, dlt = nkb - kb;   // centred in as few slots as the span needs
+          const int sl = (lane + (dlt & 31)) & 31, carry = (lane + (dlt & 31)) >> 5, q = dlt >> 5;   // new position p takes old position p + dlt: old lane sl, old slot s + q + carry
+          auto shift = [&](i32 (&v)[WR_NS]) { i32 x[WR_NS];
+#pragma unroll
+            for (int t = 0; t < WR_NS; t++) x[t] = __shfl_sync(FULLMASK, v[t], sl);
+#pragma unroll
+            for (int s_ = 0; s_ < WR_NS; s_++) { const int src = s_ + q + carry; i32 r = -1;
+#pragma unroll
+              for (int t = 0; t < WR_NS; t++) if (src == t) r = x[t]; v[s_] = r; } };
+          shift(m1); shift(m2); shift(m3); shift(m4); shift(i1); shift(d1); kb = nkb; } }
+      const int sa = (slo <= shi) ? max(0, (slo - kb) >> 5) : 0, sb = (slo <= shi) ? min(WR_NS - 1, (shi - kb) >> 5) : -1;   // slots that can hold anything but nulls
+      WrCell c[WR_NS];
+#pragma unroll
+      for (int s_ = 0; s_ < WR_NS; s_++) { c[s_].om = c[s_].oi = c[s_].od = -1; c[s_].dv = INT32_MAX; c[s_].word = 0; }
+      if (!allnull) {   // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab); positions 31|32, 63|64, 95|96 are the seams between the slots
+        i32 r4[WR_NS], ri[WR_NS], t4[WR_NS], td[WR_NS];
+#pragma unroll
+        for (int t = 0; t < WR_NS; t++) { r4[t] = ri[t] = t4[t] = td[t] = -1; if (t >= sa && t <= sb) { r4[t] = __shfl_sync(FULLMASK, m4[t], lm1); ri[t] = __shfl_sync(FULLMASK, i1[t], lm1); t4[t] = __shfl_sync(FULLMASK, m4[t], lp1); td[t] = __shfl_sync(FULLMASK, d1[t], lp1); } }
+#pragma unroll
+        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ >= sa && s_ <= sb && lo <= kb + 32 * s_ + 31 && hi >= kb + 32 * s_) { const i32 k = kb + 32 * s_ + lane;
+            const i32 l4 = lane ? r4[s_] : (s_ ? r4[s_ - 1] : -1), li = lane ? ri[s_] : (s_ ? ri[s_ - 1] : -1), g4 = lane < 31 ? t4[s_] : (s_ < WR_NS - 1 ? t4[s_ + 1] : -1), gd = lane < 31 ? td[s_] : (s_ < WR_NS - 1 ? td[s_ + 1] : -1);
+            c[s_] = cell(k, k >= lo && k <= hi, m2[s_], l4, li, g4, gd); } }
+      bool hm = false, hi_ = false, hd = false;
+#pragma unroll
+      for (int s_ = 0; s_ < WR_NS; s_++) { hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
+      bool anyM = __any_sync(FULLMASK, hm), anyI = __any_sync(FULLMASK, hi_), anyD = __any_sync(FULLMASK, hd);
       if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa / k_wfa_fast / the oracle
-        i32 mind = min(ca.dv, cb.dv); for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50; const bool oka = (ca.om >= 0) && ca.dv <= thr, okb = (cb.om >= 0) && cb.dv <= thr;   // distances of null cells are +inf
-        const i32 top_limit = min(kend, hi); i32 nlo = lo; { const u32 ba = __ballot_sync(FULLMASK, oka && ka >= lo && ka < top_limit), bb = __ballot_sync(FULLMASK, okb && kbb >= lo && kbb < top_limit); if (ba) nlo = kb + __ffs(ba) - 1; else if (bb) nlo = kb + 32 + __ffs(bb) - 1; else if (top_limit > lo) nlo = top_limit; }
-        const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; { const u32 ba = __ballot_sync(FULLMASK, oka && ka <= hi && ka > bottom_limit), bb = __ballot_sync(FULLMASK, okb && kbb <= hi && kbb > bottom_limit); if (bb) nhi = kb + 63 - __clz(bb); else if (ba) nhi = kb + 31 - __clz(ba); else if (hi > bottom_limit) nhi = bottom_limit; }
-        if (nlo != lo || nhi != hi) { if (ka < nlo || ka > nhi) { ca.om = -1; ca.oi = -1; ca.od = -1; } if (kbb < nlo || kbb > nhi) { cb.om = -1; cb.oi = -1; cb.od = -1; }
-          anyM = __any_sync(FULLMASK, ca.om >= 0 || cb.om >= 0); anyI = __any_sync(FULLMASK, ca.oi >= 0 || cb.oi >= 0); anyD = __any_sync(FULLMASK, ca.od >= 0 || cb.od >= 0); lo = nlo; hi = nhi; }
+        i32 mind = INT32_MAX;
+#pragma unroll
+        for (int s_ = 0; s_ < WR_NS; s_++) mind = min(mind, c[s_].dv);
+        for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50;   // distances of null cells are +inf
+        const i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
+#pragma unroll
+        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k >= lo && k < top_limit); if (bal && !found) { nlo = kb + 32 * s_ + __ffs(bal) - 1; found = true; } }
+        if (!found && top_limit > lo) nlo = top_limit;
+        const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; found = false;
+#pragma unroll
+        for (int s_ = WR_NS - 1; s_ >= 0; s_--) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k <= hi && k > bottom_limit); if (bal && !found) { nhi = kb + 32 * s_ + 31 - __clz(bal); found = true; } }
+        if (!found && hi > bottom_limit) nhi = bottom_limit;
+        if (nlo != lo || nhi != hi) { hm = hi_ = hd = false;
+#pragma unroll
+          for (int s_ = 0; s_ < WR_NS; s_++) { const i32 k = kb + 32 * s_ + lane; if (k < nlo || k > nhi) { c[s_].om = -1; c[s_].oi = -1; c[s_].od = -1; } hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
+          anyM = __any_sync(FULLMASK, hm); anyI = __any_sync(FULLMASK, hi_); anyD = __any_sync(FULLMASK, hd); lo = nlo; hi = nhi; }
       }
-      { u32* row = slab + (u64)L * WR_W; row[lane] = lane == 0 ? (u32)kb : ca.word; if (useB) row[32 + lane] = cb.word; }
-      m4a = m3a; m3a = m2a; m2a = m1a; m1a = ca.om; i1a = ca.oi; d1a = ca.od; m4b = m3b; m3b = m2b; m2b = m1b; m1b = cb.om; i1b = cb.oi; d1b = cb.od;
+      { u32* row = slab + (u64)L * WR_W;
+#pragma unroll
+        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ == 0 || (s_ >= sa && s_ <= sb)) row[32 * s_ + lane] = (s_ == 0 && lane == 0) ? (u32)kb : c[s_].word; }
+#pragma unroll
+      for (int s_ = 0; s_ < WR_NS; s_++) { m4[s_] = m3[s_]; m3[s_] = m2[s_]; m2[s_] = m1[s_]; m1[s_] = c[s_].om; i1[s_] = c[s_].oi; d1[s_] = c[s_].od; }
       for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
-      if (!allnull && kend >= lo && kend <= hi) { const i32 v = at(m1a, m1b, kend - kb); done = (v >= tlen); }
+      if (!allnull && kend >= lo && kend <= hi) { const i32 v = at(m1, kend - kb); done = (v >= tlen); }
     }
     if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = 2 * L; outs[jb] = Rz; }
     __syncwarp();
@@ -1255,7 +1294,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
       i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
       const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64));
-      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.2), 32ull << 30) / (u64)std::max(1, active_lanes);
+      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.35), 64ull << 30) / (u64)std::max(1, active_lanes);
       if (g_lap) (*g_lap)("wfa prep kernel");
       // pass 1, every job: the register kernel (one diagonal per lane, 128 B of backtrace words per level). Rounds only when the slabs of all jobs exceed the budget.
       std::vector<u32> rest;   // jobs whose band left the 32-lane window (or too deep / too long): pass 2
@@ -1646,6 +1685,20 @@ int lmg_wfa_batch(int device, const uint8_t* seqs, const uint64_t* off, int32_t 
 int lmg_index_set_total_bases(lmg_index* ix, int64_t tb) { if (!ix || tb <= 0) { g_err = "lmg_index_set_total_bases: total_bases must be positive"; return -1; } std::lock_guard<std::mutex> lk(ix->mu); ix->imgp->total_bases = tb; return 0; }
 int lmg_index_load_times(const lmg_index* ix, double* ms4) { for (int i = 0; i < 4; i++) ms4[i] = ix->img.load_ms[i]; return 0; }
 int lmg_probe_model(const lmg_index* ix, uint64_t* s4) { for (int i = 0; i < 4; i++) s4[i] = ix->pstat[i]; return 0; }
+// Random 32-byte-sector read rate of the device: every thread reads `per_thread` independent pseudo-random 8-byte words of a buffer far larger than L2.
+// This is the physical ceiling of a lookup kernel whose accesses are dependent random sectors (DRAM row activations, not streaming bandwidth, bound it).
+__global__ void __launch_bounds__(256) k_gather_bench(const u64* __restrict__ buf, u64 nwords, u64 n, int per_thread, u64 seed, u64* __restrict__ sink) {
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (t >= n) return; u64 acc = 0, r = mix64(seed ^ t);
+  for (int i = 0; i < per_thread; i++) { r = mix64(r); acc += buf[(r % nwords) & ~3ull]; }   // sector-aligned, independent addresses (no pointer chasing: the rate, not the latency)
+  if (acc == 0x1234567ull) sink[0] = acc;
+}
+int lmg_gather_bench(int device, uint64_t bytes, uint64_t n_threads, int32_t per_thread, int32_t iters, double* out4) {
+  try { CUDA_CHECK(cudaSetDevice(device)); u64* buf = nullptr; u64* sink = nullptr; const u64 nwords = bytes / 8; CUDA_CHECK(cudaMalloc((void**)&buf, nwords * 8)); CUDA_CHECK(cudaMalloc((void**)&sink, 64)); CUDA_CHECK(cudaMemset(buf, 1, nwords * 8));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); double best = 1e30, sum = 0;
+    for (int it = -1; it < iters; it++) { cudaEventRecord(e0); k_gather_bench<<<(unsigned)((n_threads + 255) / 256), 256>>>(buf, nwords, n_threads, per_thread, 77 + it, sink); KERNEL_CHECK(); cudaEventRecord(e1); CUDA_CHECK(cudaEventSynchronize(e1)); float f = 0; cudaEventElapsedTime(&f, e0, e1); if (it >= 0) { best = std::min(best, (double)f); sum += f; } }
+    const double acc = (double)n_threads * per_thread; out4[0] = acc / (best * 1e-3); out4[1] = out4[0] * 32 / 1e9; out4[2] = best; out4[3] = iters > 0 ? sum / iters : 0; cudaFree(buf); cudaFree(sink); cudaEventDestroy(e0); cudaEventDestroy(e1); return 0; }
+  catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
+}
 int lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed, int32_t mask_lo, int32_t mask_hi, int32_t with_values, lmg_index** out) {
   try { int ndev = 0; CUDA_CHECK(cudaGetDeviceCount(&ndev)); if (ndev == 0) throw std::runtime_error("no CUDA device: the LexicMap GPU path has no CPU fallback"); if (masks < 64 || per_mask == 0 || per_mask >= (1ull << 31) || mask_lo < 0 || mask_hi > masks || mask_lo >= mask_hi) throw std::runtime_error("lmg_index_synth: bad arguments");
     Image* im = new Image; lmg_index* ix = nullptr; try { im->synth(device, masks, per_mask, seed, mask_lo, mask_hi, with_values != 0); im->info.chunks = 0; im->info.partitions = im->NA; im->info.genome_batches = 0; im->synth_per = per_mask; im->synth_seed = seed; ix = make_ctx(im, true, device); } catch (...) { if (!ix) { im->release(); delete im; } throw; }
