@@ -117,6 +117,23 @@ def ensure_c2(rank):
     return idx, qf
 
 
+def c3_queries(world, part=None):
+    """the C3 batch: `world` parts of n/world queries, part p cut from the genomes of shard p (so every shard owns the hits of its share of the
+    batch); the parts are regenerated straight from the synthetic collection, no index needed. Returns the list of part files (all parts, or [part])."""
+    fam = C3["genomes"] // C3["members"]
+    files = []
+    for p in (range(world) if part is None else [part]):
+        f0, f1 = fam * p // world, fam * (p + 1) // world
+        n = C3["n_queries"] * (p + 1) // world - C3["n_queries"] * p // world
+        path = os.path.join(WORK, "c3d_q%d_%d_w%d_p%d.fa" % (C3["n_queries"], C3["query_len"], world, p))
+        if not os.path.exists(path):
+            subprocess.check_call([tools(), "synth-queries", "--synth", "%d,%d,%d,%d,20" % (fam, C3["members"], C3["genome_len"], C3["genome_seed"]), "--genome-range", "%d,%d" % (f0 * C3["members"], f1 * C3["members"]),
+                                   "--n", str(n), "--len", str(C3["query_len"]), "--seed", str(C3["query_seed"] + p), "--out", path + ".tmp%d" % os.getpid()])
+            os.rename(path + ".tmp%d" % os.getpid(), path)
+        files.append(path)
+    return files
+
+
 def ensure_c3(rank, world):
     """shard `rank` of the 100,000-genome collection: families [f0, f1) of 1,000 families x 100 members; one .lmi per shard"""
     fam = C3["genomes"] // C3["members"]
@@ -254,12 +271,14 @@ def run_search(a, rank, world, local):
         idx_dir = ensure_c3(rank, world)
         if dist:
             dist.barrier()
-        qf = os.path.join(WORK, "c3d_q%d_%d.fa" % (C3["n_queries"], C3["query_len"]))
-        if rank == 0:   # queries are cut from shard 0's genomes (every rank searches the same batch)
-            synth_queries(idx_dir, qf, C3["n_queries"], C3["query_len"], C3["query_seed"])
+        c3_queries(world, part=rank)   # every rank writes the part cut from its own shard's genomes, then all read all parts (same box)
         if dist:
             dist.barrier()
-        ids, seqs = read_fasta(qf)
+        ids, seqs = [], []
+        for qf in c3_queries(world):
+            i2, s2 = read_fasta(qf)
+            ids += i2
+            seqs += s2
         full = (C3["genomes"], C3["n_queries"]) == (100000, 10000)
         workload = "%d synthetic %d-bp queries vs %d-genome synthetic collection (%d bp each) genome-sharded over %d GPU(s), %s" % (
             C3["n_queries"], C3["query_len"], C3["genomes"], C3["genome_len"], world, "BASELINE.json configs[2] (10k-query headline)" if full else "REDUCED rehearsal of BASELINE.json configs[2]")
@@ -514,8 +533,11 @@ def run_reference(a):
     elif a.config == "c3":
         world = max(1, a.gpus)
         idx_dir = ensure_c3(0, world)
-        qf = synth_queries(idx_dir, os.path.join(WORK, "c3d_q%d_%d.fa" % (C3["n_queries"], C3["query_len"])), C3["n_queries"], C3["query_len"], C3["query_seed"])
-        ids, seqs = read_fasta(qf)
+        ids, seqs = [], []
+        for qf in c3_queries(world):   # the whole batch: part 0 hits shard 0's genomes, the other parts only probe it (as on every GPU rank)
+            i2, s2 = read_fasta(qf)
+            ids += i2
+            seqs += s2
         config = base_config(a, "BASELINE.json configs[2]: %d x %d-bp queries vs %d genomes, CPU port against shard 0 of %d" % (C3["n_queries"], C3["query_len"], C3["genomes"], world), {"genomes": C3["genomes"]})
         div = world
         note_extra = "; measured against shard 0 (1/%d of the genomes) and divided by %d" % (world, world)

@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 // K2: seed probe (kv.Searcher.Search / Search2, kv/kv-searcher.go:190-1088) + anchors (lib-index-search.go:1357-1569)
 // =====================================================================================================
 struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 bucket; };  // mask_dir = capturing mask<<1 | dir ; [lo,lo+n) = query table rows (locs); bucket = mask bucket searched; [e0, e0+ne) = matched index entries
-struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_start, *anchor_bits, *pbloom; u32 pbmask; int m, k, NA, mask_prefix, anchor_prefix, p; };
+struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_cbase, *anchor_cstart, *anchor_bits, *pbloom; const u16* anchor_cum; u32 pbmask; int m, k, NA, mask_prefix, anchor_prefix, p; };
+// bucket-relative index of the first key of anchor `an` (present anchors only): rank of the anchor among the bucket's present anchors -> compact start array
+__device__ __forceinline__ u32 anchor_start_of(const ProbeParams& P, u32 bucket, u32 an) { const u64 w = (u64)bucket * (u32)(P.NA >> 5) + (an >> 5); const u32 bits = P.anchor_bits[w]; const u32 rank = (u32)P.anchor_cum[w] + __popc(bits & ((1u << (an & 31)) - 1)); return P.anchor_cstart[P.anchor_cbase[bucket] + rank]; }
 // a probe survives when its anchor exists in the bucket's anchor table (the reference's own test) AND some key of the bucket starts with the probe's first maskPrefix+anchorPrefix bases (prefix Bloom filter, image.cuh)
 __device__ __forceinline__ bool probe_may_hit(const ProbeParams& P, u32 bucket, u64 left, int ash) { const u32 pre = (u32)(left >> ash); const u64 aslot = (u64)bucket * P.NA + (pre & (u32)(P.NA - 1)); if (!((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1)) return false;
   const u32 hb = pb_hash(bucket, pre) & P.pbmask; return (P.pbloom[hb >> 5] >> (hb & 31)) & 1; }
@@ -201,7 +203,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0, lg = 0, hsec = 0, nout = 0;
   if (t < ns) { Surv sv = surv[t]; const u32 dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; const u32 bucket = aslot / (u32)P.NA; u64 kmer = sv.kmer;
-    int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; u32 as = P.anchor_start[aslot];
+    int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; const u32 as = anchor_start_of(P, bucket, aslot - bucket * (u32)P.NA);
     const u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; const SeedEntry* __restrict__ E = P.entries; u64 lo = b0 + as, hi = b1;
     u64 step = 1, l = lo; while (l + step < hi && E[l + step].key < left) { l += step; step <<= 1; steps++; }
     u64 r = min(hi, l + step); if (E[l].key >= left) r = l; else l = l + 1;
@@ -340,7 +342,7 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
-static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_start = I.d_anchor_start; P.anchor_bits = I.d_anchor_bits; P.pbloom = I.d_pbloom; P.pbmask = I.pbmask; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
+static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_cbase = I.d_anchor_cbase; P.anchor_cstart = I.d_anchor_cstart; P.anchor_cum = I.d_anchor_cum; P.anchor_bits = I.d_anchor_bits; P.pbloom = I.d_pbloom; P.pbmask = I.pbmask; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
@@ -1303,14 +1305,17 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
         auto lv_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return (u64)std::max<i64>(256, ((i64)(0.8 * (double)len) + 63) / 64 * 64); };
         auto op_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return want_ops ? (u64)std::max<i64>(1024, len + 64) : 0ull; };
         std::vector<u64> hso, hoo; std::vector<u32> skipped; u32 rounds = 0, round_max = 0;
+        // longest alignments first: the persistent warps pull jobs in this order, so the expensive ones start early and the tail of a launch is made of short ones
+        std::vector<u32> order(nj); std::iota(order.begin(), order.end(), 0u); { std::vector<i32> len(nj); for (u32 j = 0; j < nj; j++) len[j] = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return len[a] > len[b]; }); }
+        DBuf<u32> d_order(nj, st); d_order.from_host(order.data(), nj);
         { KTimer kt(st, &ms[11]);
           for (u32 j0 = 0; j0 < nj;) { hso.assign(1, 0); hoo.assign(1, 0); u64 bytes = 0; u32 n = 0;
-            while (j0 + n < nj) { const u64 lv = lv_cap(j0 + n), oc = op_cap(j0 + n), b = lv * WR_W * 4 + oc * 8; if (n > 0 && (bytes + b > budgetF || (g_arena == nullptr && n >= 8192))) break; if (n == 0 && b > budgetF) { skipped.push_back(j0); j0++; continue; } hso.push_back(hso.back() + lv); hoo.push_back(hoo.back() + oc); bytes += b; n++; }
+            while (j0 + n < nj) { const u32 jid = order[j0 + n]; const u64 lv = lv_cap(jid), oc = op_cap(jid), b = lv * WR_W * 4 + oc * 8; if (n > 0 && (bytes + b > budgetF || (g_arena == nullptr && n >= 8192))) break; if (n == 0 && b > budgetF) { skipped.push_back(jid); j0++; continue; } hso.push_back(hso.back() + lv); hoo.push_back(hoo.back() + oc); bytes += b; n++; }
             if (n == 0) continue;
             DBuf<u64> soff(n + 1, st), ooff(n + 1, st); soff.from_host(hso.data(), n + 1); ooff.from_host(hoo.data(), n + 1); DBuf<u32> rslabs(hso.back() * WR_W + 64, st); DBuf<u64> oscr(hoo.back() + 8, st); DBuf<u32> next(1, st); next.zero();
             const u32 blocks = (u32)std::min<u64>((u64)sm_count * 8, (n + WR_WARPS - 1) / WR_WARPS);
-            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, nullptr, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive); KERNEL_CHECK();
-            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, nullptr, j0, n, rslabs.p, soff.p, oscr.p, ooff.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, d_order.p, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive); KERNEL_CHECK();
+            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, d_order.p, j0, n, rslabs.p, soff.p, oscr.p, ooff.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
             CUDA_CHECK(cudaStreamSynchronize(st));   // the round's buffers go back to the arena
             j0 += n; rounds++; round_max = std::max(round_max, n); } }
         std::vector<WfaOut> o = d_out.to_host(nj); std::vector<char> sk(nj, 0); for (u32 j : skipped) sk[j] = 1;

@@ -63,9 +63,22 @@ __global__ void k_kv_fill(const u8* __restrict__ d, const u8* __restrict__ x, co
 __global__ void k_kv_anchor(const u8* __restrict__ x, const u64* __restrict__ xoff, const u32* __restrict__ xn, int nmasks, int mask0, const u64* __restrict__ bucket_off, const SeedEntry* __restrict__ entries, int sh, u32 NA, u32* __restrict__ anchor_start, u32* __restrict__ bad) {
   const int wm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31; if (wm >= nmasks) return; const u32 nrec = xn[wm]; const u64 b0 = bucket_off[mask0 + wm], b1 = bucket_off[mask0 + wm + 1]; const SeedEntry* E = entries + b0; const u32 n = (u32)(b1 - b0);
   for (u32 r = 1 + lane; r < nrec; r += 32) { const u64 kmer = ld_be(x + xoff[wm] + 16ull * r, 8); u32 lo = 0, hi = n; while (lo < hi) { u32 mid = (lo + hi) >> 1; if (E[mid].key < kmer) lo = mid + 1; else hi = mid; }
-    if (lo >= n || E[lo].key != kmer) { atomicAdd(bad, 1u); continue; } anchor_start[(u64)(mask0 + wm) * NA + (u32)((kmer >> sh) & (u64)(NA - 1))] = lo; }
+    if (lo >= n || E[lo].key != kmer) { atomicAdd(bad, 1u); continue; } anchor_start[(u64)wm * NA + (u32)((kmer >> sh) & (u64)(NA - 1))] = lo; }   // dense scratch table of the chunk
 }
-__global__ void k_anchor_bits(const u32* __restrict__ anchor_start, u64 n, u32* __restrict__ bits) { u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (w * 32 >= n) return; u32 v = 0; for (int i = 0; i < 32; i++) { u64 t = w * 32 + i; if (t < n && anchor_start[t] != 0xFFFFFFFFu) v |= 1u << i; } bits[w] = v; }
+// Compact anchor table. A bucket uses 100-200 of its 4^anchorPrefix anchors, so the dense table (m x 4096 x 4 B = 328 MB, one random DRAM sector
+// per probe) is replaced by three small arrays that stay in L2: the presence bitmap (1 bit per anchor), per 32-anchor word the number of present anchors
+// before it in the bucket (u16), and the starts of the present anchors only (bucket b: cstart[cbase[b] ...]); start = cstart[cbase[b] + cum[word] + popc(bits below)].
+// One CTA per bucket of the chunk: `full` is the chunk's dense scratch table (0xFFFFFFFF = absent).
+__global__ void __launch_bounds__(128) k_anchor_compact(const u32* __restrict__ full, int nm, int mask0, u32 NA, const u32* __restrict__ cbase, u32* __restrict__ bits, u16* __restrict__ cum, u32* __restrict__ cstart, u32* __restrict__ bad) {
+  __shared__ u32 s_cnt[128]; __shared__ u32 s_run; const int b = blockIdx.x; if (b >= nm) return; const u32 nw = NA >> 5; const u32* F = full + (u64)b * NA; const u64 w0 = (u64)(mask0 + b) * nw;
+  for (u32 wbase = 0; wbase < nw; wbase += 128) { const u32 w = wbase + threadIdx.x; u32 v = 0; if (w < nw) for (int i = 0; i < 32; i++) if (F[w * 32 + i] != 0xFFFFFFFFu) v |= 1u << i; if (w < nw) bits[w0 + w] = v; s_cnt[threadIdx.x] = (w < nw) ? __popc(v) : 0; __syncthreads();
+    if (wbase == 0 && threadIdx.x == 0) s_run = 0; __syncthreads();
+    if (threadIdx.x == 0) { u32 run = s_run; for (u32 i = 0; i < 128; i++) { const u32 c = s_cnt[i]; s_cnt[i] = run; run += c; } s_run = run; } __syncthreads();
+    if (w < nw) { const u32 before = s_cnt[threadIdx.x]; cum[w0 + w] = (u16)before; u32 r = 0; const u32 base = cbase[mask0 + b]; u32 vv = v; while (vv) { const int i = __ffs(vv) - 1; vv &= vv - 1; cstart[base + before + r] = F[w * 32 + i]; r++; } } __syncthreads(); }
+  (void)bad;
+}
+__global__ void k_anchor_count(const u32* __restrict__ full, int nm, u32 NA, u32* __restrict__ counts) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= nm) return; const u32* F = full + (u64)b * NA; u32 c = 0; for (u32 i = 0; i < NA; i++) c += F[i] != 0xFFFFFFFFu; counts[b] = c; }
+__global__ void k_anchor_verify(const u32* __restrict__ bits, const u32* __restrict__ cbase, int m, u32 nw, u32* __restrict__ bad) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= m) return; u32 c = 0; for (u32 w = 0; w < nw; w++) c += __popc(bits[(u64)b * nw + w]); if (c != cbase[b + 1] - cbase[b]) atomicAdd(bad, 1u); }
 
 // ---- synthetic seed image (BASELINE.json configs[4]): per mask `per` keys = the mask's prefix + stratified-uniform low bits (sorted
 // by construction), one random value each (reversed flag = bit 0 of a hash)
@@ -89,7 +102,8 @@ struct Image {
   u64 E = 0, V = 0; int G = 0; size_t bytes = 0; int n_shards = 1, shard = 0;
   int mask_lo = 0, mask_hi = 0;   // masks whose buckets this image holds ([0, m) except for mask-range-partitioned synthetic images)
   // device arrays
-  u64 *d_masks = nullptr, *d_bucket_off = nullptr, *d_bucket_voff = nullptr, *d_vals = nullptr; SeedEntry* d_entries = nullptr; u32* d_anchor_start = nullptr;
+  u64 *d_masks = nullptr, *d_bucket_off = nullptr, *d_bucket_voff = nullptr, *d_vals = nullptr; SeedEntry* d_entries = nullptr;
+  u32 *d_anchor_cbase = nullptr, *d_anchor_cstart = nullptr; u16* d_anchor_cum = nullptr; u64 n_anchors = 0;   // compact anchor table (k_anchor_compact)
   u32* d_pbloom = nullptr; u32 pbmask = 0;   // prefix Bloom filter (pb_hash): pbmask + 1 bits, a power of two >= 8 bits per stored k-mer (<= 2^32)
   u32* d_anchor_bits = nullptr;   // m * NA/32 words: bit a of mask i set iff anchor_start[i][a] is present (10 MB, L2-resident filter in front of the 328 MB table)
   u32* d_mask_pstart = nullptr; int mask_pbits = 14;   // masks bucketed by their mask_prefix leading bases: [pstart[p], pstart[p+1])
@@ -108,7 +122,11 @@ struct Image {
 
   void alloc_pbloom() { u64 bits = 1ull << 20; while (bits < 8 * E && bits < (1ull << 32)) bits <<= 1; pbmask = (u32)(bits - 1); d_pbloom = dalloc<u32>(bits / 32); CUDA_CHECK(cudaMemset(d_pbloom, 0, bits / 8)); }
   void finish_masks() { mask_pbits = 2 * mask_prefix; std::vector<u32> ps(((size_t)1 << mask_pbits) + 1, 0); for (u64 mk : h_masks) ps[(mk >> (2 * k - mask_pbits)) + 1]++; for (size_t i = 0; i + 1 < ps.size(); i++) ps[i + 1] += ps[i]; d_mask_pstart = up(ps); d_masks = up(h_masks); }
-  void make_anchor_bits() { const u64 n = (u64)m * NA; d_anchor_bits = dalloc<u32>(n / 32 + 1); k_anchor_bits<<<(unsigned)((n / 32 + 256) / 256), 256>>>(d_anchor_start, n, d_anchor_bits); CUDA_CHECK(cudaGetLastError()); CUDA_CHECK(cudaDeviceSynchronize()); }
+  // compact anchor arrays from per-bucket counts (host): allocations + prefix sums; the chunks are compacted afterwards
+  void alloc_anchors(const std::vector<u32>& counts) { if (NA < 32) lmi::die("indexes with fewer than 64 partitions are not supported by the GPU path"); std::vector<u32> cb(m + 1, 0); for (int j = 0; j < m; j++) cb[j + 1] = cb[j] + counts[j]; n_anchors = cb[m];
+    d_anchor_cbase = up(cb); d_anchor_cstart = dalloc<u32>(n_anchors); const u64 nwords = (u64)m * (NA >> 5); d_anchor_bits = dalloc<u32>(nwords); d_anchor_cum = dalloc<u16>(nwords); CUDA_CHECK(cudaMemset(d_anchor_bits, 0, nwords * 4)); CUDA_CHECK(cudaMemset(d_anchor_cum, 0, nwords * 2)); }
+  void verify_anchors() { u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); k_anchor_verify<<<(m + 127) / 128, 128>>>(d_anchor_bits, d_anchor_cbase, m, (u32)(NA >> 5), d_bad); CUDA_CHECK(cudaGetLastError()); u32 bad = 0; CUDA_CHECK(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad);
+    if (bad) lmi::die("kv-index: the anchor records of " + std::to_string(bad) + " masks are inconsistent (duplicate or missing anchors)"); }
 
   void load(const std::string& dir, int dev, int shard_, int n_shards_) {
     auto t_all = std::chrono::steady_clock::now(); auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -139,7 +157,7 @@ struct Image {
     load_ms[0] = ms_since(t0);
     // ---- seeds: chunk files -> device, decoded there
     t0 = std::chrono::steady_clock::now();
-    struct ChunkDev { u8 *d = nullptr, *x = nullptr; u64 *xoff = nullptr; u32* xn = nullptr; int mask0 = 0, nm = 0, vb = 7; size_t dsz = 0, xsz = 0; };
+    struct ChunkDev { u8 *d = nullptr, *x = nullptr; u64 *xoff = nullptr; u32* xn = nullptr; int mask0 = 0, nm = 0, vb = 7; size_t dsz = 0, xsz = 0; std::vector<u32> h_xn; };
     auto free_chunk = [](ChunkDev& c) { for (void* p : {(void*)c.d, (void*)c.x, (void*)c.xoff, (void*)c.xn}) if (p) cudaFree(p); c.d = c.x = nullptr; c.xoff = nullptr; c.xn = nullptr; };
     auto upload_chunk = [&](int ci) { ChunkDev c; std::string f = lmi::chunk_file(dir, ci); std::vector<u8> d = lmi::read_file(f), x = lmi::read_file(f + ".idx");
       if (d.size() < 32 || memcmp(d.data(), ".kv-data", 8)) lmi::die("not a kv-data file: " + f); if (x.size() < 32 || memcmp(x.data(), ".kvindex", 8)) lmi::die("not a kv-index file: " + f + ".idx"); if (d[8] != 1 || x[8] != 1) lmi::die("kv-data: version mismatch");
@@ -148,27 +166,31 @@ struct Image {
       std::vector<u64> xoff(c.nm); std::vector<u32> xn(c.nm); size_t q = 32; for (int i = 0; i < c.nm; i++) { if (q + 8 > x.size()) lmi::die("kv-index: truncated"); u64 nrec = lmi::get_be(&x[q], 8); xoff[i] = q + 8; xn[i] = (u32)nrec; q += 8 + 16 * nrec; } if (q > x.size()) lmi::die("kv-index: truncated");
       // xoff = first 16-byte record of the mask's block: record 0 is (record count, file offset of the first k-mer << 1), record r >= 1 is (anchor k-mer, offset << 1 | second-of-pair) (kv-data.go:566-599)
       c.dsz = d.size(); c.xsz = x.size(); CUDA_CHECK(cudaMalloc((void**)&c.d, d.size() + 64)); CUDA_CHECK(cudaMalloc((void**)&c.x, x.size() + 64)); CUDA_CHECK(cudaMalloc((void**)&c.xoff, sizeof(u64) * (c.nm + 1))); CUDA_CHECK(cudaMalloc((void**)&c.xn, sizeof(u32) * (c.nm + 1)));
-      CUDA_CHECK(cudaMemcpy(c.d, d.data(), d.size(), cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.x, x.data(), x.size(), cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.xoff, xoff.data(), sizeof(u64) * c.nm, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.xn, xn.data(), sizeof(u32) * c.nm, cudaMemcpyHostToDevice)); return c; };
+      CUDA_CHECK(cudaMemcpy(c.d, d.data(), d.size(), cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.x, x.data(), x.size(), cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.xoff, xoff.data(), sizeof(u64) * c.nm, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(c.xn, xn.data(), sizeof(u32) * c.nm, cudaMemcpyHostToDevice)); c.h_xn = xn; return c; };
     // keep the raw chunk bytes on the device between the two passes when they are small next to the free memory, otherwise read the files twice
     u64 raw_total = 0; for (int c = 0; c < info.chunks; c++) { struct stat st; std::string f = lmi::chunk_file(dir, c); if (stat(f.c_str(), &st) == 0) raw_total += (u64)st.st_size; if (stat((f + ".idx").c_str(), &st) == 0) raw_total += (u64)st.st_size; }
     size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); const bool keep_raw = raw_total * 4 < freeb && !getenv("LMG_INGEST_REREAD");
     ShardSel S{d_batch_base, n_shards, shard}; u64 *d_nk = nullptr, *d_nv = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_nk, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMalloc((void**)&d_nv, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMemset(d_nk, 0, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMemset(d_nv, 0, sizeof(u64) * (m + 1)));
-    std::vector<ChunkDev> kept(info.chunks);
-    for (int c = 0; c < info.chunks; c++) { ChunkDev cd = upload_chunk(c); if (cd.nm) { k_kv_count<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_nk + cd.mask0, d_nv + cd.mask0); CUDA_CHECK(cudaGetLastError()); }
+    std::vector<ChunkDev> kept(info.chunks); std::vector<u32> anchor_counts(m, 0);
+    for (int c = 0; c < info.chunks; c++) { ChunkDev cd = upload_chunk(c); for (int i = 0; i < cd.nm; i++) anchor_counts[cd.mask0 + i] = cd.h_xn[i] ? cd.h_xn[i] - 1 : 0;   // one .idx record per present anchor after the header record if (cd.nm) { k_kv_count<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_nk + cd.mask0, d_nv + cd.mask0); CUDA_CHECK(cudaGetLastError()); }
       if (keep_raw) kept[c] = cd; else { CUDA_CHECK(cudaDeviceSynchronize()); free_chunk(cd); } }
     CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<u64> nk(m + 1), nv(m + 1), bucket_off(m + 1, 0), bucket_voff(m + 1, 0); CUDA_CHECK(cudaMemcpy(nk.data(), d_nk, sizeof(u64) * m, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(nv.data(), d_nv, sizeof(u64) * m, cudaMemcpyDeviceToHost)); cudaFree(d_nk); cudaFree(d_nv);
     for (int j = 0; j < m; j++) { bucket_off[j + 1] = bucket_off[j] + nk[j]; bucket_voff[j + 1] = bucket_voff[j] + nv[j]; if (nk[j] >= (1ull << 32) || nv[j] >= (1ull << 31)) lmi::die("a mask bucket holds more than 2^32 k-mers or 2^31 values"); }
     E = bucket_off[m]; V = bucket_voff[m]; load_ms[1] = ms_since(t0); t0 = std::chrono::steady_clock::now();
-    d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V); d_anchor_start = dalloc<u32>((size_t)m * NA); CUDA_CHECK(cudaMemset(d_anchor_start, 0xff, (size_t)m * NA * 4));
+    d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V); alloc_anchors(anchor_counts);
+    int max_nm = 1; for (int c = 0; c < info.chunks; c++) max_nm = std::max(max_nm, (m + info.chunks - 1) / info.chunks + 1); u32* d_full = nullptr; size_t full_cap = 0;   // dense anchor scratch of one chunk
     alloc_pbloom();
     u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); const int sh = 2 * (k - mask_prefix - anchor_prefix);
     for (int c = 0; c < info.chunks; c++) { ChunkDev cd = keep_raw ? kept[c] : upload_chunk(c); if (cd.nm) {
         k_kv_fill<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_bucket_off + cd.mask0, d_bucket_voff + cd.mask0, d_entries, d_vals, d_pbloom, pbmask, sh, cd.mask0); CUDA_CHECK(cudaGetLastError());
-        k_kv_anchor<<<(cd.nm * 32 + 127) / 128, 128>>>(cd.x, cd.xoff, cd.xn, cd.nm, cd.mask0, d_bucket_off, d_entries, sh, (u32)NA, d_anchor_start, d_bad); CUDA_CHECK(cudaGetLastError()); }
+        const size_t need = (size_t)cd.nm * NA; if (need > full_cap) { if (d_full) cudaFree(d_full); CUDA_CHECK(cudaMalloc((void**)&d_full, need * 4)); full_cap = need; } CUDA_CHECK(cudaMemset(d_full, 0xff, need * 4));
+        k_kv_anchor<<<(cd.nm * 32 + 127) / 128, 128>>>(cd.x, cd.xoff, cd.xn, cd.nm, cd.mask0, d_bucket_off, d_entries, sh, (u32)NA, d_full, d_bad); CUDA_CHECK(cudaGetLastError());
+        k_anchor_compact<<<cd.nm, 128>>>(d_full, cd.nm, cd.mask0, (u32)NA, d_anchor_cbase, d_anchor_bits, d_anchor_cum, d_anchor_cstart, d_bad); CUDA_CHECK(cudaGetLastError()); }
       CUDA_CHECK(cudaDeviceSynchronize()); free_chunk(cd); }
+    if (d_full) cudaFree(d_full); (void)max_nm;
     u32 bad = 0; CUDA_CHECK(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad); if (bad) lmi::die("kv-index: " + std::to_string(bad) + " anchor records do not name a stored k-mer");
-    finish_masks(); make_anchor_bits(); load_ms[2] = ms_since(t0); load_ms[3] = ms_since(t_all);
+    finish_masks(); verify_anchors(); load_ms[2] = ms_since(t0); load_ms[3] = ms_since(t_all);
   }
 
   // Synthetic seeds-only image for the seed-lookup microbenchmark: masks [lo, hi) of an m-mask index, `per` keys each (no genomes: only the probe kernels may run on it)
@@ -179,10 +201,16 @@ struct Image {
       if (dup_lo || dup_hi) { r &= ~(3ull << (lowbits - 2)); r |= (u64)(dup_hi ? 2 : 1) << (lowbits - 2); } h_masks[i] = (p << lowbits) | r; }
     std::sort(h_masks.begin(), h_masks.end()); for (int i = 1; i < m; i++) if (h_masks[i] == h_masks[i - 1]) lmi::die("synthetic masks collide");
     std::vector<u64> bucket_off(m + 1, 0), bucket_voff(m + 1, 0); for (int j = 0; j < m; j++) { const u64 n = (j >= lo && j < hi) ? per : 0; bucket_off[j + 1] = bucket_off[j] + n; bucket_voff[j + 1] = bucket_voff[j] + (with_values ? n : 0); }
-    E = bucket_off[m]; V = bucket_voff[m]; finish_masks(); d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V); d_anchor_start = dalloc<u32>((size_t)m * NA); CUDA_CHECK(cudaMemset(d_anchor_start, 0xff, (size_t)m * NA * 4));
+    E = bucket_off[m]; V = bucket_voff[m]; finish_masks(); d_bucket_off = up(bucket_off); d_bucket_voff = up(bucket_voff); d_entries = dalloc<SeedEntry>(E); d_vals = dalloc<u64>(V);
     alloc_pbloom(); const int sh = 2 * (k - mask_prefix - anchor_prefix);
-    const int nm = hi - lo; if (nm > 0 && per) { const u64 tot = (u64)nm * per; k_synth_fill<<<(unsigned)((tot + 255) / 256), 256>>>(d_masks, lo, nm, mask_prefix, k, per, seed, d_entries, with_values ? d_vals : nullptr, d_pbloom, pbmask, sh); CUDA_CHECK(cudaGetLastError()); const u64 ta = (u64)nm * NA; k_synth_anchor<<<(unsigned)((ta + 255) / 256), 256>>>(d_bucket_off + lo, d_entries, nm, sh, (u32)NA, d_anchor_start + (size_t)lo * NA); CUDA_CHECK(cudaGetLastError()); }
-    make_anchor_bits(); batch_base.assign(2, 0); d_batch_base = up(batch_base); std::vector<u64> one(2, 0); d_g_off = up(one); d_g2bit = dalloc<u8>(64);
+    const int nm = hi - lo;
+    if (nm > 0 && per) { const u64 tot = (u64)nm * per; k_synth_fill<<<(unsigned)((tot + 255) / 256), 256>>>(d_masks, lo, nm, mask_prefix, k, per, seed, d_entries, with_values ? d_vals : nullptr, d_pbloom, pbmask, sh); CUDA_CHECK(cudaGetLastError());
+      const u64 ta = (u64)nm * NA; u32* d_full = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_full, ta * 4)); k_synth_anchor<<<(unsigned)((ta + 255) / 256), 256>>>(d_bucket_off + lo, d_entries, nm, sh, (u32)NA, d_full); CUDA_CHECK(cudaGetLastError());
+      u32* d_cnt = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_cnt, (size_t)nm * 4)); k_anchor_count<<<(nm + 127) / 128, 128>>>(d_full, nm, (u32)NA, d_cnt); CUDA_CHECK(cudaGetLastError()); std::vector<u32> counts(m, 0); CUDA_CHECK(cudaMemcpy(counts.data() + lo, d_cnt, (size_t)nm * 4, cudaMemcpyDeviceToHost)); cudaFree(d_cnt);
+      alloc_anchors(counts); u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); k_anchor_compact<<<nm, 128>>>(d_full, nm, lo, (u32)NA, d_anchor_cbase, d_anchor_bits, d_anchor_cum, d_anchor_cstart, d_bad); CUDA_CHECK(cudaGetLastError()); CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(d_full); cudaFree(d_bad); }
+    else alloc_anchors(std::vector<u32>(m, 0));
+    verify_anchors();
+    batch_base.assign(2, 0); d_batch_base = up(batch_base); std::vector<u64> one(2, 0); d_g_off = up(one); d_g2bit = dalloc<u8>(64);
   }
-  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_start, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits, (void*)d_pbloom}) if (p) cudaFree(p); }
+  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_cbase, (void*)d_anchor_cstart, (void*)d_anchor_cum, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits, (void*)d_pbloom}) if (p) cudaFree(p); }
 };

@@ -317,24 +317,32 @@ static void build_index(const std::string& out, size_t n_genomes, GetGenome get,
   fprintf(stderr, "[lmi-build] %zu genomes (%zu units in %zu batches), %lld bases, %zu seed values (%lld from desert filling), %d masks -> %s\n", n_input, n_units, n_batches, (long long)total_bases, all.size(), 2 * n_extra, o.masks, out.c_str());
 }
 
-// ------------------------------------------------------------------ synthetic queries from an index's genomes
-static void synth_queries(const std::string& index, int n, int len, uint64_t seed, const std::string& out, double max_sub, double max_indel) {
-  std::vector<GenomeRec> gs = read_genomes(batch_dir(index, 0) + "/genomes.bin"); IndexInfo info = read_info(index + "/info.toml");
+// ------------------------------------------------------------------ synthetic queries from an index's genomes, or straight from the synthetic collection
+// (SURVEY.md §8d): uniform random genome, uniform start, `len` bases, 0..max_sub substitutions + 0..max_indel indels, 50 % reverse-complemented.
+// `from_index` empty: genomes [glo, ghi) of the collection --synth F,S,G,seed,mc are regenerated on the fly (a shard's queries without its index).
+static void synth_queries(const std::string& index, int n, int len, uint64_t seed, const std::string& out, double max_sub, double max_indel,
+                          const std::string& synth = "", long long glo = 0, long long ghi = 0) {
+  std::vector<GenomeRec> gs; IndexInfo info; int F = 0, S = 0, G = 0, mc = 20; unsigned long long sd = 0; const bool direct = index.empty();
+  if (direct) { if (sscanf(synth.c_str(), "%d,%d,%d,%llu,%d", &F, &S, &G, &sd, &mc) < 4) die("synth-queries: --index or --synth F,S,G,seed[,max_contigs] needed"); if (ghi <= glo) { glo = 0; ghi = (long long)F * S; } }
+  else { gs = read_genomes(batch_dir(index, 0) + "/genomes.bin"); info = read_info(index + "/info.toml"); }
   FILE* f = fopen(out.c_str(), "w"); if (!f) die("cannot create " + out); uint64_t s = seed; static const char B[] = "ACGT";
   for (int q = 0; q < n; q++) {
-    std::string seq; int gi = 0, ci = 0; size_t st = 0; int tries = 0;
-    for (;; tries++) { gi = (int)(splitmix64(s) % gs.size()); const GenomeRec& g = gs[gi]; ci = (int)(splitmix64(s) % g.seq_sizes.size()); if ((int)g.seq_sizes[ci] >= len || tries > 1000) break; }
-    const GenomeRec& g = gs[gi]; size_t off = 0; for (int c = 0; c < ci; c++) off += g.seq_sizes[c] + info.contig_interval;
-    int L = std::min<int>(len, g.seq_sizes[ci]); st = splitmix64(s) % (g.seq_sizes[ci] - L + 1);
+    std::string seq, gid, contig; int ci = 0; size_t st = 0; int L = len;
+    if (direct) { InGenome g; for (int tries = 0;; tries++) { long long gi = glo + (long long)(splitmix64(s) % (uint64_t)(ghi - glo)); g = synth_genome((int)(gi / S), (int)(gi % S), S, G, sd, mc); ci = (int)(splitmix64(s) % g.seqs.size()); if ((int)g.seqs[ci].size() >= len || tries > 1000) break; }
+      gid = g.id; contig = g.seqs[ci]; L = std::min<int>(len, (int)contig.size()); st = splitmix64(s) % (contig.size() - L + 1); }
+    else { int gi = 0, tries = 0; for (;; tries++) { gi = (int)(splitmix64(s) % gs.size()); const GenomeRec& g = gs[gi]; ci = (int)(splitmix64(s) % g.seq_sizes.size()); if ((int)g.seq_sizes[ci] >= len || tries > 1000) break; }
+      const GenomeRec& g = gs[gi]; size_t off = 0; for (int c = 0; c < ci; c++) off += g.seq_sizes[c] + info.contig_interval; L = std::min<int>(len, g.seq_sizes[ci]); st = splitmix64(s) % (g.seq_sizes[ci] - L + 1); gid = g.id;
+      contig.resize(L); for (int i = 0; i < L; i++) { size_t p = off + st + i; contig[i] = B[(g.twobit[p >> 2] >> (6 - 2 * (p & 3))) & 3]; } }
+    const size_t c0 = direct ? st : 0;
     double u = (double)(splitmix64(s) >> 11) / 9007199254740992.0 * max_sub, ind = (double)(splitmix64(s) >> 11) / 9007199254740992.0 * max_indel;
     for (int i = 0; i < L; i++) {
-      size_t p = off + st + i; int c = (g.twobit[p >> 2] >> (6 - 2 * (p & 3))) & 3; double r = (double)(splitmix64(s) >> 11) / 9007199254740992.0;
+      int c = (int)base2bit((uint8_t)contig[c0 + i]); double r = (double)(splitmix64(s) >> 11) / 9007199254740992.0;
       if (r < ind) { if (splitmix64(s) & 1) continue; seq.push_back(B[splitmix64(s) & 3]); }
       if (r >= ind && r < ind + u) c = (c + 1 + (int)(splitmix64(s) % 3)) & 3;
       seq.push_back(B[c]);
     }
     bool rc = splitmix64(s) & 1; if (rc) { std::reverse(seq.begin(), seq.end()); for (char& c : seq) c = (c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A'); }
-    fprintf(f, ">q%06d g=%s c=%d s=%zu rc=%d\n%s\n", q, g.id.c_str(), ci, st, (int)rc, seq.c_str());
+    fprintf(f, ">q%06d g=%s c=%d s=%zu rc=%d\n%s\n", q, gid.c_str(), ci, st, (int)rc, seq.c_str());
   }
   fclose(f);
 }
@@ -370,8 +378,9 @@ int main(int argc, char** argv) {
           return g; }, o);
       } else die("index: need --synth or --in-list");
     } else if (cmd == "synth-queries") {
+      long long lo = 0, hi = 0; std::string rg = arg(argc, argv, "--genome-range", ""); if (!rg.empty() && sscanf(rg.c_str(), "%lld,%lld", &lo, &hi) != 2) die("--genome-range lo,hi");
       synth_queries(arg(argc, argv, "--index", ""), atoi(arg(argc, argv, "--n", "100")), atoi(arg(argc, argv, "--len", "1000")), strtoull(arg(argc, argv, "--seed", "20260925"), 0, 10),
-                    arg(argc, argv, "--out", "queries.fasta"), atof(arg(argc, argv, "--max-sub", "0.10")), atof(arg(argc, argv, "--max-indel", "0.01")));
+                    arg(argc, argv, "--out", "queries.fasta"), atof(arg(argc, argv, "--max-sub", "0.10")), atof(arg(argc, argv, "--max-indel", "0.01")), arg(argc, argv, "--synth", ""), lo, hi);
     } else if (cmd == "synth-fasta") {  // dump synthetic genomes as FASTA files (small test sets)
       int F, S, G, mc = 20; unsigned long long sd; std::string synth = arg(argc, argv, "--synth", ""); if (sscanf(synth.c_str(), "%d,%d,%d,%llu,%d", &F, &S, &G, &sd, &mc) < 4) die("--synth F,S,G,seed[,max_contigs]");
       std::string out = arg(argc, argv, "--out", "refs"); mkdir_p(out);
