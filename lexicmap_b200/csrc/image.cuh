@@ -172,7 +172,7 @@ struct Image {
     size_t freeb = 0, totalb = 0; CUDA_CHECK(cudaMemGetInfo(&freeb, &totalb)); const bool keep_raw = raw_total * 4 < freeb && !getenv("LMG_INGEST_REREAD");
     ShardSel S{d_batch_base, n_shards, shard}; u64 *d_nk = nullptr, *d_nv = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_nk, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMalloc((void**)&d_nv, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMemset(d_nk, 0, sizeof(u64) * (m + 1))); CUDA_CHECK(cudaMemset(d_nv, 0, sizeof(u64) * (m + 1)));
     std::vector<ChunkDev> kept(info.chunks); std::vector<u32> anchor_counts(m, 0);
-    for (int c = 0; c < info.chunks; c++) { ChunkDev cd = upload_chunk(c); for (int i = 0; i < cd.nm; i++) anchor_counts[cd.mask0 + i] = cd.h_xn[i] ? cd.h_xn[i] - 1 : 0;   // one .idx record per present anchor after the header record if (cd.nm) { k_kv_count<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_nk + cd.mask0, d_nv + cd.mask0); CUDA_CHECK(cudaGetLastError()); }
+    for (int c = 0; c < info.chunks; c++) { ChunkDev cd = upload_chunk(c); for (int i = 0; i < cd.nm; i++) anchor_counts[cd.mask0 + i] = cd.h_xn[i] ? cd.h_xn[i] - 1 : 0;   /* one .idx record per present anchor after the header record */ if (cd.nm) { k_kv_count<<<(cd.nm + 63) / 64, 64>>>(cd.d, cd.x, cd.xoff, cd.xn, cd.nm, cd.vb, S, d_nk + cd.mask0, d_nv + cd.mask0); CUDA_CHECK(cudaGetLastError()); }
       if (keep_raw) kept[c] = cd; else { CUDA_CHECK(cudaDeviceSynchronize()); free_chunk(cd); } }
     CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<u64> nk(m + 1), nv(m + 1), bucket_off(m + 1, 0), bucket_voff(m + 1, 0); CUDA_CHECK(cudaMemcpy(nk.data(), d_nk, sizeof(u64) * m, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(nv.data(), d_nv, sizeof(u64) * m, cudaMemcpyDeviceToHost)); cudaFree(d_nk); cudaFree(d_nv);

@@ -360,3 +360,24 @@ def test_desert_filling_closes_seed_gaps(tmp_path):
         assert len(big) <= 4 and all(d >= 1000 for d in big if d > 400)   # only the 1000-bp contig intervals (<= 2 per genome) stay wide
         assert len(pb) > 1.5 * len(pa)
     assert "max-seed-dist = 100" in open(os.path.join(b, "info.toml")).read().replace('"', "") or "100" in open(os.path.join(b, "info.toml")).read()
+
+
+def test_no_statement_hides_behind_a_line_comment():
+    """the CUDA sources use long lines; a `//` comment in the middle of one silently disables whatever follows it (it happened twice: a
+    kernel launch vanished without a compile error). Nothing that looks like a launch or a checked call may follow a `//` on its line."""
+    import glob
+    bad = []
+    for f in glob.glob(os.path.join(ROOT, "lexicmap_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "oracle", "*.?pp")):
+        for n, line in enumerate(open(f, errors="replace"), 1):
+            code, in_str, i = line, False, 0
+            while i < len(code) - 1:
+                c = code[i]
+                if c == '"' and (i == 0 or code[i - 1] != "\\"):
+                    in_str = not in_str
+                if not in_str and code[i:i + 2] == "//":
+                    rest = code[i + 2:]
+                    if re.search(r"<<<[^>]*>>>|CUDA_CHECK\(|KERNEL_CHECK\(\)", rest):
+                        bad.append("%s:%d" % (os.path.basename(f), n))
+                    break
+                i += 1
+    assert not bad, "code after a line comment: " + ", ".join(bad)
