@@ -416,6 +416,9 @@ def run_search(a, rank, world, local):
         idx.search_count(packed, p1)
         iso.append(idx.timing()[0][8])
     t_iso = float(np.mean(iso[1:])) * 1e-3
+    # the device's random 32-byte-sector read rate (the physical ceiling of a lookup made of dependent random sectors), measured beside the kernel
+    from lexicmap_b200.api import gather_bench
+    gb = gather_bench(device=local, gbytes=8.0)
     # ---- CPU baseline on this box (bounded sample)
     threads = usable_cpus()[0]
     cpu_s = float(os.environ.get("LMG_BENCH_CPU_S", 15.0))   # 0 skips the CPU leg (parameter sweeps only; the default run always reports it)
@@ -436,6 +439,8 @@ def run_search(a, rank, world, local):
                         "model": "SURVEY.md §8d: per probe 12 + 32 + 32*ceil(log2(n_a+1)) + 32*ceil(16h/32) + 16*h_out bytes", "algorithmic_bytes_per_step": alg_bytes, "probes_per_step": float(cnt[1]) * scale, "kernel_ms_per_step": t_probe * 1e3, "launches_per_step": config_lanes,
                         "alone": {"kernel_ms": t_iso * 1e3, "achieved": alg_bytes / t_iso / 1e9 if t_iso > 0 else 0.0, "frac": (alg_bytes / t_iso / 1e9 / peak) if t_iso > 0 else 0.0, "note": "same batch through one lane: no concurrent kernels"},
                         "r01_model": {"note": "round 1's byte model (24+32 B per probe, 32 B per search step taken, 16 B per entry scanned, 48 B per hit): kept for continuity with BENCH_r01", "algorithmic_bytes_per_step": r01_bytes, "frac": (r01_bytes / t_probe / 1e9 / peak) if t_probe > 0 else 0.0},
+                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): this, not the streaming peak, bounds a lookup whose accesses are dependent random sectors",
+                                                  "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak, "kernel_alone_vs_ceiling": (alg_bytes / t_iso / 1e9 / gb["gbs_at_32B"]) if t_iso > 0 else 0.0, "kernel_in_region_vs_ceiling": achieved / gb["gbs_at_32B"]},
                         "peak_source": peak_src},
            "roofline_wfa": {"bound": "issue", "kernel": "k_wfa_fast + k_wfa_bt (wavefront alignment: forward pass and backtrace)", "kernel_ms_per_step": wfa_ms, "alignments_per_step": int(kcnt[9]), "share_of_kernel_time": None,
                             "note": "instruction-issue bound (ncu: issue-active ~78 %, DRAM < 15 % of peak); see profiles/ for the ncu capture"},

@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
     { const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
       if (nqw + nA + ntw <= WR_SEQW) { u64* sq = seqb; for (u32 i = lane; i < nqw + nA; i += 32) sq[i] = Q[i]; for (u32 i = lane; i < ntw; i += 32) sq[nqw + nA + i] = T[i]; __syncwarp(); Q = sq; A = sq + nqw; T = sq + nqw + nA; } }
     WfaOut Rz; Rz.qbegin = Rz.qend = Rz.tbegin = Rz.tend = Rz.alen = Rz.matches = Rz.gaps = Rz.bscore = Rz.has_m = 0; Rz.wscore = 0; Rz.status = 0; Rz.ops_n = 0; Rz.ops_off = 0;
-    if (plen >= WR_MAXLEN || tlen >= WR_MAXLEN || plen <= 0 || tlen <= 0 || lmax < 2) { if (lane == 0) { Rz.status = 1; outs[jb] = Rz; } __syncwarp(); continue; }
+    if (plen >= WR_MAXLEN || tlen >= WR_MAXLEN || plen <= 0 || tlen <= 0 || lmax < 2) { if (lane == 0) { Rz.status = 1; Rz.wscore = -3; outs[jb] = Rz; } __syncwarp(); continue; }
     auto extend = [&](i32 kk, i32 h) { i32 v = h - kk; for (;;) { i32 rem = min(plen - v, tlen - h); if (rem <= 0) break; u64 x = fetch64(Q, v) ^ fetch64(T, h); if (amb) x |= fetch64(A, v); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); v += n; h += n; if (n < 32) break; } return h; };
     // one cell: recurrences + extension + the backtrace word (decisions from the unfiltered neighbour values: offset first, then mismatch(9) > D-ext(6) > D-open(5) > I-ext(2) > I-open(1))
     auto cell = [&](i32 k, bool live, i32 c_m2, i32 m4l, i32 i1l, i32 m4r, i32 d1r) { WrCell c; c.om = -1; c.oi = -1; c.od = -1; c.dv = INT32_MAX; c.word = 0;
@@ -1189,16 +1189,16 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
     auto at = [&](const i32 (&v)[WR_NS], i32 j) { i32 r = -1;   // value on window position j, warp-uniform j
 #pragma unroll
       for (int t = 0; t < WR_NS; t++) { const i32 x = __shfl_sync(FULLMASK, v[t], j & 31); if ((j >> 5) == t) r = x; } return r; };
-    i32 L = 0; bool done = false, overflow = false; { const i32 v0 = at(m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }
+    i32 L = 0, why = 0; bool done = false, overflow = false; { const i32 v0 = at(m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }   // why: reason for leaving the register path (-1 level capacity, -2 band wider than the window, -3 not eligible)
     while (!done) {
-      L++; if (L >= lmax) { overflow = true; break; }
+      L++; if (L >= lmax) { overflow = true; why = -1; break; }
       const bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; const bool allnull = nx && no && ni && nd;
       if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
       // the window must hold this level's range and the ranges of the levels still in registers on positions 1..WR_W-2 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
       i32 slo = allnull ? INT32_MAX : lo, shi = allnull ? INT32_MIN : hi; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { slo = min(slo, hlo[i]); shi = max(shi, hhi[i]); }
       if (slo <= shi) { const i32 span = shi - slo + 1;
-        if (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30)) { if (span > WR_W - 2) { overflow = true; break; }
+        if (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30)) { if (span > WR_W - 2) { overflow = true; why = -2; break; }
           const i32 room = span <= 30 ? 30 : (span <= 62 ? 62 : (span <= 94 ? 94 : WR_W - 2)); const i32 nkb = slo - 1 - (room - span) / 2, dlt = nkb - kb;   // centred in as few slots as the span needs
           const int sl = (lane + (dlt & 31)) & 31, carry = (lane + (dlt & 31)) >> 5, q = dlt >> 5;   // new position p takes old position p + dlt: old lane sl, old slot s + q + carry
           auto shift = [&](i32 (&v)[WR_NS]) { i32 x[WR_NS];
@@ -1252,7 +1252,7 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
       if (!allnull && kend >= lo && kend <= hi) { const i32 v = at(m1, kend - kb); done = (v >= tlen); }
     }
-    if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = 2 * L; outs[jb] = Rz; }
+    if (lane == 0) { Rz.status = overflow ? 1 : 0; Rz.wscore = overflow ? why : 2 * L; outs[jb] = Rz; }
     __syncwarp();
   }
 }
@@ -1319,7 +1319,9 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
             CUDA_CHECK(cudaStreamSynchronize(st));   // the round's buffers go back to the arena
             j0 += n; rounds++; round_max = std::max(round_max, n); } }
         std::vector<WfaOut> o = d_out.to_host(nj); std::vector<char> sk(nj, 0); for (u32 j : skipped) sk[j] = 1;
-        for (u32 j = 0; j < nj; j++) { if (sk[j] || o[j].status == 1) rest.push_back(j); else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
+        u32 why[5] = {0, 0, 0, 0, 0};
+        for (u32 j = 0; j < nj; j++) { if (sk[j] || o[j].status == 1) { rest.push_back(j); why[sk[j] ? 4 : (o[j].wscore == -1 ? 1 : o[j].wscore == -2 ? 2 : o[j].wscore == -3 ? 3 : 0)]++; } else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
+        if (g_lap && g_lap->on && !rest.empty()) fprintf(stderr, "[lmg host] register WFA pass: %zu of %u alignments left (op scratch %u, level capacity %u, band > %d diagonals %u, not eligible %u, slab over budget %u)\n", rest.size(), nj, why[0], why[1], WR_W - 2, why[2], why[3], why[4]);
         counters[14] = round_max; (void)rounds; if (g_lap) (*g_lap)("wfa register pass"); }
       else { rest.resize(nj); std::iota(rest.begin(), rest.end(), 0u); }
       counters[9] = nj; counters[10] = rest.size(); counters[15] = (u64)lmax;
