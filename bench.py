@@ -254,6 +254,9 @@ def run_search(a, rank, world, local):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     search_kw, total_bases_all = {}, None
+    # the device's random 32-byte-sector read rate (the physical ceiling of a lookup made of dependent random sectors), measured before the image and the arenas fill the memory
+    from lexicmap_b200.api import gather_bench
+    gb = gather_bench(device=local, gbytes=8.0) if rank == 0 else None
     if cfgname == "c2":
         if rank == 0:
             ensure_c2(0)
@@ -268,9 +271,21 @@ def run_search(a, rank, world, local):
                                            "sharding": "by query, index replicated" if a.gpus > 1 else "single GPU", "seeds": [C2["genome_seed"], C2["query_seed"]]})
         scaling = "weak"
     elif cfgname == "c3":
-        idx_dir = ensure_c3(rank, world)
-        if dist:
-            dist.barrier()
+        # the shard indexes are written in LMG_C3_WAVES groups of ranks so that the scratch disk holds world / waves of them at a time
+        # (a shard of 12,500 genomes is ~10 GB on disk; ranks other than 0 delete theirs once the image is in HBM)
+        waves = max(1, int(os.environ.get("LMG_C3_WAVES", 1)))
+        idx_dir, idx = None, None
+        for wv in range(waves):
+            if rank % waves == wv:
+                idx_dir = ensure_c3(rank, world)
+                t0 = time.time()
+                idx = lexicmap_b200.Index(idx_dir, device=local)
+                log("rank %d: image resident in %.1fs (%.2f GB, %d keys, %d values) %s" % (rank, time.time() - t0, idx.info.image_bytes / 1e9, idx.info.seed_keys, idx.info.seed_values, idx.load_times()))
+                if rank != 0 and waves > 1:
+                    import shutil
+                    shutil.rmtree(idx_dir, ignore_errors=True)
+            if dist:
+                dist.barrier()
         c3_queries(world, part=rank)   # every rank writes the part cut from its own shard's genomes, then all read all parts (same box)
         if dist:
             dist.barrier()
@@ -299,9 +314,10 @@ def run_search(a, rank, world, local):
         workload = "%d simulated ONT reads (%s x%d; 67-90,376 bp) vs the reference's 15 demo genomes, flags of demo/README.md:365-368; BASELINE.json configs[3] on the demo index" % (len(seqs), os.path.basename(qf), rep)
         config = base_config(a, workload, {"queries_per_gpu": len(seqs), "genomes": 15, "masks": 20000, "sharding": "by query, index replicated" if a.gpus > 1 else "single GPU", "flags": search_kw})
         scaling = "weak"
-    t0 = time.time()
-    idx = lexicmap_b200.Index(idx_dir, device=local)
-    log("rank %d: image resident in %.1fs (%.2f GB, %d keys, %d values) %s" % (rank, time.time() - t0, idx.info.image_bytes / 1e9, idx.info.seed_keys, idx.info.seed_values, idx.load_times()))
+    if cfgname != "c3":
+        t0 = time.time()
+        idx = lexicmap_b200.Index(idx_dir, device=local)
+        log("rank %d: image resident in %.1fs (%.2f GB, %d keys, %d values) %s" % (rank, time.time() - t0, idx.info.image_bytes / 1e9, idx.info.seed_keys, idx.info.seed_values, idx.load_times()))
     if cfgname == "c3":   # e-values over the whole collection
         tb = torch.tensor([float(idx.info.input_bases)], device="cuda", dtype=torch.float64)
         if dist:
@@ -416,13 +432,14 @@ def run_search(a, rank, world, local):
         idx.search_count(packed, p1)
         iso.append(idx.timing()[0][8])
     t_iso = float(np.mean(iso[1:])) * 1e-3
-    # the device's random 32-byte-sector read rate (the physical ceiling of a lookup made of dependent random sectors), measured beside the kernel
-    from lexicmap_b200.api import gather_bench
-    gb = gather_bench(device=local, gbytes=8.0)
     # ---- CPU baseline on this box (bounded sample)
     threads = usable_cpus()[0]
     cpu_s = float(os.environ.get("LMG_BENCH_CPU_S", 15.0))   # 0 skips the CPU leg (parameter sweeps only; the default run always reports it)
-    cpu_bps, cpu_n, cpu_dt, _ = cpu_port_throughput(idx_dir, seqs, threads, target_s=cpu_s, params=search_kw) if cpu_s > 0 else (0.0, 0, 0.0, None)
+    cpu_seqs = seqs
+    if cfgname == "c3" and world > 1:   # the batch is part 0 | part 1 | ...: the CPU sample takes the parts in turn so that 1/world of it hits shard 0's genomes, as in the whole job
+        per = len(seqs) // world
+        cpu_seqs = [seqs[p * per + i] for i in range(per) for p in range(world)]
+    cpu_bps, cpu_n, cpu_dt, _ = cpu_port_throughput(idx_dir, cpu_seqs, threads, target_s=cpu_s, params=search_kw) if cpu_s > 0 else (0.0, 0, 0.0, None)
     cpu_note = "%d of the %d queries, %.1fs (C++ port of the reference path; Go toolchain absent)" % (cpu_n, len(seqs), cpu_dt)
     if cfgname == "c3" and world > 1:
         cpu_bps /= world
@@ -539,10 +556,10 @@ def run_reference(a):
         world = max(1, a.gpus)
         idx_dir = ensure_c3(0, world)
         ids, seqs = [], []
-        for qf in c3_queries(world):   # the whole batch: part 0 hits shard 0's genomes, the other parts only probe it (as on every GPU rank)
-            i2, s2 = read_fasta(qf)
-            ids += i2
-            seqs += s2
+        parts = [read_fasta(qf)[1] for qf in c3_queries(world)]   # the whole batch: part 0 hits shard 0's genomes, the other parts only probe it (as on every GPU rank)
+        per = min(len(x) for x in parts)
+        seqs = [parts[p][i] for i in range(per) for p in range(world)]   # parts in turn: any prefix of the batch is a fair sample of the whole job
+        ids = ["q%d" % i for i in range(len(seqs))]
         config = base_config(a, "BASELINE.json configs[2]: %d x %d-bp queries vs %d genomes, CPU port against shard 0 of %d" % (C3["n_queries"], C3["query_len"], C3["genomes"], world), {"genomes": C3["genomes"]})
         div = world
         note_extra = "; measured against shard 0 (1/%d of the genomes) and divided by %d" % (world, world)

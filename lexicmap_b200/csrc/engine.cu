@@ -1296,7 +1296,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
       i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
       const int lmax = (int)std::min<i64>(WF_LMAX * 2, std::max<i64>(256, ((i64)(0.8 * maxlen) + 63) / 64 * 64));
-      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.35), 64ull << 30) / (u64)std::max(1, active_lanes);
+      const size_t tb_ = total_mem; const u64 budgetF = std::min<u64>((u64)(tb_ * 0.25), 36ull << 30) / (u64)std::max(1, active_lanes);
       if (g_lap) (*g_lap)("wfa prep kernel");
       // pass 1, every job: the register kernel (one diagonal per lane, 128 B of backtrace words per level). Rounds only when the slabs of all jobs exceed the budget.
       std::vector<u32> rest;   // jobs whose band left the 32-lane window (or too deep / too long): pass 2
