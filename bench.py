@@ -274,6 +274,9 @@ def run_search(a, rank, world, local):
         # the shard indexes are written in LMG_C3_WAVES groups of ranks so that the scratch disk holds world / waves of them at a time
         # (a shard of 12,500 genomes is ~10 GB on disk; ranks other than 0 delete theirs once the image is in HBM)
         waves = max(1, int(os.environ.get("LMG_C3_WAVES", 1)))
+        sim = int(os.environ.get("LMG_C3_SIM_WORLD", 0))   # profiling aid: one GPU does exactly the work of rank 0 of a `sim`-GPU run (shard 0 of `sim`, the whole batch)
+        if sim > 1 and world == 1:
+            world = sim
         idx_dir, idx = None, None
         for wv in range(waves):
             if rank % waves == wv:
