@@ -550,6 +550,18 @@ __global__ void k_tree_offsets(const u32* __restrict__ pos, const u64* __restric
 struct WinItem { u32 q, g; i32 tBegin, tEnd, W, qBegin, qEnd; u32 rc; i32 mp; u32 chain; };  // mp = min prefix for this window (lib-seq_compare.go:339-348)
 
 __device__ __forceinline__ u32 win_base(const u8* __restrict__ g2, i32 tBegin, i32 tEnd, u32 rc, i32 i) { return rc ? 3u - get_base(g2, (u64)(tEnd - i)) : get_base(g2, (u64)(tBegin + i)); }
+// 16 window bases [16x, 16x+16) of the oriented window as one word (first base in the top bits), zero beyond the window: five byte loads and a shift instead of
+// sixteen single-base extractions; the minus strand reverses the 2-bit groups of the mirrored genome word and complements them
+__device__ __forceinline__ u32 gword16(const u8* __restrict__ g2, i64 pos) {   // genome bases [pos, pos+16), pos >= 0; reads 5 bytes (the payload arrays are padded)
+  const u8* p = g2 + (pos >> 2); const u64 v = ((u64)p[0] << 32) | ((u64)p[1] << 24) | ((u64)p[2] << 16) | ((u64)p[3] << 8) | (u64)p[4]; return (u32)(v >> (8 - 2 * (pos & 3))); }
+__device__ __forceinline__ u32 win_word16(const u8* __restrict__ g2, i32 tBegin, i32 tEnd, u32 rc, i32 W, i32 x) {
+  const i32 i0 = x * 16; if (i0 >= W) return 0u; const i32 n = min(16, W - i0); u32 v;
+  if (!rc) v = gword16(g2, (i64)tBegin + i0);
+  else { const i64 hi = (i64)tEnd - i0, lo = hi - 15;   // window base i0 + j = complement of genome base hi - j
+    u32 g; if (lo >= 0) g = gword16(g2, lo); else g = gword16(g2, 0) >> (2 * (int)(-lo));   // genome bases [lo, hi] right-aligned; bases before the genome start read as 0 and fall outside n anyway
+    u32 r = __brev(g); r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1); v = ~r; }
+  return n == 16 ? v : (v & ~((1u << (2 * (16 - n))) - 1u));
+}
 __device__ __forceinline__ int lcp31(u64 a, u64 b) { return a == b ? 31 : min(31, (__clzll(a ^ b) >> 1) - 1); }   // K = 31: LZ/2 + K - 32
 
 // tree.Search emulated on the sorted table, incl. the uint8 wrap in the mismatch branch (tree/tree.go:498-501)
@@ -676,12 +688,12 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
   // Work compaction: most window positions fail the Bloom / prefix pre-check, and of those that search the table only a few take the
   // radix-tree emulation. Doing everything in one pass ran at ~10 active lanes per instruction; instead positions that pass the pre-check
   // are queued (position << 1 | strand) and searched 256 at a time, and the rare slow-path searches are queued again.
-  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nfast, nslow;
+  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nfast, nslow; __shared__ u32 s_wc[32];
   for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
     __syncthreads();   // previous window fully consumed (and, first time, table loaded)
     i32 nw = (w.W + 15) / 16 + 2;
-    for (i32 x = threadIdx.x; x < nw; x += NT) { u32 v = 0; for (int j = 0; j < 16; j++) { i32 i = x * 16 + j; u32 b = (i < w.W) ? win_base(g2, w.tBegin, w.tEnd, w.rc, i) : 0; v = (v << 2) | b; } sw[x] = v; }
+    for (i32 x = threadIdx.x; x < nw; x += NT) sw[x] = win_word16(g2, w.tBegin, w.tEnd, w.rc, w.W, x);
     if (threadIdx.x == 0) { s_base = 0; nfast = 0; nslow = 0; } __syncthreads();
     const i32 np = w.W - K + 1; u64* const out_base = a_lo + base0;
     for (i32 base = 0;; base += NT) {
@@ -691,7 +703,11 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
           if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
             u32 hb = ((u32)(km >> 40) * 2654435761u) >> BSH; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
             hb = ((u32)(kr >> 40) * 2654435761u) >> BSH; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
-        pa3_push(qfast, &nfast, c1, (u32)idx << 1, lane); pa3_push(qfast, &nfast, c2, ((u32)idx << 1) | 1u, lane); }
+        // queue the candidates of this slice with a block-wide scan (ballots -> per-warp counts in shared memory -> prefix over the warps): the former
+        // warp-aggregated atomicAdd on one shared counter serialised up to 64 same-address atomics per slice of a 1,024-thread CTA
+        const u32 b1 = __ballot_sync(FULLMASK, c1), b2 = __ballot_sync(FULLMASK, c2), old = nfast; if (lane == 0) s_wc[threadIdx.x >> 5] = __popc(b1) + __popc(b2); __syncthreads();
+        { const u32 wv = (lane < NT / 32) ? s_wc[lane] : 0u; const u32 before = __reduce_add_sync(FULLMASK, lane < (int)(threadIdx.x >> 5) ? wv : 0u), tot = __reduce_add_sync(FULLMASK, wv); const u32 wbase = old + before;
+          if (c1) qfast[wbase + __popc(b1 & ((1u << lane) - 1))] = (u32)idx << 1; if (c2) qfast[wbase + __popc(b1) + __popc(b2 & ((1u << lane) - 1))] = ((u32)idx << 1) | 1u; if (threadIdx.x == 0) nfast = old + tot; } }
       // drain: full chunks of 256 candidates while scanning, everything at the end. Every thread reads the counters between two barriers.
       for (;;) {
         __syncthreads(); const u32 nf = nfast, ns0 = nslow; __syncthreads();
