@@ -688,14 +688,20 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
   // Work compaction: most window positions fail the Bloom / prefix pre-check, and of those that search the table only a few take the
   // radix-tree emulation. Doing everything in one pass ran at ~10 active lanes per instruction; instead positions that pass the pre-check
   // are queued (position << 1 | strand) and searched 256 at a time, and the rare slow-path searches are queued again.
-  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nfast, nslow; __shared__ u32 s_wc[32];
+  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nslow; __shared__ u32 s_wc[2][32];
   for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
     __syncthreads();   // previous window fully consumed (and, first time, table loaded)
     i32 nw = (w.W + 15) / 16 + 2;
     for (i32 x = threadIdx.x; x < nw; x += NT) sw[x] = win_word16(g2, w.tBegin, w.tEnd, w.rc, w.W, x);
-    if (threadIdx.x == 0) { s_base = 0; nfast = 0; nslow = 0; } __syncthreads();
+    if (threadIdx.x == 0) { s_base = 0; nslow = 0; } __syncthreads();
     const i32 np = w.W - K + 1; u64* const out_base = a_lo + base0;
+    // The scan queues candidates, the drain searches them 1 CTA-width at a time. Barrier stalls were 24 waiting warps per issue slot in the 1,024-thread
+    // variant (ncu), so the queue length lives in a REGISTER that every thread advances identically (nq; the per-slice total comes from the same
+    // shared-memory warp counts in every warp), the warp counts are double-buffered, and the slow-path queue is only looked at when some thread
+    // pushed to it (__syncthreads_or): a slice costs one barrier, a drain two.
+    u32 nq = 0; int par = 0; bool any_slow_window = false;
+    auto slow_drain = [&](u32 ns0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } };
     for (i32 base = 0;; base += NT) {
       const bool more = (base < np) && tn;   // uniform: another slice of window positions to scan
       if (more) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
@@ -703,29 +709,25 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
           if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
             u32 hb = ((u32)(km >> 40) * 2654435761u) >> BSH; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
             hb = ((u32)(kr >> 40) * 2654435761u) >> BSH; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
-        // queue the candidates of this slice with a block-wide scan (ballots -> per-warp counts in shared memory -> prefix over the warps): the former
-        // warp-aggregated atomicAdd on one shared counter serialised up to 64 same-address atomics per slice of a 1,024-thread CTA
-        const u32 b1 = __ballot_sync(FULLMASK, c1), b2 = __ballot_sync(FULLMASK, c2), old = nfast; if (lane == 0) s_wc[threadIdx.x >> 5] = __popc(b1) + __popc(b2); __syncthreads();
-        { const u32 wv = (lane < NT / 32) ? s_wc[lane] : 0u; const u32 before = __reduce_add_sync(FULLMASK, lane < (int)(threadIdx.x >> 5) ? wv : 0u), tot = __reduce_add_sync(FULLMASK, wv); const u32 wbase = old + before;
-          if (c1) qfast[wbase + __popc(b1 & ((1u << lane) - 1))] = (u32)idx << 1; if (c2) qfast[wbase + __popc(b1) + __popc(b2 & ((1u << lane) - 1))] = ((u32)idx << 1) | 1u; if (threadIdx.x == 0) nfast = old + tot; } }
-      // drain: full chunks of 256 candidates while scanning, everything at the end. Every thread reads the counters between two barriers.
-      for (;;) {
-        __syncthreads(); const u32 nf = nfast, ns0 = nslow; __syncthreads();
-        const bool go = more ? (nf >= NT) : (nf > 0);
-        if (!go) { if (!more && ns0 > 0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } }
-          break; }
-        const u32 take = min(nf, (u32)NT), start = nf - take; bool slow = false; u32 e = 0;
+        // queue the candidates of this slice with a block-wide scan (ballots -> per-warp counts in shared memory -> prefix over the warps)
+        const u32 b1 = __ballot_sync(FULLMASK, c1), b2 = __ballot_sync(FULLMASK, c2); if (lane == 0) s_wc[par][threadIdx.x >> 5] = __popc(b1) + __popc(b2); __syncthreads();
+        const u32 wv = (lane < NT / 32) ? s_wc[par][lane] : 0u; const u32 before = __reduce_add_sync(FULLMASK, lane < (int)(threadIdx.x >> 5) ? wv : 0u), tot = __reduce_add_sync(FULLMASK, wv); const u32 wbase = nq + before;
+        if (c1) qfast[wbase + __popc(b1 & ((1u << lane) - 1))] = (u32)idx << 1; if (c2) qfast[wbase + __popc(b1) + __popc(b2 & ((1u << lane) - 1))] = ((u32)idx << 1) | 1u; nq += tot; par ^= 1; }
+      // drain: full chunks while scanning, everything at the end
+      while (more ? (nq >= (u32)NT) : (nq > 0)) {
+        __syncthreads();   // the queue entries written above (by other warps) are visible
+        const u32 take = min(nq, (u32)NT), start = nq - take; bool slow = false; u32 e = 0;
         if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = pa3_key(sw, e, ttt); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
           while (x < y) { u32 m = (x + y) >> 1; if (sk[m] < left) x = m + 1; else y = m; } u32 en = x; while (en < tn && sk[en] <= right) en++;
           if (en > x) pa3_emit(sk, sv, e, key, x, en, begin, end, &s_base, cap, out_base); else slow = quirk_possible(sk, tn, x, key, p); }
-        __syncthreads(); if (threadIdx.x == 0) nfast = start; pa3_push(qslow, &nslow, slow, e, lane);
-        __syncthreads(); const u32 ns1 = nslow; __syncthreads();
-        if (ns1 >= NT) {   // the rare radix-tree emulations, again a full chunk at a time
-          for (u32 ns = ns1; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; }
-          __syncthreads(); if (threadIdx.x == 0) nslow = 0; }
+        nq = start;
+        if (__syncthreads_or(slow)) {   // (also the barrier between reading this chunk and the next slice overwriting it) some radix-tree emulations to queue: rare
+          any_slow_window = true; pa3_push(qslow, &nslow, slow, e, lane); __syncthreads(); const u32 ns1 = nslow; __syncthreads();
+          if (ns1 >= (u32)NT) { slow_drain(ns1); __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } }
       }
       if (!more) break;
     }
+    if (any_slow_window) { __syncthreads(); const u32 ns0 = nslow; __syncthreads(); if (ns0 > 0) slow_drain(ns0); }
     __syncthreads(); if (threadIdx.x == 0) counts[it] = s_base;
   }
 }
