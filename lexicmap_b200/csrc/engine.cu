@@ -671,12 +671,18 @@ __device__ __forceinline__ void pa3_emit(const u64* sk, const u32* sv, u32 e, u6
 // ---- K4 v3: one CTA per QUERY. The query's sorted (k-mer, loc) table is staged in shared memory once and reused by all of the query's
 // target windows (typically one per candidate genome), so every table probe is a shared-memory binary search instead of an L2 round trip.
 // Windows are packed into shared memory one at a time. Queries whose table does not fit use k_pa_anchors2 (table in L2).
-template <int NT>   // threads per CTA: 256, or 1024 when the table leaves room for a single CTA per SM anyway (5-kb queries)
+// Named-barrier helpers: a CTA of NG independent groups, each working on its own window (barrier ids 1..NG; id 0 = __syncthreads).
+__device__ __forceinline__ void gbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ bool gbar_or(int id, int n, bool p) { u32 r; asm volatile("{ .reg .pred q, qr; setp.ne.u32 q, %3, 0; bar.red.or.pred qr, %1, %2, q; selp.u32 %0, 1, 0, qr; }" : "=r"(r) : "r"(id), "r"(n), "r"((u32)p) : "memory"); return r != 0; }
+template <int NT>   // threads per CTA: 256, or 1024 when the table leaves room for a single CTA per SM anyway (5-kb queries). The 1,024-thread CTA runs as TWO groups
+                    // of 512 threads, each on its own window with its own named barrier: with one CTA per SM a whole-CTA barrier left nothing to issue (ncu: 24 warps
+                    // waiting at the barrier per issue slot, issue-active 23 %); now one group scans while the other waits.
 __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ items, const u32* __restrict__ qlist, const u32* __restrict__ qitem_beg, const u32* __restrict__ qitem_end, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
-                                                     const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn) {
+                                                     const u64* __restrict__ tkeys, const u32* __restrict__ tvals, const u32* __restrict__ toff, const u64* __restrict__ abeg, const u32* __restrict__ acap, u32* __restrict__ counts, u64* __restrict__ a_lo, u32 max_tn, u32 win_words) {
   constexpr int BW = NT >= 1024 ? 4096 : 1024, BSH = NT >= 1024 ? 15 : 17;   // Bloom filter over hashed 11-base prefixes: 32 kbit for tables of up to ~4,000 rows, 128 kbit for the big-table variant (a 10,000-row table filled 26 % of 32 kbit)
-  __shared__ u32 s_base; __shared__ u32 bloom[BW]; __shared__ u32 pdir[257];   // pdir: first table row of every 4-base prefix
-  extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); u32* sw = sv + max_tn;
+  constexpr int NG = NT >= 1024 ? 2 : 1, GT = NT / NG;   // groups per CTA, threads per group
+  __shared__ u32 s_base_g[NG]; __shared__ u32 bloom[BW]; __shared__ u32 pdir[257];   // pdir: first table row of every 4-base prefix
+  extern __shared__ __align__(16) u8 smem3[]; u64* sk = (u64*)smem3; u32* sv = (u32*)(sk + max_tn); const int grp = threadIdx.x / GT, gtid = threadIdx.x % GT, bid = NG > 1 ? 1 + grp : 0; u32* sw = sv + max_tn + (size_t)grp * win_words; u32* const s_base = &s_base_g[grp];
   const u32 q = qlist[blockIdx.x]; const u32 t0q = toff[q], tn = toff[q + 1] - t0q; const int K = 31;
   for (u32 i = threadIdx.x; i < (u32)BW; i += NT) bloom[i] = 0; for (u32 i = threadIdx.x; i < 257; i += NT) pdir[i] = tn;
   for (u32 i = threadIdx.x; i < tn; i += NT) { sk[i] = tkeys[t0q + i]; sv[i] = tvals[t0q + i]; }
@@ -688,47 +694,48 @@ __global__ void __launch_bounds__(NT) k_pa_anchors3(const WinItem* __restrict__ 
   // Work compaction: most window positions fail the Bloom / prefix pre-check, and of those that search the table only a few take the
   // radix-tree emulation. Doing everything in one pass ran at ~10 active lanes per instruction; instead positions that pass the pre-check
   // are queued (position << 1 | strand) and searched 256 at a time, and the rare slow-path searches are queued again.
-  __shared__ u32 qfast[4 * NT], qslow[3 * NT]; __shared__ u32 nslow; __shared__ u32 s_wc[2][32];
-  for (u32 it = qitem_beg[q]; it < qitem_end[q]; it++) {
+  __shared__ u32 qfast_g[NG][4 * GT], qslow_g[NG][3 * GT]; __shared__ u32 nslow_g[NG]; __shared__ u32 s_wc_g[NG][2][32]; u32* const qfast = qfast_g[grp]; u32* const qslow = qslow_g[grp]; u32* const nslow = &nslow_g[grp]; u32 (*s_wc)[32] = s_wc_g[grp];
+  __syncthreads();   // table, Bloom filter and directory complete before any group starts
+  for (u32 it = qitem_beg[q] + grp; it < qitem_end[q]; it += NG) {
     WinItem w = items[it]; const u8* g2 = g2bit + g_off[w.g]; const u64 base0 = abeg[it]; const u32 cap = acap[it]; const u32 begin = (u32)w.qBegin, end = (u32)w.qEnd;
-    __syncthreads();   // previous window fully consumed (and, first time, table loaded)
+    gbar(bid, GT);   // previous window of this group fully consumed
     i32 nw = (w.W + 15) / 16 + 2;
-    for (i32 x = threadIdx.x; x < nw; x += NT) sw[x] = win_word16(g2, w.tBegin, w.tEnd, w.rc, w.W, x);
-    if (threadIdx.x == 0) { s_base = 0; nslow = 0; } __syncthreads();
+    for (i32 x = gtid; x < nw; x += GT) sw[x] = win_word16(g2, w.tBegin, w.tEnd, w.rc, w.W, x);
+    if (gtid == 0) { *s_base = 0; *nslow = 0; } gbar(bid, GT);
     const i32 np = w.W - K + 1; u64* const out_base = a_lo + base0;
     // The scan queues candidates, the drain searches them 1 CTA-width at a time. Barrier stalls were 24 waiting warps per issue slot in the 1,024-thread
     // variant (ncu), so the queue length lives in a REGISTER that every thread advances identically (nq; the per-slice total comes from the same
     // shared-memory warp counts in every warp), the warp counts are double-buffered, and the slow-path queue is only looked at when some thread
     // pushed to it (__syncthreads_or): a slice costs one barrier, a drain two.
     u32 nq = 0; int par = 0; bool any_slow_window = false;
-    auto slow_drain = [&](u32 ns0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, (u32)NT), st2 = ns - tk; if (threadIdx.x < tk) { u32 e2 = qslow[st2 + threadIdx.x]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, &s_base, cap, out_base); } ns = st2; } };
-    for (i32 base = 0;; base += NT) {
+    auto slow_drain = [&](u32 ns0) { for (u32 ns = ns0; ns > 0;) { u32 tk = min(ns, (u32)GT), st2 = ns - tk; if ((u32)gtid < tk) { u32 e2 = qslow[st2 + gtid]; u64 key = pa3_key(sw, e2, ttt); u32 l = 0, h = 0; if (tree_search_slow(sk, tn, key, w.mp, &l, &h)) pa3_emit(sk, sv, e2, key, l, h, begin, end, s_base, cap, out_base); } ns = st2; } };
+    for (i32 base = 0;; base += GT) {
       const bool more = (base < np) && tn;   // uniform: another slice of window positions to scan
-      if (more) { i32 idx = base + (i32)threadIdx.x; bool c1 = false, c2 = false;
+      if (more) { i32 idx = base + (i32)gtid; bool c1 = false, c2 = false;
         if (idx < np) { u32 wi = (u32)idx >> 4, sh = ((u32)idx & 15) * 2; u64 hi64 = ((u64)sw[wi] << 32) | sw[wi + 1]; u64 v = sh ? ((hi64 << sh) | ((u64)sw[wi + 2] >> (32 - sh))) : hi64; u64 km = v >> 2;
           if (!(km == 0 || km == ccc || km == ggg || km == ttt)) { u64 kr = kmer_reverse62(~km & ttt, K);
             u32 hb = ((u32)(km >> 40) * 2654435761u) >> BSH; c1 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((km >> 40) & 0xF) == 0);
             hb = ((u32)(kr >> 40) * 2654435761u) >> BSH; c2 = (w.mp != 11) || ((bloom[hb >> 5] >> (hb & 31)) & 1) || (((kr >> 40) & 0xF) == 0); } }
         // queue the candidates of this slice with a block-wide scan (ballots -> per-warp counts in shared memory -> prefix over the warps)
-        const u32 b1 = __ballot_sync(FULLMASK, c1), b2 = __ballot_sync(FULLMASK, c2); if (lane == 0) s_wc[par][threadIdx.x >> 5] = __popc(b1) + __popc(b2); __syncthreads();
-        const u32 wv = (lane < NT / 32) ? s_wc[par][lane] : 0u; const u32 before = __reduce_add_sync(FULLMASK, lane < (int)(threadIdx.x >> 5) ? wv : 0u), tot = __reduce_add_sync(FULLMASK, wv); const u32 wbase = nq + before;
+        const u32 b1 = __ballot_sync(FULLMASK, c1), b2 = __ballot_sync(FULLMASK, c2); if (lane == 0) s_wc[par][gtid >> 5] = __popc(b1) + __popc(b2); gbar(bid, GT);
+        const u32 wv = (lane < GT / 32) ? s_wc[par][lane] : 0u; const u32 before = __reduce_add_sync(FULLMASK, lane < (int)(gtid >> 5) ? wv : 0u), tot = __reduce_add_sync(FULLMASK, wv); const u32 wbase = nq + before;
         if (c1) qfast[wbase + __popc(b1 & ((1u << lane) - 1))] = (u32)idx << 1; if (c2) qfast[wbase + __popc(b1) + __popc(b2 & ((1u << lane) - 1))] = ((u32)idx << 1) | 1u; nq += tot; par ^= 1; }
       // drain: full chunks while scanning, everything at the end
-      while (more ? (nq >= (u32)NT) : (nq > 0)) {
-        __syncthreads();   // the queue entries written above (by other warps) are visible
-        const u32 take = min(nq, (u32)NT), start = nq - take; bool slow = false; u32 e = 0;
-        if (threadIdx.x < take) { e = qfast[start + threadIdx.x]; u64 key = pa3_key(sw, e, ttt); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
+      while (more ? (nq >= (u32)GT) : (nq > 0)) {
+        gbar(bid, GT);   // the queue entries written above (by other warps) are visible
+        const u32 take = min(nq, (u32)GT), start = nq - take; bool slow = false; u32 e = 0;
+        if ((u32)gtid < take) { e = qfast[start + gtid]; u64 key = pa3_key(sw, e, ttt); const int p = w.mp; u64 low = (1ull << (2 * (K - p))) - 1, left = key & ~low, right = key | low; u32 b = (u32)(key >> 54), x = pdir[b], y = pdir[b + 1];
           while (x < y) { u32 m = (x + y) >> 1; if (sk[m] < left) x = m + 1; else y = m; } u32 en = x; while (en < tn && sk[en] <= right) en++;
-          if (en > x) pa3_emit(sk, sv, e, key, x, en, begin, end, &s_base, cap, out_base); else slow = quirk_possible(sk, tn, x, key, p); }
+          if (en > x) pa3_emit(sk, sv, e, key, x, en, begin, end, s_base, cap, out_base); else slow = quirk_possible(sk, tn, x, key, p); }
         nq = start;
-        if (__syncthreads_or(slow)) {   // (also the barrier between reading this chunk and the next slice overwriting it) some radix-tree emulations to queue: rare
-          any_slow_window = true; pa3_push(qslow, &nslow, slow, e, lane); __syncthreads(); const u32 ns1 = nslow; __syncthreads();
-          if (ns1 >= (u32)NT) { slow_drain(ns1); __syncthreads(); if (threadIdx.x == 0) nslow = 0; __syncthreads(); } }
+        if (gbar_or(bid, GT, slow)) {   // (also the barrier between reading this chunk and the next slice overwriting it) some radix-tree emulations to queue: rare
+          any_slow_window = true; pa3_push(qslow, nslow, slow, e, lane); gbar(bid, GT); const u32 ns1 = *nslow; gbar(bid, GT);
+          if (ns1 >= (u32)GT) { slow_drain(ns1); gbar(bid, GT); if (gtid == 0) *nslow = 0; gbar(bid, GT); } }
       }
       if (!more) break;
     }
-    if (any_slow_window) { __syncthreads(); const u32 ns0 = nslow; __syncthreads(); if (ns0 > 0) slow_drain(ns0); }
-    __syncthreads(); if (threadIdx.x == 0) counts[it] = s_base;
+    if (any_slow_window) { gbar(bid, GT); const u32 ns0 = *nslow; gbar(bid, GT); if (ns0 > 0) slow_drain(ns0); }
+    gbar(bid, GT); if (gtid == 0) counts[it] = *s_base;
   }
 }
 
@@ -1417,7 +1424,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   // queries -> item ranges (items are ordered by (query, genome)); per-query kernel when table + window fit in shared memory
   std::vector<u32> qbeg(B.nq, 0), qend(B.nq, 0), qlist, rest; { u32 i = 0; while (i < nit) { u32 q = items[i].q, j = i; while (j < nit && items[j].q == q) j++; qbeg[q] = i; qend[q] = j; i = j; } }
   u32 max_tn = 0; i32 maxW3 = 0; const size_t smem_cap3 = std::min<size_t>(ix->smem_optin - 48 * 1024, 178 * 1024);   // dynamic part; the 1,024-thread variant has 46 KB of static queues + Bloom filter
-  for (int q = 0; q < B.nq; q++) if (qend[q] > qbeg[q]) { u32 tn = htoff[q + 1] - htoff[q]; i32 mw = 0; for (u32 i = qbeg[q]; i < qend[q]; i++) mw = std::max(mw, items[i].W); size_t need = (size_t)tn * 12 + ((size_t)(mw + 15) / 16 + 2) * 4 + 64;
+  for (int q = 0; q < B.nq; q++) if (qend[q] > qbeg[q]) { u32 tn = htoff[q + 1] - htoff[q]; i32 mw = 0; for (u32 i = qbeg[q]; i < qend[q]; i++) mw = std::max(mw, items[i].W); size_t need = (size_t)tn * 12 + 2 * ((size_t)(mw + 15) / 16 + 2) * 4 + 64;   // two window buffers: the 1,024-thread variant runs two groups
       if (need <= smem_cap3) { qlist.push_back(q); max_tn = std::max(max_tn, tn); maxW3 = std::max(maxW3, mw); } else for (u32 i = qbeg[q]; i < qend[q]; i++) rest.push_back(i); }
   if (rest.empty()) std::fill(hhoff.begin(), hhoff.end(), 0);   // the L2-resident hash index is only needed by the fallback kernel
   DBuf<u64> hoff(B.nq + 1, st); hoff.from_host(hhoff.data(), B.nq + 1); DBuf<u64> htab(hhoff[B.nq] + 2, st); htab.fill_ff();
@@ -1425,7 +1432,7 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
   std::vector<u32> hcap(nit); std::vector<u64> habeg(nit + 1, 0); i32 maxW = 0; for (u32 i = 0; i < nit; i++) { hcap[i] = (u32)std::min<i64>((i64)std::max(0, items[i].W - 30) + 256, 0x7fffffff); maxW = std::max(maxW, items[i].W); }
   size_t smemW = ((size_t)(maxW + 15) / 16 + 2) * 4; if (smemW > ix->smem_optin - 4096) throw std::runtime_error("target window too long for the shared-memory pseudo-alignment kernel");
   DBuf<u32> cnt(nit + 1, st), dcap(nit, st); DBuf<u64> abeg(nit + 1, st); DBuf<u64> lo0; std::vector<u32> hcnt; std::vector<u64> haend(nit); u64 NA = 0;
-  max_tn = (max_tn + 3) & ~3u; size_t smem3 = (size_t)max_tn * 12 + ((size_t)(maxW3 + 15) / 16 + 2) * 4 + 64; if (smem3 > ix->smem_optin - 48 * 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
+  max_tn = (max_tn + 3) & ~3u; const u32 win_words = (u32)((maxW3 + 15) / 16 + 2); size_t smem3 = (size_t)max_tn * 12 + 2 * (size_t)win_words * 4 + 64; if (smem3 > ix->smem_optin - 48 * 1024) { rest.clear(); qlist.clear(); for (u32 i = 0; i < nit; i++) rest.push_back(i); }   // mixed extremes: everything through the L2 kernel
   DBuf<u32> d_qlist(qlist.size() + 1, st), d_qbeg(B.nq + 1, st), d_qend(B.nq + 1, st), d_rest(rest.size() + 1, st); d_qlist.from_host(qlist.data(), qlist.size()); d_qbeg.from_host(qbeg.data(), B.nq); d_qend.from_host(qend.data(), B.nq); d_rest.from_host(rest.data(), rest.size());
   lap("k4 host prep");
   for (int pass = 0; pass < 2; pass++) {   // pass 1 only when some window produced more anchors than W+226: capacities become the exact counts
@@ -1434,8 +1441,8 @@ static void search_pipeline(lmg_index* ix, const lmg_params* prm, const u8* seqs
     if (habeg[nit] >= slot_limit) throw BatchTooLarge("more than 2^31 pseudo-alignment anchor slots in one batch; use smaller batches");
     dcap.from_host(hcap.data(), nit); abeg.from_host(habeg.data(), nit + 1); lo0.alloc(habeg[nit] + 2, st);
     { KTimer kt(st, &ix->ms[14]);
-      if (!qlist.empty()) { if (smem3 > 64 * 1024) { k_pa_anchors3<1024><<<(u32)qlist.size(), 1024, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); }
-        else { k_pa_anchors3<256><<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn); KERNEL_CHECK(); } }
+      if (!qlist.empty()) { if (smem3 > 64 * 1024) { k_pa_anchors3<1024><<<(u32)qlist.size(), 1024, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn, win_words); KERNEL_CHECK(); }
+        else { k_pa_anchors3<256><<<(u32)qlist.size(), 256, smem3, st>>>(d_items.p, d_qlist.p, d_qbeg.p, d_qend.p, I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, abeg.p, dcap.p, cnt.p, lo0.p, max_tn, win_words); KERNEL_CHECK(); } }
       if (!rest.empty()) { k_pa_anchors2<<<(u32)rest.size(), 128, smemW, st>>>(d_items.p, d_rest.p, (u32)rest.size(), I.d_g2bit, I.d_g_off, tkeys.p, tvals.p, toff.p, htab.p, hoff.p, abeg.p, dcap.p, cnt.p, lo0.p, habeg[nit]); KERNEL_CHECK(); } }
     hcnt = cnt.to_host(nit);
     bool over = false; NA = 0; for (u32 i = 0; i < nit; i++) { if (hcnt[i] > hcap[i]) over = true; haend[i] = habeg[i] + hcnt[i]; NA += hcnt[i]; }
