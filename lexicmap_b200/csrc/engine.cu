@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* 
   if (t < ns) { Surv sv = surv[t]; const u32 dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; const u32 bucket = aslot / (u32)P.NA; u64 kmer = sv.kmer;
     int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; const u32 as = anchor_start_of(P, bucket, aslot - bucket * (u32)P.NA);
     const u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; const SeedEntry* __restrict__ E = P.entries; u64 lo = b0 + as, hi = b1;
-    u64 step = 1, l = lo; while (l + step < hi && E[l + step].key < left) { l += step; step <<= 1; steps++; }
-    u64 r = min(hi, l + step); if (E[l].key >= left) r = l; else l = l + 1;
-    while (l < r) { u64 mid = (l + r) >> 1; if (E[mid].key < left) l = mid + 1; else r = mid; steps++; }
+    u64 l = lo, r = lo;   // lower bound of `left` in [lo, hi): the anchor's first key is tested first (after the Bloom filter most probes end right there: one sector), then gallop + binary search
+    if (E[lo].key < left) { u64 step = 1; while (l + step < hi && E[l + step].key < left) { l += step; step <<= 1; steps++; } r = min(hi, l + step); l = l + 1;
+      while (l < r) { u64 mid = (l + r) >> 1; if (E[mid].key < left) l = mid + 1; else r = mid; steps++; } }
     u64 e0 = l; u32 na = 0;
     while (e0 + ne < hi) { const ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(E + e0 + ne); if (raw.x > right) break; const u32 nf = (u32)(raw.y >> 32); if ((nf >> 31) == dir) na += nf & 0x7FFFFFFFu; ne++; }
     if (na) { have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = sv.lo; h.n = sv.n; h.kmer = kmer; h.nanch = na * sv.n; h.bucket = bucket; }
@@ -289,7 +289,7 @@ struct HostPool {
 // is lane 0 and owns the image; further lanes (same image, own stream/arena) are created on demand so that big batches can be split into
 // sub-batches whose host phases (window geometry, contig mapping, scoring) overlap the other sub-batch's kernels.
 struct lmg_index {
-  Image* imgp; Image& img; bool owner; cudaStream_t st = 0; CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
+  Image* imgp; Image& img; bool owner; cudaStream_t st = 0; cudaStream_t st_hi = 0; cudaEvent_t ev_hi[2] = {nullptr, nullptr};   /* st_hi: high-priority stream of this lane for the memory-bound index lookup */ CubTemp tmp; int sm_count = 148; u32 smem_optin = 0; int use_tma = 1;
   double ms[16] = {0}; u64 counters[16] = {0}; u64 pstat[4] = {0, 0, 0, 0};   /* last statistics pass of the seed lookup: sum ceil(log2(n_a+1)), sum of 32-byte sectors of matched entries, sum of values of matched entries */ std::mutex mu; cudaEvent_t kev[3] = {nullptr, nullptr, nullptr}; Arena arena; std::vector<lmg_index*> lanes; int lane_id = 0, active_lanes = 1; size_t total_mem = 0; HostPool pool;
   // workers per lane: this process's usable cores over the active lanes. LMG_HOST_CORES (or OMP_NUM_THREADS, which launchers such as torchrun set per
   // rank) tells how many cores the process may use when several ranks share a node; otherwise the affinity mask capped by the cgroup CPU quota
@@ -386,7 +386,11 @@ static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivor
   // phase B: index lookup on the survivors
   DBuf<ProbeHit> hits; u64 capH = std::max<u64>(1u << 18, (u64)ns / 2 + 1024); u32 nhit = 0;
   for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) CUDA_CHECK(cudaMemsetAsync(dstats.p + 2, 0, 40, st));
-    cudaEventRecord(ix->kev[1], st); if (stats) k_probe_find2<true><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), dstats.p); else k_probe_find2<false><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], st);
+    // The lookup is the one memory-bound kernel of the path: it runs on the lane's HIGH-PRIORITY stream so that its CTAs are scheduled ahead of the issue-bound
+    // kernels of the other lanes that share the GPU (they would otherwise stretch it 2x without gaining anything themselves).
+    cudaStream_t sl = getenv("LMG_NO_PRIO_LOOKUP") ? st : ix->st_hi; if (sl != st) { cudaEventRecord(ix->ev_hi[0], st); cudaStreamWaitEvent(sl, ix->ev_hi[0], 0); }
+    cudaEventRecord(ix->kev[1], sl); if (stats) k_probe_find2<true><<<cdiv(ns, 256), 256, 0, sl>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), dstats.p); else k_probe_find2<false><<<cdiv(ns, 256), 256, 0, sl>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], sl);
+    if (sl != st) { cudaEventRecord(ix->ev_hi[1], sl); cudaStreamWaitEvent(st, ix->ev_hi[1], 0); }
     nhit = nh.to_host()[0]; if (nhit <= capH) break; capH = (u64)ns + 1024; }
   if (!hits.p) hits.alloc(16, st);
   { float fb = 0; if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] += fb; ix->counters[13] = (u64)(fb * 1000); }
@@ -1595,6 +1599,7 @@ const char* lmg_last_error(void) { return g_err.c_str(); }
 
 static lmg_index* make_ctx(Image* im, bool owner, int device) {
   lmg_index* ix = new lmg_index(im, owner); CUDA_CHECK(cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking)); ix->tmp.st = ix->st;
+  { int lo_p = 0, hi_p = 0; CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p)); CUDA_CHECK(cudaStreamCreateWithPriority(&ix->st_hi, cudaStreamNonBlocking, hi_p)); CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_hi[0], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_hi[1], cudaEventDisableTiming)); }
   cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); ix->sm_count = pr.multiProcessorCount; ix->smem_optin = (u32)pr.sharedMemPerBlockOptin; if (pr.major < 9) ix->use_tma = 0;
   if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
   // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
@@ -1602,7 +1607,7 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
   if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3<256>); raise((const void*)k_pa_anchors3<1024>); raise((const void*)k_pa_sort<4096, 512>); }
   return ix;
 }
-static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }
+static void free_ctx(lmg_index* ix) { cudaStreamSynchronize(ix->st); if (ix->st_hi) { cudaStreamSynchronize(ix->st_hi); cudaStreamDestroy(ix->st_hi); } for (auto& e : ix->ev_hi) if (e) cudaEventDestroy(e); ix->arena.release(); if (ix->tmp.p) { cudaFree(ix->tmp.p); ix->tmp.p = nullptr; } for (auto& e : ix->kev) if (e) cudaEventDestroy(e); cudaStreamDestroy(ix->st); }
 static lmg_index* lane_ctx(lmg_index* ix, int l) { if (l == 0) return ix; while ((int)ix->lanes.size() < l) { ix->lanes.push_back(make_ctx(ix->imgp, false, ix->img.device)); ix->lanes.back()->lane_id = (int)ix->lanes.size(); } return ix->lanes[l - 1]; }
 // number of concurrent sub-batches: explicit (params.lanes / LMG_LANES) or up to 6 for batches big enough to amortise the split
 // (10,000 x 1-kb bench, ms per batch: 1 lane 124-140, 3 lanes 102, 4 lanes 88, 6 lanes 81-84, 8 lanes 85, 12 lanes 87; exclusive GPU phases were slower)

@@ -19,7 +19,9 @@ for f in sorted(glob.glob(os.path.join(d0, "bench_*.json"))):
     print("=====", os.path.basename(f), "value %.3e  ms %.1f  e2e %.3e  rows %s launches %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d.get("rows_per_step"), d.get("gpu_launches")))
     if "stage_ms" in d:
         print(" stage", {k: round(v, 1) for k, v in d["stage_ms"].items()})
-    r = d["roofline"]
+    r = d.get("roofline")
+    if not r:
+        continue
     print(" roofline frac %.3f alone %s kernel_ms %.2f bytes %.3e" % (r["frac"], r.get("alone", {}).get("frac"), r["kernel_ms_per_step"], r["algorithmic_bytes_per_step"]), r.get("random_sector_ceiling", ""))
     if "debug" in d:
         g = d["debug"]
