@@ -430,11 +430,15 @@ def run_search(a, rank, world, local):
         pass
     # the same kernel alone on the GPU (one lane, so no other lane's kernels share the SMs / HBM during its launches)
     p1 = idx.default_params(lanes=1, **search_kw)
-    iso = []
+    iso, iso_rg = [], []
     for _ in range(3):
         idx.search_count(packed, p1)
-        iso.append(idx.timing()[0][8])
+        tm = idx.timing()
+        iso.append(tm[0][8])
+        iso_rg.append(tm[1][12] * 1e-3)
     t_iso = float(np.mean(iso[1:])) * 1e-3
+    rg_iso_ms = float(np.mean(iso_rg[1:]))
+    rg_ms = float(kcnt[12]) * 1e-3   # regrouping pass (probes bucketed by mask before the lookup kernel) of the last timed step, summed over the lanes
     # ---- CPU baseline on this box (bounded sample)
     threads = usable_cpus()[0]
     cpu_s = float(os.environ.get("LMG_BENCH_CPU_S", 15.0))   # 0 skips the CPU leg (parameter sweeps only; the default run always reports it)
@@ -457,6 +461,9 @@ def run_search(a, rank, world, local):
            "stage_ms": {k: float(v) / a.steps for k, v in zip(["h2d", "sketch", "seed_probe", "chain", "pseudo_align", "extend_wfa", "host_finish", "total"], stage_ms)},
            "roofline": {"bound": "hbm", "kernel": "k_probe_find2 (seed index lookup of the surviving probes)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_capture": traffic_src,
                         "model": "SURVEY.md §8d: per probe 12 + 32 + 32*ceil(log2(n_a+1)) + 32*ceil(16h/32) + 16*h_out bytes", "algorithmic_bytes_per_step": alg_bytes, "probes_per_step": float(cnt[1]) * scale, "kernel_ms_per_step": t_probe * 1e3, "launches_per_step": config_lanes,
+                        "regroup": {"note": "the probes are bucketed by mask (histogram + scan + scatter kernels) right before the lookup kernel so that a warp searches one bucket; that pass is not part of the kernel time above",
+                                    "ms_per_step": rg_ms, "ms_alone": rg_iso_ms, "frac_with_regroup": (alg_bytes / (t_probe + rg_ms * 1e-3) / 1e9 / peak) if t_probe > 0 else 0.0,
+                                    "frac_alone_with_regroup": (alg_bytes / (t_iso + rg_iso_ms * 1e-3) / 1e9 / peak) if t_iso > 0 else 0.0},
                         "alone": {"kernel_ms": t_iso * 1e3, "achieved": alg_bytes / t_iso / 1e9 if t_iso > 0 else 0.0, "frac": (alg_bytes / t_iso / 1e9 / peak) if t_iso > 0 else 0.0, "note": "same batch through one lane: no concurrent kernels"},
                         "r01_model": {"note": "round 1's byte model (24+32 B per probe, 32 B per search step taken, 16 B per entry scanned, 48 B per hit): kept for continuity with BENCH_r01", "algorithmic_bytes_per_step": r01_bytes, "frac": (r01_bytes / t_probe / 1e9 / peak) if t_probe > 0 else 0.0},
                         "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): this, not the streaming peak, bounds a lookup whose accesses are dependent random sectors",
@@ -511,13 +518,14 @@ def run_c5(a, rank, world, local):
     r = idx.probe_bench(nq, iters=max(a.steps, 1) + a.warmup)
     sampler.finish()
 
-    t = torch.tensor([r["survivors"], r["issued"], r["hits"], r["sum_log2"], r["sum_hit_sectors"], r["sum_values"], r["kernel_ms"], r["kernel_ms_best"]], device="cuda", dtype=torch.float64)
+    t = torch.tensor([r["survivors"], r["issued"], r["hits"], r["sum_log2"], r["sum_hit_sectors"], r["sum_values"], r["kernel_ms"], r["kernel_ms_best"], r["regroup_ms"]], device="cuda", dtype=torch.float64)
     if dist:
         tm = t[6:].clone()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(t[:6], op=dist.ReduceOp.SUM)
         t[6:] = tm
-    surv, issued, hits, slog, ssec, sval, kms, kbest = (float(x) for x in t.tolist())
+    surv, issued, hits, slog, ssec, sval, kms, kbest, rms = (float(x) for x in t.tolist())
+    step_ms = kms + rms   # a lookup step = regrouping pass (probes bucketed by mask) + lookup kernel
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -525,17 +533,17 @@ def run_c5(a, rank, world, local):
     peak, peak_src = hbm_peak()
     alg = probe_model_bytes(surv, slog, ssec, sval)
     per_gpu = alg / world / (kms * 1e-3) / 1e9
-    out = {"metric": "seed lookups/s (prefix + suffix probes of 31-mers against the seed index)", "value": surv / (kms * 1e-3), "unit": "probes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": kms,
+    out = {"metric": "seed lookups/s (prefix + suffix probes of 31-mers against the seed index)", "value": surv / (step_ms * 1e-3), "unit": "probes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
            "config": {"workload": "BASELINE.json configs[4]: %d query 31-mers (half stored keys mutated in their last 0-16 bases, half uniform), one prefix + one suffix probe each, vs a synthetic seed index of %d masks x %d seeds = %.2e seeds%s"
                                   % (nq, m, per_fit, m * per_fit, "" if per_fit == per else " (REDUCED from %d per mask: 16 B per seed, %d GPU(s))" % (per, world)),
                       "sharding": "index range-partitioned by mask over %d GPU(s); every probe goes to the GPU that owns its mask; no collective" % world, "seed": C5["seed"], "l2": "index shard (tens of GB) and the probe list (hundreds of MB) exceed the 126 MB L2"},
-           "gpu_launches": a.steps + a.warmup + 2, "probes_issued": issued, "probes_with_anchor": surv, "hit_records": hits,
+           "gpu_launches": 4 * (a.steps + a.warmup + 1) + 2, "probes_issued": issued, "probes_with_anchor": surv, "hit_records": hits,
            "roofline": {"bound": "hbm", "kernel": "k_probe_find2", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None, "model": "SURVEY.md §8d per-probe bytes, per GPU (max kernel time over ranks)",
-                        "algorithmic_bytes_per_step": alg, "bytes_per_probe": alg / max(surv, 1), "kernel_ms_per_step": kms, "kernel_ms_best": kbest, "mean_log2_steps": slog / max(surv, 1), "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": alg, "bytes_per_probe": alg / max(surv, 1), "kernel_ms_per_step": kms, "kernel_ms_best": kbest, "regroup_ms_per_step": rms, "frac_with_regroup": alg / world / (step_ms * 1e-3) / 1e9 / peak, "mean_log2_steps": slog / max(surv, 1), "peak_source": peak_src,
                         "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): a lookup made of dependent random sectors is bound by this (DRAM row activations), not by the streaming peak",
                                                   "sectors_per_s": gb["sectors_per_s"], "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak}},
-           "e2e": {"value": surv / (kms * 1e-3), "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "device-resident microbenchmark: probes are generated on the GPU; the end-to-end numbers are the search configs'"},
+           "e2e": {"value": surv / (step_ms * 1e-3), "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "device-resident microbenchmark: probes are generated on the GPU; the end-to-end numbers are the search configs'"},
            "cpu_baseline": None, "clocks": sampler.summary()}
     if dist:
         dist.destroy_process_group()

@@ -108,7 +108,8 @@ void lmg_results_free(lmg_results* r);
 /* CUDA-event times of the last search, ms[16]: [0]=h2d [1]=sketch [2]=seed probe [3]=anchor sort/chain [4]=pseudo-align
  * [5]=extend+wfa [6]=host finish [7]=total [8]=k_probe_find kernel alone.  counters[16]: [0..5] probe statistics of the last
  * lmg_anchor_batch (issued, with anchor, search steps, entries scanned, hit records, anchors) [6]=query bases [7]=queries
- * [8]=probe slots [15]=kernels launched by this library so far */
+ * [8]=probe slots [12]=microseconds of the probe-regrouping pass (+ the filter kernel of long queries) [13]=microseconds of the lookup kernel
+ * [15]=kernels launched by this library so far */
 int  lmg_last_timing(const lmg_index* idx, double* ms16, uint64_t* counters16);
 /* byte-model sums of the last lmg_anchor_batch: [0] sum over probes of ceil(log2(n_a+1)), n_a = entries of the probe's anchor run
  * [1] sum of 32-byte sectors of matched entries [2] sum of matched values (anchors before the query-location product) [3] reserved */
@@ -125,7 +126,7 @@ int  lmg_index_load_times(const lmg_index* idx, double* ms4);
  * mask range [mask_lo, mask_hi) (range partitioning across GPUs), and a run of the index-lookup kernel over n_queries synthetic 31-mers (one prefix and one
  * suffix probe each; only probes of the held mask range are issued). out16: [0] probes issued [1] probes with an anchor (kernel work items) [2] mean kernel ms
  * [3] hit records [4] sum ceil(log2(n_a+1)) [5] sum of 32-B sectors of matched entries [6] sum of matched values [7] search steps taken [8] entries scanned
- * [9] generator ms [10] best kernel ms. Search entry points refuse such an index. */
+ * [9] generator ms [10] best kernel ms [11] mean ms of the pass that regroups the probes by bucket before the kernel. Search entry points refuse such an index. */
 int  lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed, int32_t mask_lo, int32_t mask_hi, int32_t with_values, lmg_index** out);
 int  lmg_probe_bench(lmg_index* idx, uint64_t n_queries, uint64_t seed, int32_t min_prefix, int32_t iters, double* out16);
 

@@ -127,7 +127,7 @@ class Index:
         out = np.zeros(16, np.float64)
         if self.lib.lmg_probe_bench(self.h, n_queries, seed, min_prefix, iters, out.ctypes.data) != 0:
             self._err()
-        keys = ["issued", "survivors", "kernel_ms", "hits", "sum_log2", "sum_hit_sectors", "sum_values", "steps", "entries", "gen_ms", "kernel_ms_best"]
+        keys = ["issued", "survivors", "kernel_ms", "hits", "sum_log2", "sum_hit_sectors", "sum_values", "steps", "entries", "gen_ms", "kernel_ms_best", "regroup_ms"]
         return dict(zip(keys, out.tolist()))
 
     def set_total_bases(self, n):

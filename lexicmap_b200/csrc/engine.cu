@@ -120,12 +120,21 @@ __global__ void __launch_bounds__(256) k_capture(const u64* __restrict__ qkeys, 
 // K2: seed probe (kv.Searcher.Search / Search2, kv/kv-searcher.go:190-1088) + anchors (lib-index-search.go:1357-1569)
 // =====================================================================================================
 struct ProbeHit { u32 q, mask_dir; u64 e0; u32 ne; u32 lo, n; u64 kmer; u32 nanch; u32 bucket; };  // mask_dir = capturing mask<<1 | dir ; [lo,lo+n) = query table rows (locs); bucket = mask bucket searched; [e0, e0+ne) = matched index entries
-struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_cbase, *anchor_cstart, *anchor_bits, *pbloom; const u16* anchor_cum; u32 pbmask; int m, k, NA, mask_prefix, anchor_prefix, p; };
-// bucket-relative index of the first key of anchor `an` (present anchors only): rank of the anchor among the bucket's present anchors -> compact start array
-__device__ __forceinline__ u32 anchor_start_of(const ProbeParams& P, u32 bucket, u32 an) { const u64 w = (u64)bucket * (u32)(P.NA >> 5) + (an >> 5); const u32 bits = P.anchor_bits[w]; const u32 rank = (u32)P.anchor_cum[w] + __popc(bits & ((1u << (an & 31)) - 1)); return P.anchor_cstart[P.anchor_cbase[bucket] + rank]; }
+struct ProbeParams { const u64 *bucket_off, *bucket_voff, *vals; const SeedEntry* entries; const u32 *anchor_cbase, *anchor_cstart, *anchor_bits, *pbloom; const u16 *anchor_cum, *anchor_cstart16; u32* bcnt; u32 pbmask; int m, k, NA, mask_prefix, anchor_prefix, p, hints; };   // bcnt: per-call histogram of the surviving probes over the buckets (filled by the kernels that emit them; may be null)
+// L2 cache policies for the lookup kernel: the compact anchor table (tens of MB, re-read by every probe) must stay in L2 while the random sectors of the
+// 16-byte entries (hundreds of MB to GB, each touched about once per launch) stream through it. Without hints the entry sectors evict the table and every
+// probe pays DRAM bursts for its bitmap word, rank and start on top of the entry itself (ncu, round 2: L2 hit rate 30 %, 383 B of DRAM traffic per probe).
+__device__ __forceinline__ u64 l2_policy(int kind) { u64 p; if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ ulonglong2 ld_hint_v2(const void* a, u64 pol) { ulonglong2 r; asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(a), "l"(pol)); return r; }
+__device__ __forceinline__ u64 ld_hint_u64(const void* a, u64 pol) { u64 r; asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(a), "l"(pol)); return r; }
+__device__ __forceinline__ u32 ld_hint_u32(const void* a, u64 pol) { u32 r; asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(a), "l"(pol)); return r; }
+__device__ __forceinline__ u32 ld_hint_u16(const void* a, u64 pol) { unsigned short r; asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(a), "l"(pol)); return r; }
+// bucket-relative index of the first key of a present anchor, from its rank among the bucket's present anchors (the rank is computed where the bitmap word is already loaded: probe_may_hit)
+__device__ __forceinline__ u32 anchor_start_of(const ProbeParams& P, u32 bucket, u32 rank, u64 pol) { const u64 i = (u64)ld_hint_u32(P.anchor_cbase + bucket, pol) + rank; return P.anchor_cstart16 ? ld_hint_u16(P.anchor_cstart16 + i, pol) : ld_hint_u32(P.anchor_cstart + i, pol); }
 // a probe survives when its anchor exists in the bucket's anchor table (the reference's own test) AND some key of the bucket starts with the probe's first maskPrefix+anchorPrefix bases (prefix Bloom filter, image.cuh)
-__device__ __forceinline__ bool probe_may_hit(const ProbeParams& P, u32 bucket, u64 left, int ash) { const u32 pre = (u32)(left >> ash); const u64 aslot = (u64)bucket * P.NA + (pre & (u32)(P.NA - 1)); if (!((P.anchor_bits[aslot >> 5] >> (aslot & 31)) & 1)) return false;
-  const u32 hb = pb_hash(bucket, pre) & P.pbmask; return (P.pbloom[hb >> 5] >> (hb & 31)) & 1; }
+__device__ __forceinline__ bool probe_may_hit(const ProbeParams& P, u32 bucket, u64 left, int ash, u32& arank) { const u32 pre = (u32)(left >> ash); const u64 aslot = (u64)bucket * P.NA + (pre & (u32)(P.NA - 1)); const u32 bits = P.anchor_bits[aslot >> 5]; if (!((bits >> (aslot & 31)) & 1)) return false;
+  const u32 hb = pb_hash(bucket, pre) & P.pbmask; if (!((P.pbloom[hb >> 5] >> (hb & 31)) & 1)) return false;
+  arank = (u32)P.anchor_cum[aslot >> 5] + __popc(bits & ((1u << (aslot & 31)) - 1)); return true; }   /* rank of the anchor among the bucket's present anchors */
 
 // Probe semantics (kv.Searcher.Search / Search2): dir 0 = captured k-mer against its own mask bucket, values must have reverse flag 0;
 // dir 1 = base-reversed k-mer against bucket `smask`, reverse flag 1 (decided by the FIRST value of each key: on-disk searcher
@@ -134,17 +143,17 @@ __device__ __forceinline__ bool probe_may_hit(const ProbeParams& P, u32 bucket, 
 // data — captured k-mer present, first-owner test of the reversed k-mer, anchor presence bit — and compaction of the surviving probes.
 // Phase B (k_probe_find2, one thread per survivor): the dependent random HBM accesses (anchor start, key search, value flags) with all
 // lanes of a warp on the long path instead of ~1 in 3.
-struct Surv { u64 kmer; u32 qi; u32 aslot_dir; u32 lo, n; };   // aslot_dir = (bucket*NA + anchor) | dir << 31; [lo, lo+n) = rows of the query table holding the captured k-mer
+struct __align__(16) Surv { u64 kmer; u32 qi; u32 bucket_dir; u32 lo, n; u32 arank, pad; };   // one 32-byte sector. bucket_dir = bucket | dir << 31; arank = rank of the probe's anchor among the bucket's present anchors; [lo, lo+n) = rows of the query table holding the captured k-mer
 __global__ void __launch_bounds__(256) k_probe_filter(ProbeParams P, CapSoA cap, const u32* __restrict__ owner, const u64* __restrict__ koff, u64 nslot, Surv* __restrict__ surv, u32* __restrict__ nsurv, u32 cap_surv, u64* __restrict__ stats) {
   u64 qi = blockIdx.x * (u64)blockDim.x + threadIdx.x; bool s0 = false, s1 = false; Surv a, b; u32 issued = 0;
   if (qi < nslot) { u64 kmer = cap.kmer[qi];
     if (kmer != 0) { u32 q = (u32)(qi / P.m); int i = (int)(qi % P.m); const int s2 = (P.k - P.p) << 1; const u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1;
-      { u64 left = kmer & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++; if (probe_may_hit(P, (u32)i, left, ash)) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.aslot_dir = (u32)aslot; a.lo = cap.lo[qi]; a.n = cap.n[qi]; } }
-      u32 lo = cap.lo[qi]; if (owner[koff[q] + lo] == (u32)i) { u64 rv = kmer_reverse62(kmer, P.k); u32 sm = cap.smask[qi]; u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)sm * P.NA + an; issued++;
-        if (probe_may_hit(P, sm, left, ash)) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = lo; b.n = cap.n[qi]; } } } }
+      { u64 left = kmer & ~low; issued++; if (probe_may_hit(P, (u32)i, left, ash, a.arank)) { s0 = true; a.kmer = kmer; a.qi = (u32)qi; a.bucket_dir = (u32)i; a.pad = 0; a.lo = cap.lo[qi]; a.n = cap.n[qi]; } }
+      u32 lo = cap.lo[qi]; if (owner[koff[q] + lo] == (u32)i) { u64 rv = kmer_reverse62(kmer, P.k); u32 sm = cap.smask[qi]; u64 left = rv & ~low; issued++;
+        if (probe_may_hit(P, sm, left, ash, b.arank)) { s1 = true; b.kmer = rv; b.qi = (u32)qi; b.bucket_dir = sm | 0x80000000u; b.pad = 0; b.lo = lo; b.n = cap.n[qi]; } } } }
   int lane = threadIdx.x & 31; u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1); u32 tot = __popc(b0) + __popc(b1);
   if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
-    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = b; } }
+    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = a; if (P.bcnt) atomicAdd(&P.bcnt[a.bucket_dir & 0x7FFFFFFFu], 1u); } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = b; if (P.bcnt) atomicAdd(&P.bcnt[b.bucket_dir & 0x7FFFFFFFu], 1u); } }
   if (stats) { for (int o = 16; o; o >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, o); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
 }
 // K1b + K2 phase A fused (queries whose sorted k-mer table fits in shared memory): one CTA per query captures every mask (pass 1, as
@@ -173,13 +182,13 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
   __shared__ u32 e_cnt[2][32], e_base[2]; int ep = 0; const int wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   auto emit = [&](bool have, const Surv& r) { const u32 bal = __ballot_sync(FULLMASK, have); if (lane == 0) e_cnt[ep][wid] = __popc(bal); __syncthreads();
     if (threadIdx.x == 0) { u32 tot = 0; for (int i = 0; i < nwarp; i++) { const u32 c = e_cnt[ep][i]; e_cnt[ep][i] = tot; tot += c; } e_base[ep] = tot ? atomicAdd(nsurv, tot) : 0u; } __syncthreads();
-    if (have) { const u32 w = e_base[ep] + e_cnt[ep][wid] + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; } ep ^= 1; };
+    if (have) { const u32 w = e_base[ep] + e_cnt[ep][wid] + __popc(bal & ((1u << lane) - 1)); if (w < cap_surv) surv[w] = r; if (P.bcnt) atomicAdd(&P.bcnt[r.bucket_dir & 0x7FFFFFFFu], 1u); } ep ^= 1; };
   // pass 1: masks
   for (int ib = 0; ib < m; ib += blockDim.x) { int i = ib + threadIdx.x; bool s0 = false; Surv r;
     if (i < m) { u64 mk = masks[i]; u32 p = (u32)(mk >> psh); u32 lo = pst[p], hi = pen[p]; if (lo == 0xFFFFFFFFu) { lo = 0; hi = n; } xor_argmin_range(tab, lo, hi, mk);
       u64 km = tab[lo]; bool lc = (lcb[lo >> 5] >> (lo & 31)) & 1;   // km==0 is DUST-low-complexity too, as in the reference
-      if (!lc) { atomicMin(&own[lo], (u32)i); u64 left = km & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)i * P.NA + an; issued++;
-        if (probe_may_hit(P, (u32)i, left, ash)) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot; r.lo = lo; r.n = hi - lo; } }
+      if (!lc) { atomicMin(&own[lo], (u32)i); u64 left = km & ~low; issued++;
+        if (probe_may_hit(P, (u32)i, left, ash, r.arank)) { s0 = true; r.kmer = km; r.qi = (u32)((u64)q * m + i); r.bucket_dir = (u32)i; r.pad = 0; r.lo = lo; r.n = hi - lo; } }
       if (DUMP) { u64 w = (u64)q * m + i; cap.kmer[w] = lc ? 0 : km; cap.lo[w] = lo; cap.n[w] = hi - lo; cap.smask[w] = 0; } }
     emit(s0, r); }
   __syncthreads();
@@ -188,13 +197,26 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
     if (rr < n) { u32 i = own[rr];
       if (i != 0xFFFFFFFFu) { u64 km = tab[rr]; u32 c = 1; while (rr + c < n && tab[rr + c] == km) c++;
         u64 rv = kmer_reverse62(km, k); u32 mp = (u32)(rv >> msh); u32 a = mask_pstart[mp], b = mask_pstart[mp + 1]; if (a == b) { a = 0; b = (u32)m; } xor_argmin_range(masks, a, b, rv);
-        u64 left = rv & ~low; u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); u64 aslot = (u64)a * P.NA + an; issued++;
-        if (probe_may_hit(P, a, left, ash)) { s1 = true; r.kmer = rv; r.qi = (u32)((u64)q * m + i); r.aslot_dir = (u32)aslot | 0x80000000u; r.lo = rr; r.n = c; }
+        u64 left = rv & ~low; issued++;
+        if (probe_may_hit(P, a, left, ash, r.arank)) { s1 = true; r.kmer = rv; r.qi = (u32)((u64)q * m + i); r.bucket_dir = a | 0x80000000u; r.pad = 0; r.lo = rr; r.n = c; }
         if (DUMP) { cap.smask[(u64)q * m + i] = a; owner_g[o + rr] = i; } } }
     emit(s1, r); }
   if (stats) { for (int of = 16; of; of >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, of); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued); }
 }
 
+// K2 phase A': the surviving probes regrouped by mask bucket (counting sort on the bucket id: histogram, one-CTA scan, scatter). The probes leave the
+// capture kernel in query order, i.e. scattered over all m buckets: every lookup then costs three to four random 64-byte DRAM bursts (start of the anchor,
+// first key, next key) and the kernel sits at the DRAM burst rate (~79 G/s measured) while moving four times the bytes it needs. Grouped by bucket, a warp's
+// 32 probes search the SAME bucket: its entries (tens of KB) and anchor starts are fetched from DRAM once and then hit in L2, and the scatter itself
+// writes m sequential streams that L2 merges into full lines.
+__global__ void __launch_bounds__(256) k_surv_hist(const Surv* __restrict__ s, u32 ns, u32* __restrict__ cnt) { const u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t < ns) atomicAdd(&cnt[s[t].bucket_dir & 0x7FFFFFFFu], 1u); }
+__global__ void __launch_bounds__(1024) k_bucket_scan(u32* __restrict__ cnt, int m) {   /* in-place exclusive prefix sum over m counters, one CTA */
+  __shared__ u32 s_part[1024]; const int per = (m + 1023) / 1024, b = threadIdx.x * per, e = min(m, b + per); u32 sum = 0; for (int i = b; i < e; i++) sum += cnt[i]; s_part[threadIdx.x] = sum; __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) { u32 v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0; __syncthreads(); s_part[threadIdx.x] += v; __syncthreads(); }
+  u32 run = s_part[threadIdx.x] - sum; for (int i = b; i < e; i++) { const u32 c = cnt[i]; cnt[i] = run; run += c; } }
+__global__ void __launch_bounds__(256) k_surv_scatter(const Surv* __restrict__ s, u32 ns, u32* __restrict__ cur, Surv* __restrict__ out) { const u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= ns) return;
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(s + t), b = *(reinterpret_cast<const ulonglong2*>(s + t) + 1); const u32 pos = atomicAdd(&cur[(u32)(a.y >> 32) & 0x7FFFFFFFu], 1u);
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(out + pos); o[0] = a; o[1] = b; }
 // K2 phase B, the roofline kernel: one thread per surviving probe. Anchor start (one random 32-byte sector), galloping + binary lower bound
 // over the bucket's 16-byte entries (two per sector), then the range walk over the same records: the entry that ends the search already
 // holds the first-value flag and the value count, so no second or third array is touched (round 1 read keys, val_off and vals[v0]).
@@ -202,14 +224,17 @@ __global__ void __launch_bounds__(1024) k_capture2(const u64* __restrict__ qkeys
 template <bool STATS>
 __global__ void __launch_bounds__(256) k_probe_find2(ProbeParams P, const Surv* __restrict__ surv, u32 ns, ProbeHit* __restrict__ hits, u32* __restrict__ nhits, u32 cap_hits, u64* __restrict__ stats) {
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; bool have = false; ProbeHit h; u32 steps = 0, ne = 0, lg = 0, hsec = 0, nout = 0;
-  if (t < ns) { Surv sv = surv[t]; const u32 dir = sv.aslot_dir >> 31; u32 aslot = sv.aslot_dir & 0x7FFFFFFFu; const u32 bucket = aslot / (u32)P.NA; u64 kmer = sv.kmer;
-    int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; const u32 as = anchor_start_of(P, bucket, aslot - bucket * (u32)P.NA);
-    const u64 b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1]; const SeedEntry* __restrict__ E = P.entries; u64 lo = b0 + as, hi = b1;
+  if (t < ns) { const u64 pol_tab = l2_policy(P.hints ? 2 : 0), pol_str = l2_policy(P.hints ? 1 : 0);
+    Surv sv; { const ulonglong2 a = ld_hint_v2(surv + t, pol_str), b = ld_hint_v2((const u8*)(surv + t) + 16, pol_str); sv.kmer = a.x; sv.qi = (u32)a.y; sv.bucket_dir = (u32)(a.y >> 32); sv.lo = (u32)b.x; sv.n = (u32)(b.x >> 32); sv.arank = (u32)b.y; }
+    const u32 dir = sv.bucket_dir >> 31, bucket = sv.bucket_dir & 0x7FFFFFFFu; u64 kmer = sv.kmer;
+    int s2 = (P.k - P.p) << 1; u64 low = (P.p < P.k) ? ((1ull << s2) - 1) : 0; u64 left = kmer & ~low, right = kmer | low; const u32 as = anchor_start_of(P, bucket, sv.arank, pol_tab);
+    const u64 b0 = ld_hint_u64(P.bucket_off + bucket, pol_tab), b1 = ld_hint_u64(P.bucket_off + bucket + 1, pol_tab); const SeedEntry* __restrict__ E = P.entries; u64 lo = b0 + as, hi = b1;
+    auto keyat = [&](u64 i) { return ld_hint_u64(&E[i].key, pol_str); };
     u64 l = lo, r = lo;   // lower bound of `left` in [lo, hi): the anchor's first key is tested first (after the Bloom filter most probes end right there: one sector), then gallop + binary search
-    if (E[lo].key < left) { u64 step = 1; while (l + step < hi && E[l + step].key < left) { l += step; step <<= 1; steps++; } r = min(hi, l + step); l = l + 1;
-      while (l < r) { u64 mid = (l + r) >> 1; if (E[mid].key < left) l = mid + 1; else r = mid; steps++; } }
+    if (keyat(lo) < left) { u64 step = 1; while (l + step < hi && keyat(l + step) < left) { l += step; step <<= 1; steps++; } r = min(hi, l + step); l = l + 1;
+      while (l < r) { u64 mid = (l + r) >> 1; if (keyat(mid) < left) l = mid + 1; else r = mid; steps++; } }
     u64 e0 = l; u32 na = 0;
-    while (e0 + ne < hi) { const ulonglong2 raw = *reinterpret_cast<const ulonglong2*>(E + e0 + ne); if (raw.x > right) break; const u32 nf = (u32)(raw.y >> 32); if ((nf >> 31) == dir) na += nf & 0x7FFFFFFFu; ne++; }
+    while (e0 + ne < hi) { const ulonglong2 raw = ld_hint_v2(E + e0 + ne, pol_str); if (raw.x > right) break; const u32 nf = (u32)(raw.y >> 32); if ((nf >> 31) == dir) na += nf & 0x7FFFFFFFu; ne++; }
     if (na) { have = true; h.q = sv.qi / (u32)P.m; h.mask_dir = (u32)((sv.qi % (u32)P.m) << 1 | dir); h.e0 = e0; h.ne = ne; h.lo = sv.lo; h.n = sv.n; h.kmer = kmer; h.nanch = na * sv.n; h.bucket = bucket; }
     if (STATS) { const int ash = (P.k - P.mask_prefix - P.anchor_prefix) << 1; const u64 an = E[lo].key >> ash; u32 n_a = 0; while (lo + n_a < hi && (E[lo + n_a].key >> ash) == an) n_a++; lg = 32 - __clz(n_a); hsec = (16 * ne + 31) / 32; nout = na; }   // ceil(log2(n_a + 1)) = bit length of n_a
   }
@@ -233,14 +258,14 @@ __global__ void __launch_bounds__(256) k_c5_gen(ProbeParams P, const u64* __rest
     if (r & 1) { bucket = (u32)((r >> 1) % (u64)P.m); const u64 j = mix64(r) % per; key = synth_key(masks[bucket], P.mask_prefix, k, per, j, iseed, bucket); const u64 r2 = mix64(r ^ 0x5bd1e995ull); const int t = (int)(r2 % 17); if (t) key ^= (r2 >> 8) & ((1ull << (2 * t)) - 1); }
     else { key = r >> 2; bucket = argmin_mask(key); }
     const int s2 = (k - P.p) << 1; const u64 low = (P.p < k) ? ((1ull << s2) - 1) : 0; const int ash = (k - P.mask_prefix - P.anchor_prefix) << 1;
-    if ((int)bucket >= mask_lo && (int)bucket < mask_hi) { issued++; const u64 left = key & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)bucket * P.NA + an;
-      if (probe_may_hit(P, bucket, left, ash)) { s0 = true; a.kmer = key; a.qi = (u32)q; a.aslot_dir = (u32)aslot; a.lo = 0; a.n = 1; } }
+    if ((int)bucket >= mask_lo && (int)bucket < mask_hi) { issued++; const u64 left = key & ~low;
+      if (probe_may_hit(P, bucket, left, ash, a.arank)) { s0 = true; a.kmer = key; a.qi = (u32)q; a.bucket_dir = bucket; a.pad = 0; a.lo = 0; a.n = 1; } }
     const u64 rv = kmer_reverse62(key, k); const u32 b2 = argmin_mask(rv);
-    if ((int)b2 >= mask_lo && (int)b2 < mask_hi) { issued++; const u64 left = rv & ~low; const u32 an = (u32)((left >> ash) & (u64)(P.NA - 1)); const u64 aslot = (u64)b2 * P.NA + an;
-      if (probe_may_hit(P, b2, left, ash)) { s1 = true; b.kmer = rv; b.qi = (u32)q; b.aslot_dir = (u32)aslot | 0x80000000u; b.lo = 0; b.n = 1; } } }
+    if ((int)b2 >= mask_lo && (int)b2 < mask_hi) { issued++; const u64 left = rv & ~low;
+      if (probe_may_hit(P, b2, left, ash, b.arank)) { s1 = true; b.kmer = rv; b.qi = (u32)q; b.bucket_dir = b2 | 0x80000000u; b.pad = 0; b.lo = 0; b.n = 1; } } }
   const u32 b0 = __ballot_sync(FULLMASK, s0), b1 = __ballot_sync(FULLMASK, s1), tot = __popc(b0) + __popc(b1);
   if (tot) { u32 base = 0; if (lane == 0) base = atomicAdd(nsurv, tot); base = __shfl_sync(FULLMASK, base, 0);
-    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap) surv[w] = a; } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap) surv[w] = b; } }
+    if (s0) { u32 w = base + __popc(b0 & ((1u << lane) - 1)); if (w < cap) surv[w] = a; if (P.bcnt) atomicAdd(&P.bcnt[a.bucket_dir & 0x7FFFFFFFu], 1u); } if (s1) { u32 w = base + __popc(b0) + __popc(b1 & ((1u << lane) - 1)); if (w < cap) surv[w] = b; if (P.bcnt) atomicAdd(&P.bcnt[b.bucket_dir & 0x7FFFFFFFu], 1u); } }
   for (int o = 16; o; o >>= 1) issued += __shfl_xor_sync(FULLMASK, issued, o); if (lane == 0 && issued) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)issued);
 }
 
@@ -342,7 +367,7 @@ static void sketch_tables(lmg_index* ix, QBatch& B) {
 struct CapBufs { DBuf<u64> kmer; DBuf<u32> lo, n, smask; CapSoA soa() { CapSoA c; c.kmer = kmer.p; c.lo = lo.p; c.n = n.p; c.smask = smask.p; return c; } void free() { kmer.free(); lo.free(); n.free(); smask.free(); } };
 struct Anchors { u64 n = 0; DBuf<u64> hi, lo; };
 
-static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_cbase = I.d_anchor_cbase; P.anchor_cstart = I.d_anchor_cstart; P.anchor_cum = I.d_anchor_cum; P.anchor_bits = I.d_anchor_bits; P.pbloom = I.d_pbloom; P.pbmask = I.pbmask; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; return P; }
+static ProbeParams probe_params(const Image& I, int p) { ProbeParams P; P.bucket_off = I.d_bucket_off; P.bucket_voff = I.d_bucket_voff; P.entries = I.d_entries; P.vals = I.d_vals; P.anchor_cbase = I.d_anchor_cbase; P.anchor_cstart = I.d_anchor_cstart; P.anchor_cum = I.d_anchor_cum; P.anchor_bits = I.d_anchor_bits; P.pbloom = I.d_pbloom; P.pbmask = I.pbmask; P.m = I.m; P.k = I.k; P.NA = I.NA; P.mask_prefix = I.mask_prefix; P.anchor_prefix = I.anchor_prefix; P.p = p; P.anchor_cstart16 = I.d_anchor_cstart16; P.bcnt = nullptr; static const int hints = getenv("LMG_L2_HINTS") ? 1 : 0; P.hints = hints; return P; }   /* measured on C2: evict-first entries + evict-last tables lower the L2 hit rate (27 % -> 19 %) and cost 6 %: off unless asked for */
 
 template <class K, class V> static void radix_sort_pairs(lmg_index* ix, DBuf<K>& k_in, DBuf<K>& k_out, DBuf<V>& v_in, DBuf<V>& v_out, u64 n, int begin_bit, int end_bit) {
   size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, (i64)n, begin_bit, end_bit, ix->st);
@@ -353,10 +378,10 @@ static int bits_for(u64 v) { int b = 1; while ((v >> b) && b < 64) b++; return b
 
 // K1b + K2 phase A: surviving probes of the batch. Fused kernel when every query table fits in shared memory next to its owner array,
 // otherwise (long queries) capture into HBM arrays with several CTAs per query, then the separate filter kernel.
-struct Survivors { DBuf<Surv> d; u32 n = 0; };
+struct Survivors { DBuf<Surv> d; DBuf<u32> bcnt; u32 n = 0; };   // bcnt: survivors per bucket, counted while they are emitted
 static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivors& SV, CapBufs* dump_cap, DBuf<u32>* dump_owner) {
   cudaStream_t st = ix->st; const Image& I = ix->img; if (prm->min_prefix < I.mask_prefix + I.anchor_prefix || prm->min_prefix > I.k) throw std::runtime_error("the minimum prefix length should be in the range of [maskPrefix+anchorPrefix, k]");  // kv-searcher.go:202
-  ProbeParams P = probe_params(I, prm->min_prefix); const u64 nslot = (u64)B.nq * I.m, nprobe = nslot * 2; DBuf<u32> nsv(1, st); DBuf<u64> dstats(8, st);
+  ProbeParams P = probe_params(I, prm->min_prefix); const u64 nslot = (u64)B.nq * I.m, nprobe = nslot * 2; DBuf<u32> nsv(1, st); DBuf<u64> dstats(8, st); SV.bcnt.alloc((u64)I.m + 1, st); P.bcnt = SV.bcnt.p;
   if (!ix->kev[0]) { cudaEventCreate(&ix->kev[0]); cudaEventCreate(&ix->kev[1]); cudaEventCreate(&ix->kev[2]); }
   u64 maxn = 0; for (int q = 0; q < B.nq; q++) maxn = std::max(maxn, B.h_koff[q + 1] - B.h_koff[q]);
   const bool fused = maxn <= 16384 && maxn * 12 + 16384 <= ix->smem_optin && !getenv("LMG_NO_FUSED_CAPTURE"); ix->ms[8] = 0;
@@ -370,7 +395,7 @@ static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Sur
     k_capture<<<B.nq * slices, 256, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, I.m, I.k, slices, cap->soa(), owner->p, need, ix->use_tma, I.d_mask_pstart, I.mask_pbits); KERNEL_CHECK(); }
   // capacity: a quarter of all probes first (about 10 % survive on the bench workload), everything on overflow
   u64 capS = std::max<u64>(1u << 20, nprobe / 4);
-  for (int attempt = 0; attempt < 2; attempt++) { SV.d.alloc(capS, st); nsv.zero(); dstats.zero();
+  for (int attempt = 0; attempt < 2; attempt++) { SV.d.alloc(capS, st); nsv.zero(); dstats.zero(); SV.bcnt.zero();
     if (fused) { u32 mx = (u32)((maxn + 1) & ~1ull); size_t smem = (size_t)mx * 12 + 16;
       if (dump_cap) { k_capture2<true><<<B.nq, cthreads, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), owner->p, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); }
       else { k_capture2<false><<<B.nq, cthreads, smem, st>>>(B.qkeys.p, B.koff.p, I.d_masks, P, cap->soa(), nullptr, mx, ix->use_tma, I.d_mask_pstart, I.mask_pbits, SV.d.p, nsv.p, (u32)std::min<u64>(capS, 0xFFFFFFFFu), dstats.p); KERNEL_CHECK(); } }
@@ -380,20 +405,30 @@ static void probe_survivors(lmg_index* ix, QBatch& B, const lmg_params* prm, Sur
   ix->counters[0] = dstats.to_host()[0]; ix->counters[1] = SV.n; ix->counters[8] = nprobe;
 }
 
+// regroup `in` by bucket into `out` on stream sl (same capacity); LMG_NO_REGROUP keeps the capture order
+static bool regroup_survivors(cudaStream_t sl, const Surv* in, u32 ns, int m, Surv* out, u32* bcnt, bool have_hist) {   /* have_hist: the kernel that emitted the probes already counted them per bucket (ProbeParams::bcnt); bcnt is consumed */
+  static const bool off = getenv("LMG_NO_REGROUP") != nullptr; if (off || ns == 0) return false;
+  if (!have_hist) { CUDA_CHECK(cudaMemsetAsync(bcnt, 0, ((size_t)m + 1) * 4, sl)); k_surv_hist<<<cdiv(ns, 256), 256, 0, sl>>>(in, ns, bcnt); KERNEL_CHECK(); }
+  k_bucket_scan<<<1, 1024, 0, sl>>>(bcnt, m); KERNEL_CHECK();
+  k_surv_scatter<<<cdiv(ns, 256), 256, 0, sl>>>(in, ns, bcnt, out); KERNEL_CHECK(); return true; }
 // K2 phase B: index lookup on the surviving probes -> anchors sorted by (query, genome, QBegin, QEnd desc, TBegin, qrc, trc)
 static void seed_probe(lmg_index* ix, QBatch& B, const lmg_params* prm, Survivors& SV, Anchors& A, bool stats) {
   cudaStream_t st = ix->st; const Image& I = ix->img; ProbeParams P = probe_params(I, prm->min_prefix); DBuf<u32> nh(1, st); DBuf<u64> dstats(8, st); dstats.zero(); const u32 ns = SV.n; DBuf<Surv>& surv = SV.d;
   // phase B: index lookup on the survivors
   DBuf<ProbeHit> hits; u64 capH = std::max<u64>(1u << 18, (u64)ns / 2 + 1024); u32 nhit = 0;
+  cudaStream_t sl = getenv("LMG_NO_PRIO_LOOKUP") ? st : ix->st_hi; DBuf<Surv> grouped; DBuf<u32> bcnt; const Surv* sp = surv.p; float fr = 0; bool fr_valid = ns != 0;
+  if (ns) { grouped.alloc(ns, st); const bool hh = SV.bcnt.p != nullptr; if (!hh) bcnt.alloc((u64)I.m + 1, st); if (sl != st) { cudaEventRecord(ix->ev_hi[0], st); cudaStreamWaitEvent(sl, ix->ev_hi[0], 0); }
+    cudaEventRecord(ix->kev[0], sl); if (regroup_survivors(sl, surv.p, ns, I.m, grouped.p, hh ? SV.bcnt.p : bcnt.p, hh)) sp = grouped.p; }
   for (int attempt = 0; attempt < 2 && ns; attempt++) { hits.alloc(capH, st); nh.zero(); if (attempt) CUDA_CHECK(cudaMemsetAsync(dstats.p + 2, 0, 40, st));
     // The lookup is the one memory-bound kernel of the path: it runs on the lane's HIGH-PRIORITY stream so that its CTAs are scheduled ahead of the issue-bound
     // kernels of the other lanes that share the GPU (they would otherwise stretch it 2x without gaining anything themselves).
-    cudaStream_t sl = getenv("LMG_NO_PRIO_LOOKUP") ? st : ix->st_hi; if (sl != st) { cudaEventRecord(ix->ev_hi[0], st); cudaStreamWaitEvent(sl, ix->ev_hi[0], 0); }
-    cudaEventRecord(ix->kev[1], sl); if (stats) k_probe_find2<true><<<cdiv(ns, 256), 256, 0, sl>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), dstats.p); else k_probe_find2<false><<<cdiv(ns, 256), 256, 0, sl>>>(P, surv.p, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], sl);
+    if (attempt) fr_valid = false;   /* kev[1] is recorded again: the regroup time of this (rare, hit-buffer overflow) call is not reported */
+    if (sl != st) { cudaEventRecord(ix->ev_hi[0], st); cudaStreamWaitEvent(sl, ix->ev_hi[0], 0); }   /* hits / counters were (re)allocated and cleared on st */
+    cudaEventRecord(ix->kev[1], sl); if (stats) k_probe_find2<true><<<cdiv(ns, 256), 256, 0, sl>>>(P, sp, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), dstats.p); else k_probe_find2<false><<<cdiv(ns, 256), 256, 0, sl>>>(P, sp, ns, hits.p, nh.p, (u32)std::min<u64>(capH, 0xFFFFFFFFu), nullptr); KERNEL_CHECK(); cudaEventRecord(ix->kev[2], sl);
     if (sl != st) { cudaEventRecord(ix->ev_hi[1], sl); cudaStreamWaitEvent(st, ix->ev_hi[1], 0); }
     nhit = nh.to_host()[0]; if (nhit <= capH) break; capH = (u64)ns + 1024; }
   if (!hits.p) hits.alloc(16, st);
-  { float fb = 0; if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] += fb; ix->counters[13] = (u64)(fb * 1000); }
+  { float fb = 0; if (ns) { cudaEventSynchronize(ix->kev[2]); cudaEventElapsedTime(&fb, ix->kev[1], ix->kev[2]); } ix->ms[8] += fb; ix->counters[13] = (u64)(fb * 1000); if (fr_valid) { cudaEventElapsedTime(&fr, ix->kev[0], ix->kev[1]); ix->counters[12] += (u64)(fr * 1000); } }   /* [12]: filter kernel of the non-fused capture + the regrouping pass */
   { auto sdt = dstats.to_host(); if (stats) { ix->counters[2] = sdt[2]; ix->counters[3] = sdt[3]; ix->pstat[0] = sdt[4]; ix->pstat[1] = sdt[5]; ix->pstat[2] = sdt[6]; } ix->counters[4] = nhit; }
   A.n = 0; if (nhit == 0) return;
   DBuf<u64> hoff(nhit + 1, st);
@@ -942,7 +977,8 @@ struct WfDir { i32 lo, hi; u32 base; u32 nullmask; i32 elo, ehi; };   // [lo,hi]
 
 // One warp per alignment; persistent warps pull jobs from a queue. Wavefront offsets live in a per-warp HBM slab
 // (directory + offsets), lanes own diagonals, extension compares bases straight from the 2-bit genome / query arrays.
-__global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 njobs, u32* __restrict__ next_job,
+__device__ __forceinline__ u64 fetch64(const u64* __restrict__ W, i32 pos);
+__global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 njobs, u32* __restrict__ next_job, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb,
                                              const u8* __restrict__ qpacked, const u8* __restrict__ qamask, const u64* __restrict__ qboff, const u8* __restrict__ g2bit, const u64* __restrict__ g_off,
                                              i32* __restrict__ slabs, u64 slab_words, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int adaptive) {
   const int X = 4, OE = 8, E = 2, STEP = 2; int lane = threadIdx.x & 31; u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i32* slab = slabs + (u64)warp * slab_words;
@@ -954,7 +990,11 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
     // slab layout: [directory: ndir x 4 words][offsets ...]
     const u32 ndir = (u32)((4 * (i64)max(plen, tlen) + 16) / STEP + 2); WfDir* dir = (WfDir*)slab; u64 used = (u64)ndir * 6; bool overflow = used + 64 > slab_words;
     i32* offs = slab;
-    auto extend = [&](i32 k, i32 h) { i32 vv = h - k; while (vv < plen && h < tlen && qcmp(v, q0 + vv) == tbase(v, t0 + h)) { vv++; h++; } return h; };
+    // extension on the packed words of k_wfa_prep (32 bases per XOR + CLZ; ambiguous query bases never match), as in k_wfa_fast / k_wfa_reg
+    const u32 nqw = (u32)((plen + 31) / 32 + 2); const u64* Qw = words + woff[2 * jb]; const u64* Aw = Qw + nqw; const u64* Tw = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0; (void)v; (void)q0; (void)t0;
+    auto extend = [&](i32 k, i32 h) { i32 vv = h - k; for (;;) { const i32 rem = min(plen - vv, tlen - h); if (rem <= 0) break; u64 x = fetch64(Qw, vv) ^ fetch64(Tw, h); if (amb) x |= fetch64(Aw, vv); i32 n = x ? (__clzll(x) >> 1) : 32; n = min(n, rem); vv += n; h += n; if (n < 32) break; } return h; };
+    // wavefront value through a directory record held in registers (the three source levels of a score are loaded once per level)
+    auto getd = [&](const WfDir& d, int comp, i32 k) -> i32 { if ((d.nullmask >> comp) & 1) return WF_NULL; if (k < d.lo || k > d.hi) return WF_NULL; return offs[d.base + (u32)comp * (u32)(d.hi - d.lo + 1) + (u32)(k - d.lo)]; };
     auto getw = [&](i32 sidx, int comp, i32 k) -> i32 { if (sidx < 0) return WF_NULL; WfDir d = dir[sidx]; if ((d.nullmask >> comp) & 1) return WF_NULL; if (k < d.lo || k > d.hi) return WF_NULL; return offs[d.base + (u32)comp * (u32)(d.hi - d.lo + 1) + (u32)(k - d.lo)]; };
     i32 s = 0; bool done = false;
     if (!overflow) { if (lane == 0) { WfDir d; d.lo = 0; d.hi = 0; d.elo = 0; d.ehi = 0; d.base = (u32)used; d.nullmask = 6; dir[0] = d; offs[used] = extend(0, 0); } used += 3; __syncwarp(); done = (getw(0, 0, kend) >= tlen); }
@@ -968,9 +1008,9 @@ __global__ void __launch_bounds__(128) k_wfa(const HspJob* __restrict__ jobs, co
       u32 w = (u32)(hi - lo + 1); if (used + 3ull * w + 64 > slab_words) { overflow = true; break; }
       u32 base = (u32)used; bool anyM = false, anyI = false, anyD = false;
       for (i32 k = lo + lane; k <= hi; k += 32) {
-        i32 a = getw(io, 0, k - 1), b2 = getw(ie, 1, k - 1); i32 ins = max(a, b2); ins = (ins <= WF_NULL) ? WF_NULL : ins + 1;
-        a = getw(io, 0, k + 1); b2 = getw(ie, 2, k + 1); i32 del = max(a, b2);
-        i32 mis = getw(ix, 0, k); mis = (mis <= WF_NULL) ? WF_NULL : mis + 1;
+        i32 a = getd(dop, 0, k - 1), b2 = getd(de, 1, k - 1); i32 ins = max(a, b2); ins = (ins <= WF_NULL) ? WF_NULL : ins + 1;
+        a = getd(dop, 0, k + 1); b2 = getd(de, 2, k + 1); i32 del = max(a, b2);
+        i32 mis = getd(dx, 0, k); mis = (mis <= WF_NULL) ? WF_NULL : mis + 1;
         if (!(ins > WF_NULL && ins >= 0 && ins - k >= 0 && ins <= tlen && ins - k <= plen)) ins = WF_NULL;
         if (!(del > WF_NULL && del >= 0 && del - k >= 0 && del <= tlen && del - k <= plen)) del = WF_NULL;
         if (!(mis > WF_NULL && mis >= 0 && mis - k >= 0 && mis <= tlen && mis - k <= plen)) mis = WF_NULL;
@@ -1186,13 +1226,15 @@ __global__ void __launch_bounds__(128) k_wfa_bt(const ExtOut* __restrict__ ext, 
 // slot 0, ~25 % divergence needs two or three slots. Window position 0 never holds a live cell: its slab word stores kb of the level for the backtrace.
 // This is what lets long, indel-rich alignments (ONT reads: |tlen - plen| of hundreds, tens of thousands of levels) stay on the register path.
 struct WrCell { i32 om, oi, od, dv; u32 word; };
+template <int NS>
 __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restrict__ ext, const u64* __restrict__ woff, const u64* __restrict__ words, const u32* __restrict__ has_amb, const u32* __restrict__ job_ids, u32 job0, u32 njobs, u32* __restrict__ next_job,
                                                          u32* __restrict__ slabs, const u64* __restrict__ slab_off, WfaOut* __restrict__ outs, int adaptive) {
   extern __shared__ __align__(16) u8 wr_smem[];
+  constexpr int W = 32 * NS;   /* diagonals in the window */
   const int X2 = 2, OE2 = 4, E2 = 1; const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5; u64* seqb = (u64*)wr_smem + (size_t)wib * WR_SEQW; const int lm1 = (lane + 31) & 31, lp1 = (lane + 1) & 31;
   for (;;) {
     u32 jr = 0; if (lane == 0) jr = atomicAdd(next_job, 1u); jr = __shfl_sync(FULLMASK, jr, 0); if (jr >= njobs) return; const u32 jb = job_ids ? job_ids[job0 + jr] : job0 + jr;
-    u32* slab = slabs + slab_off[jr] * WR_W; const i32 lmax = (i32)(slab_off[jr + 1] - slab_off[jr]);   // levels this alignment may use
+    u32* slab = slabs + slab_off[jr] * W; const i32 lmax = (i32)(slab_off[jr + 1] - slab_off[jr]);   // levels this alignment may use
     ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32 nqw = (u32)((plen + 31) / 32 + 2);
     const u64* Q = words + woff[2 * jb]; const u64* A = Q + nqw; const u64* T = words + woff[2 * jb + 1]; const bool amb = has_amb[jb] != 0;
     { const u32 ntw = (u32)((tlen + 31) / 32 + 2), nA = amb ? nqw : 0; __syncwarp();
@@ -1211,72 +1253,72 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
       return c; };
     i32 hlo[4], hhi[4]; u32 hnull[4]; for (int i = 0; i < 4; i++) { hlo[i] = 0; hhi[i] = -1; hnull[i] = 7; }
     i32 kb = -16;   // diagonal 0 on lane 16 of slot 0
-    i32 m1[WR_NS], m2[WR_NS], m3[WR_NS], m4[WR_NS], i1[WR_NS], d1[WR_NS];   // per slot: M of levels L-1..L-4, I / D of level L-1 on this lane's diagonals; -1 = null
+    i32 m1[NS], m2[NS], m3[NS], m4[NS], i1[NS], d1[NS];   // per slot: M of levels L-1..L-4, I / D of level L-1 on this lane's diagonals; -1 = null
 #pragma unroll
-    for (int s_ = 0; s_ < WR_NS; s_++) { m1[s_] = m2[s_] = m3[s_] = m4[s_] = i1[s_] = d1[s_] = -1; }
+    for (int s_ = 0; s_ < NS; s_++) { m1[s_] = m2[s_] = m3[s_] = m4[s_] = i1[s_] = d1[s_] = -1; }
     if (kb + lane == 0) m1[0] = extend(0, 0); hlo[0] = 0; hhi[0] = 0; hnull[0] = 6; slab[lane] = lane == 0 ? (u32)kb : 0u;
-    auto at = [&](const i32 (&v)[WR_NS], i32 j) { i32 r = -1;   // value on window position j, warp-uniform j
+    auto at = [&](const i32 (&v)[NS], i32 j) { i32 r = -1;   // value on window position j, warp-uniform j
 #pragma unroll
-      for (int t = 0; t < WR_NS; t++) { const i32 x = __shfl_sync(FULLMASK, v[t], j & 31); if ((j >> 5) == t) r = x; } return r; };
+      for (int t = 0; t < NS; t++) { const i32 x = __shfl_sync(FULLMASK, v[t], j & 31); if ((j >> 5) == t) r = x; } return r; };
     i32 L = 0, why = 0; bool done = false, overflow = false; { const i32 v0 = at(m1, 0 - kb); done = (kend == 0 && v0 >= tlen); }   // why: reason for leaving the register path (-1 level capacity, -2 band wider than the window, -3 not eligible)
     while (!done) {
       L++; if (L >= lmax) { overflow = true; why = -1; break; }
       const bool nx = (L - X2 < 0) || (hnull[X2 - 1] & 1), no = (L - OE2 < 0) || (hnull[OE2 - 1] & 1), ni = (hnull[E2 - 1] >> 1) & 1, nd = (hnull[E2 - 1] >> 2) & 1;
       i32 lo = INT32_MAX, hi = INT32_MIN; const bool allnull = nx && no && ni && nd;
       if (!allnull) { if (!nx) { lo = min(lo, hlo[X2 - 1]); hi = max(hi, hhi[X2 - 1]); } if (!no) { lo = min(lo, hlo[OE2 - 1] - 1); hi = max(hi, hhi[OE2 - 1] + 1); } if (!ni || !nd) { lo = min(lo, hlo[E2 - 1] - 1); hi = max(hi, hhi[E2 - 1] + 1); } }
-      // the window must hold this level's range and the ranges of the levels still in registers on positions 1..WR_W-2 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
+      // the window must hold this level's range and the ranges of the levels still in registers on positions 1..W-2 (the edge positions stay null: k-1 / k+1 of a live cell is always inside)
       i32 slo = allnull ? INT32_MAX : lo, shi = allnull ? INT32_MIN : hi; for (int i = 0; i < 4; i++) if (hnull[i] != 7) { slo = min(slo, hlo[i]); shi = max(shi, hhi[i]); }
       if (slo <= shi) { const i32 span = shi - slo + 1;
-        if (slo < kb + 1 || shi > kb + WR_W - 2 || (span <= 30 && shi > kb + 30)) { if (span > WR_W - 2) { overflow = true; why = -2; break; }
-          const i32 room = span <= 30 ? 30 : (span <= 62 ? 62 : (span <= 94 ? 94 : WR_W - 2)); const i32 nkb = slo - 1 - (room - span) / 2, dlt = nkb - kb;   // centred in as few slots as the span needs
+        if (slo < kb + 1 || shi > kb + W - 2 || (span <= 30 && shi > kb + 30)) { if (span > W - 2) { overflow = true; why = -2; break; }
+          const i32 room = min(W - 2, ((span + 33) >> 5) * 32 - 2); const i32 nkb = slo - 1 - (room - span) / 2, dlt = nkb - kb;   // centred in as few slots as the span needs
           const int sl = (lane + (dlt & 31)) & 31, carry = (lane + (dlt & 31)) >> 5, q = dlt >> 5;   // new position p takes old position p + dlt: old lane sl, old slot s + q + carry
-          auto shift = [&](i32 (&v)[WR_NS]) { i32 x[WR_NS];
+          auto shift = [&](i32 (&v)[NS]) { i32 x[NS];
 #pragma unroll
-            for (int t = 0; t < WR_NS; t++) x[t] = __shfl_sync(FULLMASK, v[t], sl);
+            for (int t = 0; t < NS; t++) x[t] = __shfl_sync(FULLMASK, v[t], sl);
 #pragma unroll
-            for (int s_ = 0; s_ < WR_NS; s_++) { const int src = s_ + q + carry; i32 r = -1;
+            for (int s_ = 0; s_ < NS; s_++) { const int src = s_ + q + carry; i32 r = -1;
 #pragma unroll
-              for (int t = 0; t < WR_NS; t++) if (src == t) r = x[t]; v[s_] = r; } };
+              for (int t = 0; t < NS; t++) if (src == t) r = x[t]; v[s_] = r; } };
           shift(m1); shift(m2); shift(m3); shift(m4); shift(i1); shift(d1); kb = nkb; } }
-      const int sa = (slo <= shi) ? max(0, (slo - kb) >> 5) : 0, sb = (slo <= shi) ? min(WR_NS - 1, (shi - kb) >> 5) : -1;   // slots that can hold anything but nulls
-      WrCell c[WR_NS];
+      const int sa = (slo <= shi) ? max(0, (slo - kb) >> 5) : 0, sb = (slo <= shi) ? min(NS - 1, (shi - kb) >> 5) : -1;   // slots that can hold anything but nulls
+      WrCell c[NS];
 #pragma unroll
-      for (int s_ = 0; s_ < WR_NS; s_++) { c[s_].om = c[s_].oi = c[s_].od = -1; c[s_].dv = INT32_MAX; c[s_].word = 0; }
+      for (int s_ = 0; s_ < NS; s_++) { c[s_].om = c[s_].oi = c[s_].od = -1; c[s_].dv = INT32_MAX; c[s_].word = 0; }
       if (!allnull) {   // raw neighbour values (what the backtrace of k_wfa_fast loads from its slab); positions 31|32, 63|64, 95|96 are the seams between the slots
-        i32 r4[WR_NS], ri[WR_NS], t4[WR_NS], td[WR_NS];
+        i32 r4[NS], ri[NS], t4[NS], td[NS];
 #pragma unroll
-        for (int t = 0; t < WR_NS; t++) { r4[t] = ri[t] = t4[t] = td[t] = -1; if (t >= sa && t <= sb) { r4[t] = __shfl_sync(FULLMASK, m4[t], lm1); ri[t] = __shfl_sync(FULLMASK, i1[t], lm1); t4[t] = __shfl_sync(FULLMASK, m4[t], lp1); td[t] = __shfl_sync(FULLMASK, d1[t], lp1); } }
+        for (int t = 0; t < NS; t++) { r4[t] = ri[t] = t4[t] = td[t] = -1; if (t >= sa && t <= sb) { r4[t] = __shfl_sync(FULLMASK, m4[t], lm1); ri[t] = __shfl_sync(FULLMASK, i1[t], lm1); t4[t] = __shfl_sync(FULLMASK, m4[t], lp1); td[t] = __shfl_sync(FULLMASK, d1[t], lp1); } }
 #pragma unroll
-        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ >= sa && s_ <= sb && lo <= kb + 32 * s_ + 31 && hi >= kb + 32 * s_) { const i32 k = kb + 32 * s_ + lane;
-            const i32 l4 = lane ? r4[s_] : (s_ ? r4[s_ - 1] : -1), li = lane ? ri[s_] : (s_ ? ri[s_ - 1] : -1), g4 = lane < 31 ? t4[s_] : (s_ < WR_NS - 1 ? t4[s_ + 1] : -1), gd = lane < 31 ? td[s_] : (s_ < WR_NS - 1 ? td[s_ + 1] : -1);
+        for (int s_ = 0; s_ < NS; s_++) if (s_ >= sa && s_ <= sb && lo <= kb + 32 * s_ + 31 && hi >= kb + 32 * s_) { const i32 k = kb + 32 * s_ + lane;
+            const i32 l4 = lane ? r4[s_] : (s_ ? r4[s_ - 1] : -1), li = lane ? ri[s_] : (s_ ? ri[s_ - 1] : -1), g4 = lane < 31 ? t4[s_] : (s_ < NS - 1 ? t4[s_ + 1] : -1), gd = lane < 31 ? td[s_] : (s_ < NS - 1 ? td[s_ + 1] : -1);
             c[s_] = cell(k, k >= lo && k <= hi, m2[s_], l4, li, g4, gd); } }
       bool hm = false, hi_ = false, hd = false;
 #pragma unroll
-      for (int s_ = 0; s_ < WR_NS; s_++) { hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
+      for (int s_ = 0; s_ < NS; s_++) { hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
       bool anyM = __any_sync(FULLMASK, hm), anyI = __any_sync(FULLMASK, hi_), anyD = __any_sync(FULLMASK, hd);
       if (adaptive && !allnull && anyM && hi - lo + 1 >= 10) {   // WFA-adaptive reduction, same rule as k_wfa / k_wfa_fast / the oracle
         i32 mind = INT32_MAX;
 #pragma unroll
-        for (int s_ = 0; s_ < WR_NS; s_++) mind = min(mind, c[s_].dv);
+        for (int s_ = 0; s_ < NS; s_++) mind = min(mind, c[s_].dv);
         for (int o = 16; o; o >>= 1) mind = min(mind, __shfl_xor_sync(FULLMASK, mind, o)); const i32 thr = mind + 50;   // distances of null cells are +inf
         const i32 top_limit = min(kend, hi); i32 nlo = lo; bool found = false;
 #pragma unroll
-        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k >= lo && k < top_limit); if (bal && !found) { nlo = kb + 32 * s_ + __ffs(bal) - 1; found = true; } }
+        for (int s_ = 0; s_ < NS; s_++) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k >= lo && k < top_limit); if (bal && !found) { nlo = kb + 32 * s_ + __ffs(bal) - 1; found = true; } }
         if (!found && top_limit > lo) nlo = top_limit;
         const i32 bottom_limit = max(kend, nlo); i32 nhi = hi; found = false;
 #pragma unroll
-        for (int s_ = WR_NS - 1; s_ >= 0; s_--) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k <= hi && k > bottom_limit); if (bal && !found) { nhi = kb + 32 * s_ + 31 - __clz(bal); found = true; } }
+        for (int s_ = NS - 1; s_ >= 0; s_--) if (s_ >= sa && s_ <= sb) { const i32 k = kb + 32 * s_ + lane; const u32 bal = __ballot_sync(FULLMASK, c[s_].om >= 0 && c[s_].dv <= thr && k <= hi && k > bottom_limit); if (bal && !found) { nhi = kb + 32 * s_ + 31 - __clz(bal); found = true; } }
         if (!found && hi > bottom_limit) nhi = bottom_limit;
         if (nlo != lo || nhi != hi) { hm = hi_ = hd = false;
 #pragma unroll
-          for (int s_ = 0; s_ < WR_NS; s_++) { const i32 k = kb + 32 * s_ + lane; if (k < nlo || k > nhi) { c[s_].om = -1; c[s_].oi = -1; c[s_].od = -1; } hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
+          for (int s_ = 0; s_ < NS; s_++) { const i32 k = kb + 32 * s_ + lane; if (k < nlo || k > nhi) { c[s_].om = -1; c[s_].oi = -1; c[s_].od = -1; } hm |= c[s_].om >= 0; hi_ |= c[s_].oi >= 0; hd |= c[s_].od >= 0; }
           anyM = __any_sync(FULLMASK, hm); anyI = __any_sync(FULLMASK, hi_); anyD = __any_sync(FULLMASK, hd); lo = nlo; hi = nhi; }
       }
-      { u32* row = slab + (u64)L * WR_W;
+      { u32* row = slab + (u64)L * W;
 #pragma unroll
-        for (int s_ = 0; s_ < WR_NS; s_++) if (s_ == 0 || (s_ >= sa && s_ <= sb)) row[32 * s_ + lane] = (s_ == 0 && lane == 0) ? (u32)kb : c[s_].word; }
+        for (int s_ = 0; s_ < NS; s_++) if (s_ == 0 || (s_ >= sa && s_ <= sb)) row[32 * s_ + lane] = (s_ == 0 && lane == 0) ? (u32)kb : c[s_].word; }
 #pragma unroll
-      for (int s_ = 0; s_ < WR_NS; s_++) { m4[s_] = m3[s_]; m3[s_] = m2[s_]; m2[s_] = m1[s_]; m1[s_] = c[s_].om; i1[s_] = c[s_].oi; d1[s_] = c[s_].od; }
+      for (int s_ = 0; s_ < NS; s_++) { m4[s_] = m3[s_]; m3[s_] = m2[s_]; m2[s_] = m1[s_]; m1[s_] = c[s_].om; i1[s_] = c[s_].oi; d1[s_] = c[s_].od; }
       for (int i = 3; i > 0; i--) { hlo[i] = hlo[i - 1]; hhi[i] = hhi[i - 1]; hnull[i] = hnull[i - 1]; }
       hlo[0] = allnull ? 0 : lo; hhi[0] = allnull ? -1 : hi; hnull[0] = allnull ? 7u : ((anyM ? 0u : 1u) | (anyI ? 0u : 2u) | (anyD ? 0u : 4u));
       if (!allnull && kend >= lo && kend <= hi) { const i32 v = at(m1, kend - kb); done = (v >= tlen); }
@@ -1286,16 +1328,16 @@ __global__ void __launch_bounds__(WR_WARPS * 32) k_wfa_reg(const ExtOut* __restr
   }
 }
 // backtrace of the register path, one thread per alignment: two words of one 128-byte line per step (the level's window base and the cell)
-__global__ void __launch_bounds__(128) k_wfa_bt2(const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 job0, u32 njobs, const u32* __restrict__ slabs, const u64* __restrict__ slab_off, u64* __restrict__ ops_scratch, const u64* __restrict__ ops_off, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops) {
+__global__ void __launch_bounds__(128) k_wfa_bt2(const ExtOut* __restrict__ ext, const u32* __restrict__ job_ids, u32 job0, u32 njobs, const u32* __restrict__ slabs, const u64* __restrict__ slab_off, u64* __restrict__ ops_scratch, const u64* __restrict__ ops_off, WfaOut* __restrict__ outs, u64* __restrict__ ops_pool, u64* __restrict__ ops_cursor, u64 ops_cap, int want_ops, int W) {   /* W: diagonals per level row (32 x the slots of the forward kernel) */
   u32 t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= njobs) return; u32 jb = job_ids ? job_ids[job0 + t] : job0 + t; WfaOut Rr = outs[jb]; if (Rr.status != 0) return;
-  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32* slab = slabs + slab_off[t] * WR_W; u64* ops = ops_scratch + (want_ops ? ops_off[t] : 0); const u32 ops_max = want_ops ? (u32)(ops_off[t + 1] - ops_off[t]) : 0;
+  ExtOut ex = ext[jb]; const i32 plen = ex.qe - ex.qs, tlen = ex.te - ex.ts, kend = tlen - plen; const u32* slab = slabs + slab_off[t] * W; u64* ops = ops_scratch + (want_ops ? ops_off[t] : 0); const u32 ops_max = want_ops ? (u32)(ops_off[t + 1] - ops_off[t]) : 0;
   i32 k = kend, off = tlen, lv = Rr.wscore / 2; int mat = 0; i32 vv = off - k, h = off; u32 nops = 0; bool ops_over = false; int cur = 0; u32 curn = 0; i32 p_alen = 0, p_gaps = 0, p_bs = 0; int prev = 0;
   auto flush = [&]() { if (want_ops && curn) { if (nops < ops_max) ops[nops++] = ((u64)cur << 32) | curn; else ops_over = true; } curn = 0; };
   auto put = [&](int op, i32 cntp, i32 vend, i32 hend) { if (cntp <= 0) return; if (op != cur) { flush(); cur = op; } curn += (u32)cntp;
     if (op == 'M') { if (Rr.has_m) { Rr.alen += p_alen; Rr.gaps += p_gaps; Rr.bscore += p_bs; } else { Rr.has_m = 1; Rr.qend = vend; Rr.tend = hend; } p_alen = p_gaps = p_bs = 0; Rr.alen += cntp; Rr.matches += cntp; Rr.bscore += 2 * cntp; Rr.qbegin = vend - cntp + 1; Rr.tbegin = hend - cntp + 1; }
     else if (op == 'X') { p_alen += cntp; p_bs -= 3 * cntp; } else { p_alen += cntp; p_gaps += cntp; p_bs -= 2 * cntp; if (prev != op) p_bs -= 5; } prev = op; };
   while (vv > 0 && h > 0 && lv > 0) {
-    const u32* row = slab + (u64)lv * WR_W; const i32 kb = (i32)row[0]; const u32 li = (u32)(k - kb); if (li - 1u > (u32)(WR_W - 3)) { Rr.status = 2; break; } const u32 cell = row[li]; int type;
+    const u32* row = slab + (u64)lv * W; const i32 kb = (i32)row[0]; const u32 li = (u32)(k - kb); if (li - 1u > (u32)(W - 3)) { Rr.status = 2; break; } const u32 cell = row[li]; int type;
     if (mat == 0) { type = (int)((cell >> 20) & 15); if (type == 0) { Rr.status = 2; break; } const i32 mo = (i32)(cell & 0xFFFFF); put('M', off - mo, off - k, off); off = mo; vv = off - k; h = off; if (vv <= 0 || h <= 0) continue; }
     else if (mat == 1) { if ((cell >> 26) & 1) { Rr.status = 2; break; } type = ((cell >> 24) & 1) ? 2 : 1; }
     else { if ((cell >> 27) & 1) { Rr.status = 2; break; } type = ((cell >> 25) & 1) ? 6 : 5; }
@@ -1319,8 +1361,9 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
     wfa_raise_smem_limit();
     DBuf<WfaOut> d_out(nj, st); std::vector<u32> ids; hw.resize(nj);
     u64 ops_cap = 0; if (want_ops) { for (u32 j = 0; j < nj; j++) ops_cap += (u64)(hext[j].qe - hext[j].qs) + (hext[j].te - hext[j].ts) + 4; } DBuf<u64> ops_pool(ops_cap + 2, st); DBuf<u64> ops_cur(1, st); ops_cur.zero();
+    DBuf<u64> woff, words; DBuf<u32> hasamb;   /* packed sequences of every job (k_wfa_prep): all four WFA kernels read them */
     { std::vector<u64> hwoff(2 * (u64)nj + 1, 0); for (u32 j = 0; j < nj; j++) { u64 nqw = (u64)((hext[j].qe - hext[j].qs + 31) / 32 + 2), ntw = (u64)((hext[j].te - hext[j].ts + 31) / 32 + 2); hwoff[2 * j + 1] = hwoff[2 * j] + 2 * nqw; hwoff[2 * j + 2] = hwoff[2 * j + 1] + ntw; }
-      DBuf<u64> woff(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); DBuf<u64> words(hwoff.back() + 4, st); DBuf<u32> hasamb(nj + 1, st);
+      woff.alloc(hwoff.size(), st); woff.from_host(hwoff.data(), hwoff.size()); words.alloc(hwoff.back() + 4, st); hasamb.alloc(nj + 1, st);
       if (g_lap) (*g_lap)("wfa host prep"); { KTimer kt(st, &ms[10]); k_wfa_prep<<<nj, 64, 0, st>>>(d_jobs.p, d_ext.p, nj, woff.p, qpacked, qamask, qboff, g2bit, g_off, words.p, hasamb.p); KERNEL_CHECK(); }
       // Levels per slab follow the longest sequence of the batch (score <= 1.6 x length covers ~40 % divergence; deeper ones use k_wfa).
       i32 maxlen = 1; for (u32 j = 0; j < nj; j++) maxlen = std::max(maxlen, std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts));
@@ -1333,25 +1376,35 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       if (use_reg) {   // per-job slabs: levels for ~40 % divergence of THIS alignment (0.8 x its longer side), op runs up to its length; rounds fill the HBM budget
         auto lv_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return (u64)std::max<i64>(256, ((i64)(0.8 * (double)len) + 63) / 64 * 64); };
         auto op_cap = [&](u32 j) { const i64 len = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); return want_ops ? (u64)std::max<i64>(1024, len + 64) : 0ull; };
-        std::vector<u64> hso, hoo; std::vector<u32> skipped; u32 rounds = 0, round_max = 0;
-        // longest alignments first: the persistent warps pull jobs in this order, so the expensive ones start early and the tail of a launch is made of short ones
-        std::vector<u32> order(nj); std::iota(order.begin(), order.end(), 0u); { std::vector<i32> len(nj); for (u32 j = 0; j < nj; j++) len[j] = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts); std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return len[a] > len[b]; }); }
-        DBuf<u32> d_order(nj, st); d_order.from_host(order.data(), nj);
-        { KTimer kt(st, &ms[11]);
-          for (u32 j0 = 0; j0 < nj;) { hso.assign(1, 0); hoo.assign(1, 0); u64 bytes = 0; u32 n = 0;
-            while (j0 + n < nj) { const u32 jid = order[j0 + n]; const u64 lv = lv_cap(jid), oc = op_cap(jid), b = lv * WR_W * 4 + oc * 8; if (n > 0 && (bytes + b > budgetF || (g_arena == nullptr && n >= 8192))) break; if (n == 0 && b > budgetF) { skipped.push_back(jid); j0++; continue; } hso.push_back(hso.back() + lv); hoo.push_back(hoo.back() + oc); bytes += b; n++; }
+        std::vector<u32> skipped; u32 round_max = 0; std::vector<i32> len(nj); for (u32 j = 0; j < nj; j++) len[j] = std::max(hext[j].qe - hext[j].qs, hext[j].te - hext[j].ts);
+        // one pass of the register kernel over the jobs `ord` with NS slots per lane (window of 32 x NS diagonals, 128 x NS bytes of backtrace words per level); rounds fill the HBM budget
+        auto run_reg = [&](const std::vector<u32>& ord, int NS, std::vector<u32>& skip) { const u32 cnt = (u32)ord.size(); const u64 W = 32ull * (u64)NS; std::vector<u64> hso, hoo; DBuf<u32> d_order(cnt, st); d_order.from_host(ord.data(), cnt);
+          KTimer kt(st, &ms[11]);
+          for (u32 j0 = 0; j0 < cnt;) { hso.assign(1, 0); hoo.assign(1, 0); u64 bytes = 0; u32 n = 0;
+            while (j0 + n < cnt) { const u32 jid = ord[j0 + n]; const u64 lv = lv_cap(jid), oc = op_cap(jid), b = lv * W * 4 + oc * 8; if (n > 0 && (bytes + b > budgetF || (g_arena == nullptr && n >= 8192))) break; if (n == 0 && b > budgetF) { skip.push_back(jid); j0++; continue; } hso.push_back(hso.back() + lv); hoo.push_back(hoo.back() + oc); bytes += b; n++; }
             if (n == 0) continue;
-            DBuf<u64> soff(n + 1, st), ooff(n + 1, st); soff.from_host(hso.data(), n + 1); ooff.from_host(hoo.data(), n + 1); DBuf<u32> rslabs(hso.back() * WR_W + 64, st); DBuf<u64> oscr(hoo.back() + 8, st); DBuf<u32> next(1, st); next.zero();
+            DBuf<u64> soff(n + 1, st), ooff(n + 1, st); soff.from_host(hso.data(), n + 1); ooff.from_host(hoo.data(), n + 1); DBuf<u32> rslabs(hso.back() * W + 64, st); DBuf<u64> oscr(hoo.back() + 8, st); DBuf<u32> next(1, st); next.zero();
             const u32 blocks = (u32)std::min<u64>((u64)sm_count * 8, (n + WR_WARPS - 1) / WR_WARPS);
-            k_wfa_reg<<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, d_order.p, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive); KERNEL_CHECK();
-            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, d_order.p, j0, n, rslabs.p, soff.p, oscr.p, ooff.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops); KERNEL_CHECK();
+            if (NS == 4) k_wfa_reg<4><<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, d_order.p, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive);
+            else k_wfa_reg<8><<<blocks, WR_WARPS * 32, WR_SMEM_BYTES, st>>>(d_ext.p, woff.p, words.p, hasamb.p, d_order.p, j0, n, next.p, rslabs.p, soff.p, d_out.p, adaptive);
+            KERNEL_CHECK();
+            k_wfa_bt2<<<cdiv(n, 128), 128, 0, st>>>(d_ext.p, d_order.p, j0, n, rslabs.p, soff.p, oscr.p, ooff.p, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, (int)W); KERNEL_CHECK();
             CUDA_CHECK(cudaStreamSynchronize(st));   // the round's buffers go back to the arena
-            j0 += n; rounds++; round_max = std::max(round_max, n); } }
+            j0 += n; round_max = std::max(round_max, n); } };
+        // longest alignments first: the persistent warps pull jobs in this order, so the expensive ones start early and the tail of a launch is made of short ones
+        std::vector<u32> order(nj); std::iota(order.begin(), order.end(), 0u); std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return len[a] > len[b]; });
+        run_reg(order, 4, skipped);
         std::vector<WfaOut> o = d_out.to_host(nj); std::vector<char> sk(nj, 0); for (u32 j : skipped) sk[j] = 1;
-        u32 why[5] = {0, 0, 0, 0, 0};
-        for (u32 j = 0; j < nj; j++) { if (sk[j] || o[j].status == 1) { rest.push_back(j); why[sk[j] ? 4 : (o[j].wscore == -1 ? 1 : o[j].wscore == -2 ? 2 : o[j].wscore == -3 ? 3 : 0)]++; } else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
-        if (g_lap && g_lap->on && !rest.empty()) fprintf(stderr, "[lmg host] register WFA pass: %zu of %u alignments left (op scratch %u, level capacity %u, band > %d diagonals %u, not eligible %u, slab over budget %u)\n", rest.size(), nj, why[0], why[1], WR_W - 2, why[2], why[3], why[4]);
-        counters[14] = round_max; (void)rounds; if (g_lap) (*g_lap)("wfa register pass"); }
+        u32 why[5] = {0, 0, 0, 0, 0}; std::vector<u32> wide;   // wide: the band left the 128-diagonal window
+        for (u32 j = 0; j < nj; j++) { if (sk[j] || o[j].status == 1) { const int w = sk[j] ? 4 : (o[j].wscore == -1 ? 1 : o[j].wscore == -2 ? 2 : o[j].wscore == -3 ? 3 : 0); why[w]++; if (w == 2) wide.push_back(j); else rest.push_back(j); } else if (o[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel)"); else hw[j] = o[j]; }
+        if (g_lap && g_lap->on && (!rest.empty() || !wide.empty())) fprintf(stderr, "[lmg host] register WFA pass: %zu of %u alignments left (op scratch %u, level capacity %u, band > %d diagonals %u, not eligible %u, slab over budget %u)\n", rest.size() + wide.size(), nj, why[0], why[1], 32 * 4 - 2, why[2], why[3], why[4]);
+        // pass 1b, wide bands (long, indel-rich alignments: ONT reads against the less similar genomes): the same kernel with 8 slots per lane = a 256-diagonal window
+        static const bool use_reg8 = getenv("LMG_NO_WFA_REG8") == nullptr;
+        if (!wide.empty() && use_reg8) { std::stable_sort(wide.begin(), wide.end(), [&](u32 a, u32 b) { return len[a] > len[b]; }); std::vector<u32> sk8; run_reg(wide, 8, sk8); std::vector<WfaOut> o8 = d_out.to_host(nj); std::vector<char> s8(nj, 0); for (u32 j : sk8) s8[j] = 1; u32 left = 0;
+          for (u32 j : wide) { if (s8[j] || o8[j].status == 1) { rest.push_back(j); left++; } else if (o8[j].status != 0) throw std::runtime_error("WFA backtrace failed (register kernel, wide window)"); else hw[j] = o8[j]; }
+          if (g_lap && g_lap->on) fprintf(stderr, "[lmg host] register WFA pass, 256-diagonal window: %u of %zu alignments left\n", left, wide.size()); }
+        else rest.insert(rest.end(), wide.begin(), wide.end());
+        counters[14] = round_max; if (g_lap) (*g_lap)("wfa register pass"); }
       else { rest.resize(nj); std::iota(rest.begin(), rest.end(), 0u); }
       counters[9] = nj; counters[10] = rest.size(); counters[15] = (u64)lmax;
       // pass 2, the jobs left: shared-memory-ring kernel (bands up to 256 diagonals), per-alignment slabs of 3 x u16 per cell in rounds bounded by the HBM budget
@@ -1371,7 +1424,7 @@ static void wfa_run_all(cudaStream_t st, int sm_count, DBuf<HspJob>& d_jobs, DBu
       u32 n = (u32)ids.size(); u32 warps = (u32)std::min<u64>(std::min<u64>((u64)sm_count * 32, n), std::max<u64>(1, budget / (slab_words * 4))); warps = std::max(1u, (warps / 4) * 4); if (warps < 4) warps = 4;
       if ((u64)warps * slab_words * 4 > budget) throw std::runtime_error("WFA workspace does not fit in HBM for an alignment in this batch");
       DBuf<i32> slabs((u64)warps * slab_words, st); DBuf<u32> d_ids(n, st); d_ids.from_host(ids.data(), n); DBuf<u32> next(1, st); next.zero();
-      { KTimer kt(st, &ms[10]); k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); } counters[11] += n;
+      { KTimer kt(st, &ms[10]); k_wfa<<<warps / 4, 128, 0, st>>>(d_jobs.p, d_ext.p, d_ids.p, n, next.p, woff.p, words.p, hasamb.p, qpacked, qamask, qboff, g2bit, g_off, slabs.p, slab_words, d_out.p, ops_pool.p, ops_cur.p, ops_cap, want_ops, adaptive); KERNEL_CHECK(); } counters[11] += n;
       std::vector<WfaOut> o = d_out.to_host(nj); std::vector<u32> again; for (u32 id : ids) { if (o[id].status == 1) again.push_back(id); else if (o[id].status != 0) throw std::runtime_error("WFA backtrace failed"); else hw[id] = o[id]; }
       ids.swap(again); slab_words *= 8;
     }
@@ -1602,6 +1655,7 @@ static lmg_index* make_ctx(Image* im, bool owner, int device) {
   { int lo_p = 0, hi_p = 0; CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p)); CUDA_CHECK(cudaStreamCreateWithPriority(&ix->st_hi, cudaStreamNonBlocking, hi_p)); CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_hi[0], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_hi[1], cudaEventDisableTiming)); }
   cudaDeviceProp pr; CUDA_CHECK(cudaGetDeviceProperties(&pr, device)); ix->sm_count = pr.multiProcessorCount; ix->smem_optin = (u32)pr.sharedMemPerBlockOptin; if (pr.major < 9) ix->use_tma = 0;
   if (getenv("LMG_NO_TMA")) ix->use_tma = 0; ix->total_mem = pr.totalGlobalMem;
+  if (const char* e = getenv("LMG_L2_FETCH")) { const int g = atoi(e); if (g == 32 || g == 64 || g == 128) CUDA_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g)); }   /* experiment: DRAM bytes fetched per missing 32-byte sector (a device-wide hint) */
   // dynamic shared memory ceilings are per function and device-global: raise them once to the opt-in limit so concurrent lanes never race on them
   auto raise = [&](const void* f) { cudaFuncAttributes fa; CUDA_CHECK(cudaFuncGetAttributes(&fa, f)); CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin - fa.sharedSizeBytes))); };
   if (owner) { raise((const void*)k_capture); raise((const void*)k_capture2<true>); raise((const void*)k_capture2<false>); raise((const void*)k_pa_anchors2); raise((const void*)k_pa_anchors3<256>); raise((const void*)k_pa_anchors3<1024>); raise((const void*)k_pa_sort<4096, 512>); }
@@ -1744,12 +1798,13 @@ int lmg_index_synth(int device, int32_t masks, uint64_t per_mask, uint64_t seed,
 int lmg_probe_bench(lmg_index* ix, uint64_t n_queries, uint64_t seed, int32_t min_prefix, int32_t iters, double* out16) {
   try { std::lock_guard<std::mutex> lk(ix->mu); const Image& I = ix->img; if (!I.synth_per) throw std::runtime_error("lmg_probe_bench needs an index made by lmg_index_synth"); CUDA_CHECK(cudaSetDevice(I.device)); cudaStream_t st = ix->st;
     if (n_queries == 0 || n_queries >= (1ull << 31)) throw std::runtime_error("lmg_probe_bench: 1 <= n_queries < 2^31"); ProbeParams P = probe_params(I, min_prefix); for (int i = 0; i < 16; i++) out16[i] = 0;
-    DBuf<Surv> surv(2 * n_queries + 64, st); DBuf<u32> nsv(1, st), nh(1, st); DBuf<u64> dstats(8, st); nsv.zero(); dstats.zero(); cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    DBuf<Surv> surv(2 * n_queries + 64, st); DBuf<u32> nsv(1, st), nh(1, st), bcnt0((u64)I.m + 1, st); DBuf<u64> dstats(8, st); nsv.zero(); dstats.zero(); bcnt0.zero(); P.bcnt = bcnt0.p; cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st); k_c5_gen<<<cdiv((i64)n_queries, 256), 256, 0, st>>>(P, I.d_masks, I.d_mask_pstart, I.mask_pbits, I.synth_per, I.synth_seed, seed, n_queries, I.mask_lo, I.mask_hi, surv.p, nsv.p, (u32)(2 * n_queries), dstats.p); KERNEL_CHECK(); cudaEventRecord(e1, st);
-    const u32 ns = nsv.to_host()[0]; float fg = 0; cudaEventElapsedTime(&fg, e0, e1); out16[0] = (double)dstats.to_host()[0]; out16[1] = (double)ns; out16[9] = fg; DBuf<ProbeHit> hits((u64)ns + 64, st); double tsum = 0, tmin = 1e30;
-    for (int it = -1; it < iters && ns; it++) { nh.zero(); cudaEventRecord(e0, st); k_probe_find2<false><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, ns, nullptr); KERNEL_CHECK(); cudaEventRecord(e1, st); CUDA_CHECK(cudaEventSynchronize(e1)); float f = 0; cudaEventElapsedTime(&f, e0, e1); if (it >= 0) { tsum += f; tmin = std::min(tmin, (double)f); } }
-    out16[2] = iters > 0 ? tsum / iters : 0; out16[10] = tmin < 1e29 ? tmin : 0; out16[3] = (double)nh.to_host()[0];
-    if (ns) { nh.zero(); dstats.zero(); k_probe_find2<true><<<cdiv(ns, 256), 256, 0, st>>>(P, surv.p, ns, hits.p, nh.p, ns, dstats.p); KERNEL_CHECK(); auto sd = dstats.to_host(); out16[4] = (double)sd[4]; out16[5] = (double)sd[5]; out16[6] = (double)sd[6]; out16[7] = (double)sd[2]; out16[8] = (double)sd[3]; }
+    const u32 ns = nsv.to_host()[0]; float fg = 0; cudaEventElapsedTime(&fg, e0, e1); out16[0] = (double)dstats.to_host()[0]; out16[1] = (double)ns; out16[9] = fg; DBuf<ProbeHit> hits((u64)ns + 64, st); double tsum = 0, tmin = 1e30, rsum = 0; DBuf<Surv> grouped((u64)ns + 64, st); DBuf<u32> bcnt((u64)I.m + 1, st); const Surv* sp = surv.p; cudaEvent_t er; cudaEventCreate(&er);
+    for (int it = -1; it < iters && ns; it++) { nh.zero(); cudaEventRecord(er, st); CUDA_CHECK(cudaMemcpyAsync(bcnt.p, bcnt0.p, ((size_t)I.m + 1) * 4, cudaMemcpyDeviceToDevice, st)); if (regroup_survivors(st, surv.p, ns, I.m, grouped.p, bcnt.p, true)) sp = grouped.p;   /* the regrouping pass is part of every lookup: timed next to the kernel ([11]) */
+      cudaEventRecord(e0, st); k_probe_find2<false><<<cdiv(ns, 256), 256, 0, st>>>(P, sp, ns, hits.p, nh.p, ns, nullptr); KERNEL_CHECK(); cudaEventRecord(e1, st); CUDA_CHECK(cudaEventSynchronize(e1)); float f = 0, fr = 0; cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&fr, er, e0); if (it >= 0) { tsum += f; rsum += fr; tmin = std::min(tmin, (double)f); } }
+    out16[2] = iters > 0 ? tsum / iters : 0; out16[11] = iters > 0 ? rsum / iters : 0; out16[10] = tmin < 1e29 ? tmin : 0; out16[3] = (double)nh.to_host()[0]; cudaEventDestroy(er);
+    if (ns) { nh.zero(); dstats.zero(); k_probe_find2<true><<<cdiv(ns, 256), 256, 0, st>>>(P, sp, ns, hits.p, nh.p, ns, dstats.p); KERNEL_CHECK(); auto sd = dstats.to_host(); out16[4] = (double)sd[4]; out16[5] = (double)sd[5]; out16[6] = (double)sd[6]; out16[7] = (double)sd[2]; out16[8] = (double)sd[3]; }
     cudaEventDestroy(e0); cudaEventDestroy(e1); CUDA_CHECK(cudaStreamSynchronize(st)); return 0; } catch (std::exception& e) { g_err = e.what(); cudaGetLastError(); return -1; }
 }
 

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(128) k_anchor_compact(const u32* __restrict__ 
     if (w < nw) { const u32 before = s_cnt[threadIdx.x]; cum[w0 + w] = (u16)before; u32 r = 0; const u32 base = cbase[mask0 + b]; u32 vv = v; while (vv) { const int i = __ffs(vv) - 1; vv &= vv - 1; cstart[base + before + r] = F[w * 32 + i]; r++; } } __syncthreads(); }
   (void)bad;
 }
+__global__ void k_cstart_narrow(const u32* __restrict__ in, u16* __restrict__ out, u64 n) { const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (i < n) out[i] = (u16)in[i]; }
 __global__ void k_anchor_count(const u32* __restrict__ full, int nm, u32 NA, u32* __restrict__ counts) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= nm) return; const u32* F = full + (u64)b * NA; u32 c = 0; for (u32 i = 0; i < NA; i++) c += F[i] != 0xFFFFFFFFu; counts[b] = c; }
 __global__ void k_anchor_verify(const u32* __restrict__ bits, const u32* __restrict__ cbase, int m, u32 nw, u32* __restrict__ bad) { const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= m) return; u32 c = 0; for (u32 w = 0; w < nw; w++) c += __popc(bits[(u64)b * nw + w]); if (c != cbase[b + 1] - cbase[b]) atomicAdd(bad, 1u); }
 
@@ -104,6 +105,7 @@ struct Image {
   // device arrays
   u64 *d_masks = nullptr, *d_bucket_off = nullptr, *d_bucket_voff = nullptr, *d_vals = nullptr; SeedEntry* d_entries = nullptr;
   u32 *d_anchor_cbase = nullptr, *d_anchor_cstart = nullptr; u16* d_anchor_cum = nullptr; u64 n_anchors = 0;   // compact anchor table (k_anchor_compact)
+  u16* d_anchor_cstart16 = nullptr;   // the starts as u16 when every bucket holds < 65,536 keys (halves the table the lookup kernel wants in L2); d_anchor_cstart is released then
   u32* d_pbloom = nullptr; u32 pbmask = 0;   // prefix Bloom filter (pb_hash): pbmask + 1 bits, a power of two >= 8 bits per stored k-mer (<= 2^32)
   u32* d_anchor_bits = nullptr;   // m * NA/32 words: bit a of mask i set iff anchor_start[i][a] is present (10 MB, L2-resident filter in front of the 328 MB table)
   u32* d_mask_pstart = nullptr; int mask_pbits = 14;   // masks bucketed by their mask_prefix leading bases: [pstart[p], pstart[p+1])
@@ -125,6 +127,10 @@ struct Image {
   // compact anchor arrays from per-bucket counts (host): allocations + prefix sums; the chunks are compacted afterwards
   void alloc_anchors(const std::vector<u32>& counts) { if (NA < 32) lmi::die("indexes with fewer than 64 partitions are not supported by the GPU path"); std::vector<u32> cb(m + 1, 0); for (int j = 0; j < m; j++) cb[j + 1] = cb[j] + counts[j]; n_anchors = cb[m];
     d_anchor_cbase = up(cb); d_anchor_cstart = dalloc<u32>(n_anchors); const u64 nwords = (u64)m * (NA >> 5); d_anchor_bits = dalloc<u32>(nwords); d_anchor_cum = dalloc<u16>(nwords); CUDA_CHECK(cudaMemset(d_anchor_bits, 0, nwords * 4)); CUDA_CHECK(cudaMemset(d_anchor_cum, 0, nwords * 2)); }
+  // starts are bucket-relative key indexes: 16 bits are enough unless a bucket holds 65,536 keys or more (LMG_CSTART32 keeps the wide table)
+  void pack_cstart16(const std::vector<u64>& bucket_off) { u64 mx = 0; for (int j = 0; j < m; j++) mx = std::max(mx, bucket_off[j + 1] - bucket_off[j]); if (mx >= 65536 || n_anchors == 0 || getenv("LMG_CSTART32")) return;
+    u16* d16 = nullptr; CUDA_CHECK(cudaMalloc((void**)&d16, n_anchors * 2 + 64)); k_cstart_narrow<<<(unsigned)((n_anchors + 255) / 256), 256>>>(d_anchor_cstart, d16, n_anchors); CUDA_CHECK(cudaGetLastError()); CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaFree(d_anchor_cstart)); d_anchor_cstart = nullptr; d_anchor_cstart16 = d16; bytes -= n_anchors * 2; }
   void verify_anchors() { u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); k_anchor_verify<<<(m + 127) / 128, 128>>>(d_anchor_bits, d_anchor_cbase, m, (u32)(NA >> 5), d_bad); CUDA_CHECK(cudaGetLastError()); u32 bad = 0; CUDA_CHECK(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad);
     if (bad) lmi::die("kv-index: the anchor records of " + std::to_string(bad) + " masks are inconsistent (duplicate or missing anchors)"); }
 
@@ -190,7 +196,7 @@ struct Image {
       CUDA_CHECK(cudaDeviceSynchronize()); free_chunk(cd); }
     if (d_full) cudaFree(d_full); (void)max_nm;
     u32 bad = 0; CUDA_CHECK(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost)); cudaFree(d_bad); if (bad) lmi::die("kv-index: " + std::to_string(bad) + " anchor records do not name a stored k-mer");
-    finish_masks(); verify_anchors(); load_ms[2] = ms_since(t0); load_ms[3] = ms_since(t_all);
+    finish_masks(); verify_anchors(); pack_cstart16(bucket_off); load_ms[2] = ms_since(t0); load_ms[3] = ms_since(t_all);
   }
 
   // Synthetic seeds-only image for the seed-lookup microbenchmark: masks [lo, hi) of an m-mask index, `per` keys each (no genomes: only the probe kernels may run on it)
@@ -209,8 +215,8 @@ struct Image {
       u32* d_cnt = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_cnt, (size_t)nm * 4)); k_anchor_count<<<(nm + 127) / 128, 128>>>(d_full, nm, (u32)NA, d_cnt); CUDA_CHECK(cudaGetLastError()); std::vector<u32> counts(m, 0); CUDA_CHECK(cudaMemcpy(counts.data() + lo, d_cnt, (size_t)nm * 4, cudaMemcpyDeviceToHost)); cudaFree(d_cnt);
       alloc_anchors(counts); u32* d_bad = nullptr; CUDA_CHECK(cudaMalloc((void**)&d_bad, 4)); CUDA_CHECK(cudaMemset(d_bad, 0, 4)); k_anchor_compact<<<nm, 128>>>(d_full, nm, lo, (u32)NA, d_anchor_cbase, d_anchor_bits, d_anchor_cum, d_anchor_cstart, d_bad); CUDA_CHECK(cudaGetLastError()); CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(d_full); cudaFree(d_bad); }
     else alloc_anchors(std::vector<u32>(m, 0));
-    verify_anchors();
+    verify_anchors(); pack_cstart16(bucket_off);
     batch_base.assign(2, 0); d_batch_base = up(batch_base); std::vector<u64> one(2, 0); d_g_off = up(one); d_g2bit = dalloc<u8>(64);
   }
-  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_cbase, (void*)d_anchor_cstart, (void*)d_anchor_cum, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits, (void*)d_pbloom}) if (p) cudaFree(p); }
+  void release() { for (void* p : {(void*)d_masks, (void*)d_bucket_off, (void*)d_bucket_voff, (void*)d_entries, (void*)d_vals, (void*)d_anchor_cbase, (void*)d_anchor_cstart, (void*)d_anchor_cstart16, (void*)d_anchor_cum, (void*)d_g2bit, (void*)d_g_off, (void*)d_g_nbases, (void*)d_g_seq_off, (void*)d_seq_sizes, (void*)d_batch_base, (void*)d_mask_pstart, (void*)d_anchor_bits, (void*)d_pbloom}) if (p) cudaFree(p); }
 };
