@@ -466,7 +466,7 @@ def run_search(a, rank, world, local):
                                     "frac_alone_with_regroup": (alg_bytes / (t_iso + rg_iso_ms * 1e-3) / 1e9 / peak) if t_iso > 0 else 0.0},
                         "alone": {"kernel_ms": t_iso * 1e3, "achieved": alg_bytes / t_iso / 1e9 if t_iso > 0 else 0.0, "frac": (alg_bytes / t_iso / 1e9 / peak) if t_iso > 0 else 0.0, "note": "same batch through one lane: no concurrent kernels"},
                         "r01_model": {"note": "round 1's byte model (24+32 B per probe, 32 B per search step taken, 16 B per entry scanned, 48 B per hit): kept for continuity with BENCH_r01", "algorithmic_bytes_per_step": r01_bytes, "frac": (r01_bytes / t_probe / 1e9 / peak) if t_probe > 0 else 0.0},
-                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): this, not the streaming peak, bounds a lookup whose accesses are dependent random sectors",
+                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): the rate a lookup with scattered probes is held to; with the probes regrouped by bucket most sectors hit in L2 and the kernel is not bound by it",
                                                   "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak, "kernel_alone_vs_ceiling": (alg_bytes / t_iso / 1e9 / gb["gbs_at_32B"]) if t_iso > 0 else 0.0, "kernel_in_region_vs_ceiling": achieved / gb["gbs_at_32B"]},
                         "peak_source": peak_src},
            "roofline_wfa": {"bound": "issue", "kernel": "k_wfa_fast + k_wfa_bt (wavefront alignment: forward pass and backtrace)", "kernel_ms_per_step": wfa_ms, "alignments_per_step": int(kcnt[9]), "share_of_kernel_time": None,
@@ -541,7 +541,7 @@ def run_c5(a, rank, world, local):
            "gpu_launches": 4 * (a.steps + a.warmup + 1) + 2, "probes_issued": issued, "probes_with_anchor": surv, "hit_records": hits,
            "roofline": {"bound": "hbm", "kernel": "k_probe_find2", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak, "traffic": None, "model": "SURVEY.md §8d per-probe bytes, per GPU (max kernel time over ranks)",
                         "algorithmic_bytes_per_step": alg, "bytes_per_probe": alg / max(surv, 1), "kernel_ms_per_step": kms, "kernel_ms_best": kbest, "regroup_ms_per_step": rms, "frac_with_regroup": alg / world / (step_ms * 1e-3) / 1e9 / peak, "mean_log2_steps": slog / max(surv, 1), "peak_source": peak_src,
-                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): a lookup made of dependent random sectors is bound by this (DRAM row activations), not by the streaming peak",
+                        "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): buckets of this index are MBs, so a probe's sectors still miss in L2 after the regrouping (which helps through the TLB)",
                                                   "sectors_per_s": gb["sectors_per_s"], "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak}},
            "e2e": {"value": surv / (step_ms * 1e-3), "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "device-resident microbenchmark: probes are generated on the GPU; the end-to-end numbers are the search configs'"},
            "cpu_baseline": None, "clocks": sampler.summary()}
