@@ -469,7 +469,7 @@ def run_search(a, rank, world, local):
                         "random_sector_ceiling": {"note": "measured rate of independent random 32-byte-sector reads over an 8-GB buffer (k_gather_bench): the rate a lookup with scattered probes is held to; with the probes regrouped by bucket most sectors hit in L2 and the kernel is not bound by it",
                                                   "gbs_at_32B": gb["gbs_at_32B"], "frac_of_streaming_peak": gb["gbs_at_32B"] / peak, "kernel_alone_vs_ceiling": (alg_bytes / t_iso / 1e9 / gb["gbs_at_32B"]) if t_iso > 0 else 0.0, "kernel_in_region_vs_ceiling": achieved / gb["gbs_at_32B"]},
                         "peak_source": peak_src},
-           "roofline_wfa": {"bound": "issue", "kernel": "k_wfa_fast + k_wfa_bt (wavefront alignment: forward pass and backtrace)", "kernel_ms_per_step": wfa_ms, "alignments_per_step": int(kcnt[9]), "share_of_kernel_time": None,
+           "roofline_wfa": {"bound": "issue", "kernel": "k_wfa_reg<4>/<8> + k_wfa_bt2, then k_wfa_fast + k_wfa_bt for what is left (wavefront alignment: forward pass and backtrace)", "kernel_ms_per_step": wfa_ms, "alignments_per_step": int(kcnt[9]), "share_of_kernel_time": None,
                             "note": "instruction-issue bound (ncu: issue-active ~78 %, DRAM < 15 % of peak); see profiles/ for the ncu capture"},
            "cpu_baseline": dict({"value": cpu_bps, "unit": "bp/s", "kind": "port", "sample": cpu_note}, **cpu_desc(threads)),
            "debug": {"lanes_used": config_lanes, "staged_call_wall_ms": float(np.mean(wall_ms)), "e2e_call_wall_ms_in_lib": float(np.mean(e2e_lib_ms)), "e2e_stage_ms": [float(x) / a.steps for x in e2e_stage],
